@@ -1,0 +1,1272 @@
+// niq_api.cu -- the C ABI (include/niq.h): contexts, MLP packing, and the host-side drivers of the queries.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared -Xcompiler -fPIC
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/niq.h"
+#include "niq_grow.cuh"
+#include "niq_kernels.cuh"
+
+using namespace niq;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                    \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(e_ == cudaErrorMemoryAllocation ? NIQ_ENOMEM : NIQ_ECUDA, "%s failed: %s (%s:%d)", #expr, \
+                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
+    } while (0)
+#define TRY(expr)            \
+    do {                     \
+        int r_ = (expr);     \
+        if (r_ != NIQ_OK) return r_; \
+    } while (0)
+
+extern "C" const char* niq_last_error(void) { return g_last_error.c_str(); }
+extern "C" const char* niq_version(void) { return "niq-b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct TimedLaunch { cudaEvent_t a, b; int family; };
+
+struct niq_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    long long launches = 0;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    bool timing = false;
+    std::vector<TimedLaunch> pending;
+    std::vector<cudaEvent_t> event_pool;
+    double fam_ms[2] = {0, 0};
+    long long fam_launches[2] = {0, 0};
+    long long* pinned = nullptr;     // small pinned read-back area (64 x int64)
+};
+
+struct DevBuf {   // stream-ordered temporary
+    niq_ctx* ctx; void* p = nullptr;
+    explicit DevBuf(niq_ctx* c) : ctx(c) {}
+    int alloc(size_t bytes) {
+        if (bytes == 0) bytes = 16;
+        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
+        if (e != cudaSuccess) { p = nullptr; return fail(NIQ_ENOMEM, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
+        return NIQ_OK;
+    }
+    ~DevBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
+    template <class T> T* as() { return reinterpret_cast<T*>(p); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+static cudaEvent_t get_event(niq_ctx* c) {
+    if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+struct LaunchTimer {   // brackets one kernel launch with events when timing is on
+    niq_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr;
+    LaunchTimer(niq_ctx* ctx, int family) : c(ctx), fam(family) {
+        c->launches++;
+        if (c->timing && c->pending.size() < 8192) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
+    }
+    ~LaunchTimer() {
+        if (a) { cudaEventRecord(b, c->stream); c->pending.push_back({a, b, fam}); }
+    }
+};
+static void resolve_timers(niq_ctx* c) {
+    for (auto& t : c->pending) {
+        float ms = 0.f;
+        if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
+            c->fam_ms[t.family] += ms;
+            c->fam_launches[t.family] += 1;
+        }
+        c->event_pool.push_back(t.a);
+        c->event_pool.push_back(t.b);
+    }
+    c->pending.clear();
+}
+
+extern "C" int niq_ctx_create(int device, niq_ctx** out) {
+    if (!out) return fail(NIQ_EINVAL, "niq_ctx_create: out is NULL");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(NIQ_ECUDA, "no CUDA device available (%s): this backend has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(NIQ_EINVAL, "device %d out of range (have %d)", device, count);
+    CU(cudaSetDevice(device));
+    niq_ctx* c = new niq_ctx();
+    c->device = device;
+    CU(cudaGetDeviceProperties(&c->prop, device));
+    if (c->prop.major < 9)
+        return fail(NIQ_ECUDA, "device compute capability %d.%d: kernels are built for sm_100a only", c->prop.major, c->prop.minor);
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->t0));
+    CU(cudaEventCreate(&c->t1));
+    CU(cudaMallocHost(&c->pinned, 64 * sizeof(long long)));
+    *out = c;
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_destroy(niq_ctx* c) {
+    if (!c) return NIQ_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    resolve_timers(c);
+    for (auto e : c->event_pool) cudaEventDestroy(e);
+    if (c->t0) cudaEventDestroy(c->t0);
+    if (c->t1) cudaEventDestroy(c->t1);
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_sync(niq_ctx* c) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_device_info(niq_ctx* c, int32_t info[4]) {
+    if (!c || !info) return fail(NIQ_EINVAL, "bad argument");
+    info[0] = c->prop.multiProcessorCount; info[1] = c->prop.major; info[2] = c->prop.minor;
+    info[3] = (int32_t)c->prop.sharedMemPerBlockOptin;
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_launch_count(niq_ctx* c, int64_t* out) {
+    if (!c || !out) return fail(NIQ_EINVAL, "bad argument");
+    *out = c->launches;
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_timer_start(niq_ctx* c) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    CU(cudaEventRecord(c->t0, c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_timer_stop(niq_ctx* c, float* ms) {
+    if (!c || !ms) return fail(NIQ_EINVAL, "bad argument");
+    CU(cudaEventRecord(c->t1, c->stream));
+    CU(cudaEventSynchronize(c->t1));
+    CU(cudaEventElapsedTime(ms, c->t0, c->t1));
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_kernel_timing(niq_ctx* c, int on) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    c->timing = on != 0;
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_kernel_ms(niq_ctx* c, int which, float* ms, int64_t* launches, int reset) {
+    if (!c || which < 0 || which > 1) return fail(NIQ_EINVAL, "bad argument");
+    CU(cudaStreamSynchronize(c->stream));
+    resolve_timers(c);
+    if (ms) *ms = (float)c->fam_ms[which];
+    if (launches) *launches = c->fam_launches[which];
+    if (reset) { c->fam_ms[which] = 0; c->fam_launches[which] = 0; }
+    return NIQ_OK;
+}
+extern "C" int niq_dev_alloc(niq_ctx* c, int64_t bytes, void** out) {
+    if (!c || !out || bytes < 0) return fail(NIQ_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(out, (size_t)std::max<int64_t>(bytes, 16)));
+    return NIQ_OK;
+}
+extern "C" int niq_dev_free(niq_ctx* c, void* p) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaFree(p));
+    return NIQ_OK;
+}
+extern "C" int niq_dev_upload(niq_ctx* c, void* dst, const void* src, int64_t bytes) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_dev_download(niq_ctx* c, void* dst, const void* src, int64_t bytes) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    CU(cudaMemcpyAsync(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_measure_fp32_peak(niq_ctx* c, float* tflops) {
+    if (!c || !tflops) return fail(NIQ_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf out(c);
+    TRY(out.alloc(16));
+    const int iters = 4096, blocks = c->prop.multiProcessorCount * 8;
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(c->t0, c->stream));
+        k_ffma_peak<<<blocks, 256, 0, c->stream>>>(out.as<float>(), iters, 0.999f, 0.001f);
+        c->launches++;
+        CU(cudaEventRecord(c->t1, c->stream));
+        CU(cudaEventSynchronize(c->t1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->t0, c->t1));
+        const double flop = 2.0 * 16 * 8 * (double)iters * 256.0 * blocks;
+        if (rep > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    CU(cudaGetLastError());
+    *tflops = best;
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// MLP packing
+// ------------------------------------------------------------------------------------------------
+struct HostLayer { int in_dim, out_dim, in_pad, out_pad, act; bool dot; size_t w_off, b_off; };
+
+struct niq_mlp {
+    niq_ctx* ctx = nullptr;
+    std::vector<HostLayer> layers;
+    float* d_weights = nullptr;
+    float* d_bias = nullptr;
+    NetDev net{};
+    int wmax = 32;         // width class of the fixed-row engine
+    int maxw_pad = 8;      // widest padded row (grow engine)
+    int64_t macs = 0;
+    int sum_act_out = 0;   // sum of out_dim over activation layers (affine_all growth)
+    int max_act_out = 0;
+};
+
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+static bool invert3(const float* R, float* inv) {   // float32 Gauss-Jordan with partial pivoting
+    float a[3][6];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { a[i][j] = R[3 * i + j]; a[i][3 + j] = i == j ? 1.f : 0.f; }
+    for (int col = 0; col < 3; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 3; ++r) if (std::fabs(a[r][col]) > std::fabs(a[piv][col])) piv = r;
+        if (a[piv][col] == 0.f) return false;
+        if (piv != col) for (int j = 0; j < 6; ++j) std::swap(a[piv][j], a[col][j]);
+        const float d = a[col][col];
+        for (int j = 0; j < 6; ++j) a[col][j] = a[col][j] / d;
+        for (int r = 0; r < 3; ++r) {
+            if (r == col) continue;
+            const float f = a[r][col];
+            for (int j = 0; j < 6; ++j) a[r][j] = a[r][j] - f * a[col][j];
+        }
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) inv[3 * i + j] = a[i][3 + j];
+    return true;
+}
+
+extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops, niq_mlp** out) {
+    if (!c || !ops || !out || n_ops <= 0) return fail(NIQ_EINVAL, "niq_mlp_create: bad argument");
+    CU(cudaSetDevice(c->device));
+    struct Raw { int in, out, act; std::vector<float> A, b; };
+    std::vector<Raw> raw;
+    bool squeezed = false;
+    for (int i = 0; i < n_ops; ++i) {
+        const niq_op_desc& op = ops[i];
+        if (squeezed) return fail(NIQ_EINVAL, "op %d follows squeeze_last (squeeze_last must be the final op)", i);
+        switch (op.kind) {
+            case NIQ_OP_DENSE: {
+                if (op.in_dim <= 0 || op.out_dim <= 0 || !op.A) return fail(NIQ_EINVAL, "dense op %d: bad shape / NULL A", i);
+                Raw r; r.in = op.in_dim; r.out = op.out_dim; r.act = ACT_NONE;
+                r.A.assign(op.A, op.A + (size_t)op.in_dim * op.out_dim);
+                if (op.b) r.b.assign(op.b, op.b + op.out_dim); else r.b.assign(op.out_dim, 0.f);
+                raw.push_back(std::move(r));
+                break;
+            }
+            case NIQ_OP_SPATIAL: {
+                if (!op.A || !op.b) return fail(NIQ_EINVAL, "spatial_transformation op %d: R and t are required", i);
+                Raw r; r.in = 3; r.out = 3; r.act = ACT_NONE;
+                r.A.resize(9); r.b.resize(3);
+                if (!invert3(op.A, r.A.data())) return fail(NIQ_EINVAL, "spatial_transformation op %d: R is singular", i);
+                // reference src/affine_layers.py:175-179: dense(x, A=inv(R), b=inv(R)@(-t)), used as x@A
+                for (int k = 0; k < 3; ++k) {
+                    float s = 0.f;
+                    for (int j = 0; j < 3; ++j) s = s + r.A[3 * k + j] * (-op.b[j]);
+                    r.b[k] = s;
+                }
+                raw.push_back(std::move(r));
+                break;
+            }
+            case NIQ_OP_RELU:
+            case NIQ_OP_ELU:
+                if (raw.empty() || raw.back().act != ACT_NONE)
+                    return fail(NIQ_EUNSUPPORTED, "op %d: an activation must directly follow a dense / spatial op", i);
+                raw.back().act = op.kind == NIQ_OP_RELU ? ACT_RELU : ACT_ELU;
+                break;
+            case NIQ_OP_SQUEEZE_LAST:
+                if (raw.empty() || raw.back().out != 1) return fail(NIQ_EINVAL, "squeeze_last needs a preceding op with out_dim 1");
+                squeezed = true;
+                break;
+            default:
+                return fail(NIQ_EUNSUPPORTED, "op %d: kind %d is outside the hot-path scope (dense, relu, elu, squeeze_last, spatial_transformation)", i, op.kind);
+        }
+    }
+    if (raw.empty()) return fail(NIQ_EINVAL, "no dense layer");
+    if (raw.front().in != 3) return fail(NIQ_EUNSUPPORTED, "input dimension %d: queries are 3-D", raw.front().in);
+    if (raw.back().out != 1) return fail(NIQ_EUNSUPPORTED, "the last dense layer must have out_dim 1 (scalar implicit function)");
+    if (raw.back().act != ACT_NONE) return fail(NIQ_EUNSUPPORTED, "activation after the final layer is not supported");
+    if ((int)raw.size() > kMaxLayers) return fail(NIQ_EUNSUPPORTED, "more than %d layers", kMaxLayers);
+    for (size_t l = 1; l < raw.size(); ++l)
+        if (raw[l].in != raw[l - 1].out) return fail(NIQ_EINVAL, "layer %zu: in_dim %d != previous out_dim %d", l, raw[l].in, raw[l - 1].out);
+
+    niq_mlp* m = new niq_mlp();
+    m->ctx = c;
+    int maxw = 8;
+    for (size_t l = 0; l + 1 < raw.size(); ++l) maxw = std::max(maxw, raw[l].out);
+    if (maxw > 256) { delete m; return fail(NIQ_EUNSUPPORTED, "hidden width %d > 256", maxw); }
+    m->wmax = maxw <= 32 ? 32 : maxw <= 64 ? 64 : maxw <= 128 ? 128 : 256;
+
+    std::vector<float> hw, hb;
+    int n_chunks = 0;
+    for (size_t l = 0; l < raw.size(); ++l) {
+        HostLayer L{};
+        L.in_dim = raw[l].in; L.out_dim = raw[l].out; L.act = raw[l].act;
+        L.dot = (l + 1 == raw.size());
+        L.in_pad = l == 0 ? 4 : m->layers[l - 1].out_pad;
+        L.out_pad = L.dot ? 1 : round_up(L.out_dim, 8);
+        if (!L.dot && raw[l].out == 1) { delete m; return fail(NIQ_EUNSUPPORTED, "hidden layer of width 1"); }
+        L.w_off = hw.size();
+        hw.resize(hw.size() + (size_t)L.in_pad * (L.dot ? 1 : L.out_pad), 0.f);
+        for (int j = 0; j < L.in_dim; ++j)
+            for (int k = 0; k < L.out_dim; ++k)
+                hw[L.w_off + (size_t)j * (L.dot ? 1 : L.out_pad) + k] = raw[l].A[(size_t)j * L.out_dim + k];
+        hw.resize(round_up((int)hw.size(), 4), 0.f);
+        L.b_off = hb.size();
+        hb.resize(hb.size() + (L.dot ? 4 : L.out_pad), 0.f);
+        for (int k = 0; k < L.out_dim; ++k) hb[L.b_off + k] = raw[l].b[k];
+        m->layers.push_back(L);
+        m->macs += (int64_t)L.in_dim * L.out_dim;
+        m->maxw_pad = std::max(m->maxw_pad, std::max(L.in_pad, L.dot ? 1 : L.out_pad));
+        if (L.act != ACT_NONE) { m->sum_act_out += L.out_dim; m->max_act_out = std::max(m->max_act_out, L.out_dim); }
+    }
+    CU(cudaMalloc(&m->d_weights, hw.size() * sizeof(float)));
+    CU(cudaMalloc(&m->d_bias, hb.size() * sizeof(float)));
+    CU(cudaMemcpyAsync(m->d_weights, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(m->d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+
+    NetDev& nd = m->net;
+    nd.n_layers = (int)m->layers.size();
+    nd.n_nets = 1;
+    for (size_t l = 0; l < m->layers.size(); ++l) {
+        const HostLayer& L = m->layers[l];
+        LayerDev& D = nd.layers[l];
+        D.in_dim = L.in_dim; D.out_dim = L.out_dim; D.in_pad = L.in_pad; D.out_pad = L.out_pad; D.act = L.act;
+        D.bias = m->d_bias + L.b_off;
+        D.first_of_net = l == 0; D.last_of_net = L.dot;
+        D.chunk_begin = n_chunks;
+        const int row = L.dot ? 1 : L.out_pad;
+        int kc_max = L.dot ? L.in_pad : std::max(4, (kChunkFloats / row) / 4 * 4);
+        for (int k0 = 0; k0 < L.in_pad; k0 += kc_max) {
+            if (n_chunks >= kMaxChunks) { niq_mlp_destroy(m); return fail(NIQ_EUNSUPPORTED, "weight stream needs more than %d chunks", kMaxChunks); }
+            ChunkDev& C = nd.chunks[n_chunks++];
+            C.k0 = k0; C.kc = std::min(kc_max, L.in_pad - k0);
+            C.src = m->d_weights + L.w_off + (size_t)k0 * row;
+            C.n_floats = (unsigned)(C.kc * row);
+            C.pad_ = 0;
+        }
+        D.chunk_end = n_chunks;
+    }
+    nd.n_chunks = n_chunks;
+    *out = m;
+    return NIQ_OK;
+}
+extern "C" int niq_mlp_destroy(niq_mlp* m) {
+    if (!m) return NIQ_OK;
+    cudaSetDevice(m->ctx->device);
+    cudaStreamSynchronize(m->ctx->stream);
+    if (m->d_weights) cudaFree(m->d_weights);
+    if (m->d_bias) cudaFree(m->d_bias);
+    delete m;
+    return NIQ_OK;
+}
+extern "C" int niq_mlp_macs(const niq_mlp* m, int64_t* macs) {
+    if (!m || !macs) return fail(NIQ_EINVAL, "bad argument");
+    *macs = m->macs;
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+template <class K>
+static int set_smem(K kernel, size_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return NIQ_OK;
+}
+static int grid_for(niq_ctx* c, long long n_pass) {
+    return (int)std::max<long long>(1, std::min<long long>(n_pass, c->prop.multiProcessorCount));
+}
+
+template <int WMAX>
+static int launch_classify_fixed_w(niq_ctx* c, const NetDev& net, const BoxSource& src, long long n, float offset,
+                                   int* label, float* lower, float* upper, unsigned char* tie) {
+    using E = Engine<WMAX, TileBox3>;
+    TRY(set_smem(k_classify_fixed<WMAX>, E::smem_bytes()));
+    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
+    LaunchTimer lt(c, 0);
+    k_classify_fixed<WMAX><<<grid_for(c, n_pass), kThreads, E::smem_bytes(), c->stream>>>(net, src, n, offset, label, lower, upper, tie);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+template <int WMAX>
+static int launch_eval_points_w(niq_ctx* c, const NetDev& net, const PointSource& src, long long n, float* f, float* scale) {
+    using E = Engine<WMAX, TilePts>;
+    TRY(set_smem(k_eval_points<WMAX>, E::smem_bytes()));
+    const long long per = kWarps * E::WARP_ROWS;
+    LaunchTimer lt(c, 0);
+    k_eval_points<WMAX><<<grid_for(c, (n + per - 1) / per), kThreads, E::smem_bytes(), c->stream>>>(net, src, n, f, scale);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+template <int WMAX>
+static int launch_cast_rays_w(niq_ctx* c, const NetDev& net, const CastOpts& o, long long n, int interval,
+                              const float* roots, const float* dirs, float* t, int* hit, int* cnt,
+                              unsigned char* tie, unsigned long long* queue) {
+    using E = Engine<WMAX, TileRay>;
+    TRY(set_smem(k_cast_rays<WMAX>, E::smem_bytes()));
+    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
+    LaunchTimer lt(c, 0);
+    k_cast_rays<WMAX><<<grid_for(c, n_pass), kThreads, E::smem_bytes(), c->stream>>>(net, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+static int launch_classify_fixed(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
+                                 int* label, float* lower, float* upper, unsigned char* tie) {
+    if (n <= 0) return NIQ_OK;
+    switch (m->wmax) {
+        case 32: return launch_classify_fixed_w<32>(c, m->net, src, n, offset, label, lower, upper, tie);
+        case 64: return launch_classify_fixed_w<64>(c, m->net, src, n, offset, label, lower, upper, tie);
+        case 128: return launch_classify_fixed_w<128>(c, m->net, src, n, offset, label, lower, upper, tie);
+        default: return launch_classify_fixed_w<256>(c, m->net, src, n, offset, label, lower, upper, tie);
+    }
+}
+static int launch_eval_points(niq_ctx* c, const niq_mlp* m, const PointSource& src, long long n, float* f, float* scale) {
+    if (n <= 0) return NIQ_OK;
+    switch (m->wmax) {
+        case 32: return launch_eval_points_w<32>(c, m->net, src, n, f, scale);
+        case 64: return launch_eval_points_w<64>(c, m->net, src, n, f, scale);
+        case 128: return launch_eval_points_w<128>(c, m->net, src, n, f, scale);
+        default: return launch_eval_points_w<256>(c, m->net, src, n, f, scale);
+    }
+}
+
+static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, BoxSource src, long long n,
+                                float offset, int* label, float* lower, float* upper, unsigned char* tie) {
+    if (n <= 0) return NIQ_OK;
+    if (m->maxw_pad > 128)
+        return fail(NIQ_EUNSUPPORTED, "affine_all / affine_truncate support hidden widths up to 128 (state matrix must fit shared memory)");
+    GrowArgs g{};
+    g.src = src; g.n = n; g.offset = offset;
+    g.truncate = cfg->mode == NIQ_MODE_AFFINE_TRUNCATE;
+    g.n_keep = g.truncate ? cfg->truncate_count : 0;
+    const int v = src.kind == 0 ? src.v : 3;
+    if (g.truncate && g.n_keep < 0) return fail(NIQ_EINVAL, "affine_truncate: truncate_count must be >= 0");
+    g.kcap = g.truncate ? std::max(v, std::min(g.n_keep, v + m->sum_act_out)) + m->max_act_out : v + m->sum_act_out;
+    g.kcap = std::max(g.kcap, 4);
+    g.W = round_up(m->maxw_pad, 8);
+    g.label = label; g.lower = lower; g.upper = upper; g.near_tie = tie;
+    const size_t floats = (size_t)13 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W + (size_t)(g.truncate ? g.n_keep : 0) * g.W + 16;
+    const size_t bytes = floats * sizeof(float);
+    if (bytes > c->prop.sharedMemPerBlockOptin)
+        return fail(NIQ_EUNSUPPORTED, "affine state of %zu bytes exceeds shared memory (%zu): network too wide/deep for this mode", bytes, (size_t)c->prop.sharedMemPerBlockOptin);
+    TRY(set_smem(k_classify_grow, bytes));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify_grow, 256, bytes);
+    per_sm = std::max(per_sm, 1);
+    const int grid = (int)std::min<long long>(n, (long long)c->prop.multiProcessorCount * per_sm);
+    LaunchTimer lt(c, 0);
+    k_classify_grow<<<grid, 256, bytes, c->stream>>>(m->net, g);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+
+static int check_cfg(const niq_mode_cfg* cfg) {
+    if (!cfg) return fail(NIQ_EINVAL, "mode cfg is NULL");
+    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_AFFINE_ALL) return fail(NIQ_EINVAL, "invalid mode");
+    if (cfg->mode == NIQ_MODE_AFFINE_TRUNCATE && cfg->truncate_policy != 0)
+        return fail(NIQ_EUNSUPPORTED, "truncate policy 'relative' is not supported (reference src/affine.py:146 broadcasts (k,)/(w,))");
+    return NIQ_OK;
+}
+static bool is_fixed_mode(const niq_mode_cfg* cfg) { return cfg->mode == NIQ_MODE_INTERVAL || cfg->mode == NIQ_MODE_AFFINE_FIXED; }
+
+// classify n boxes from a device-side source, any mode
+static int classify_dev(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, BoxSource src, long long n, float offset,
+                        int* label, float* lower, float* upper, unsigned char* tie) {
+    if (is_fixed_mode(cfg)) {
+        src.interval = cfg->mode == NIQ_MODE_INTERVAL;
+        return launch_classify_fixed(c, m, src, n, offset, label, lower, upper, tie);
+    }
+    src.interval = 0;
+    return launch_classify_grow(c, m, cfg, src, n, offset, label, lower, upper, tie);
+}
+
+// exclusive scan of n ints into out[0..n] (out[n] = total); recursive over 2048-int tiles
+static int scan_exclusive(niq_ctx* c, const int* in, long long n, int* out) {
+    if (n <= 0) return NIQ_OK;
+    const long long tiles = (n + kScanTile - 1) / kScanTile;
+    if (tiles == 1) {
+        LaunchTimer lt(c, 1);
+        k_scan_apply<<<1, kScanThreads, 0, c->stream>>>(in, n, nullptr, out);
+        CU(cudaGetLastError());
+        return NIQ_OK;
+    }
+    DevBuf sums(c), offs(c);
+    TRY(sums.alloc(tiles * sizeof(int)));
+    TRY(offs.alloc((tiles + 1) * sizeof(int)));
+    {
+        LaunchTimer lt(c, 1);
+        k_scan_tile_sums<<<(int)tiles, kScanThreads, 0, c->stream>>>(in, n, sums.as<int>());
+        CU(cudaGetLastError());
+    }
+    TRY(scan_exclusive(c, sums.as<int>(), tiles, offs.as<int>()));
+    {
+        LaunchTimer lt(c, 1);
+        k_scan_apply<<<(int)tiles, kScanThreads, 0, c->stream>>>(in, n, offs.as<int>(), out);
+        CU(cudaGetLastError());
+    }
+    return NIQ_OK;
+}
+
+static int read_back(niq_ctx* c, const void* dsrc, size_t bytes, void* hdst) {
+    if (bytes <= 64 * sizeof(long long)) {
+        CU(cudaMemcpyAsync(c->pinned, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        memcpy(hdst, c->pinned, bytes);
+    } else {
+        CU(cudaMemcpyAsync(hdst, dsrc, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    return NIQ_OK;
+}
+
+// host<->device staging for `mem` = NIQ_MEM_HOST
+struct InBuf {
+    DevBuf buf; const void* dev = nullptr;
+    explicit InBuf(niq_ctx* c) : buf(c) {}
+    int stage(niq_ctx* c, const void* p, size_t bytes, int mem) {
+        if (!p) { dev = nullptr; return NIQ_OK; }
+        if (mem == NIQ_MEM_DEVICE) { dev = p; return NIQ_OK; }
+        TRY(buf.alloc(bytes));
+        CU(cudaMemcpyAsync(buf.p, p, bytes, cudaMemcpyHostToDevice, c->stream));
+        dev = buf.p;
+        return NIQ_OK;
+    }
+    template <class T> const T* as() const { return reinterpret_cast<const T*>(dev); }
+};
+struct OutBuf {
+    DevBuf buf; void* dev = nullptr; void* host = nullptr; size_t bytes = 0;
+    explicit OutBuf(niq_ctx* c) : buf(c) {}
+    int stage(niq_ctx* c, void* p, size_t nbytes, int mem) {
+        (void)c;
+        if (!p) { dev = nullptr; return NIQ_OK; }
+        if (mem == NIQ_MEM_DEVICE) { dev = p; return NIQ_OK; }
+        TRY(buf.alloc(nbytes));
+        dev = buf.p; host = p; bytes = nbytes;
+        return NIQ_OK;
+    }
+    int flush(niq_ctx* c) {
+        if (host) CU(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, c->stream));
+        return NIQ_OK;
+    }
+    template <class T> T* as() { return reinterpret_cast<T*>(dev); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// primitives
+// ------------------------------------------------------------------------------------------------
+extern "C" int niq_eval_points(niq_ctx* c, const niq_mlp* m, int64_t n, const float* x, float* f, float* scale, int mem) {
+    if (!c || !m || n < 0 || (n > 0 && (!x || !f))) return fail(NIQ_EINVAL, "niq_eval_points: bad argument");
+    if (n == 0) return NIQ_OK;
+    CU(cudaSetDevice(c->device));
+    InBuf dx(c); OutBuf df(c), ds(c);
+    TRY(dx.stage(c, x, (size_t)n * 12, mem));
+    TRY(df.stage(c, f, (size_t)n * 4, mem));
+    TRY(ds.stage(c, scale, (size_t)n * 4, mem));
+    PointSource src{};
+    src.kind = 0; src.a = dx.as<float>();
+    TRY(launch_eval_points(c, m, src, n, df.as<float>(), ds.as<float>()));
+    TRY(df.flush(c)); TRY(ds.flush(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+
+static int classify_common(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, int64_t n, BoxSource src, size_t a_bytes,
+                           size_t b_bytes, const float* a, const float* b, float offset, int32_t* label, float* lower,
+                           float* upper, uint8_t* tie, int mem) {
+    CU(cudaSetDevice(c->device));
+    InBuf da(c), db(c); OutBuf dl(c), dlo(c), dup(c), dt(c);
+    TRY(da.stage(c, a, a_bytes, mem));
+    TRY(db.stage(c, b, b_bytes, mem));
+    TRY(dl.stage(c, label, (size_t)n * 4, mem));
+    TRY(dlo.stage(c, lower, (size_t)n * 4, mem));
+    TRY(dup.stage(c, upper, (size_t)n * 4, mem));
+    TRY(dt.stage(c, tie, (size_t)n, mem));
+    src.a = da.as<float>(); src.b = db.as<float>();
+    TRY(classify_dev(c, m, cfg, src, n, offset, dl.as<int>(), dlo.as<float>(), dup.as<float>(), dt.as<unsigned char>()));
+    TRY(dl.flush(c)); TRY(dlo.flush(c)); TRY(dup.flush(c)); TRY(dt.flush(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+
+extern "C" int niq_classify_general_boxes(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, int64_t n, const float* center,
+                                          const float* vecs, int32_t v, float offset, int32_t* label, float* lower,
+                                          float* upper, uint8_t* tie, int mem) {
+    if (!c || !m || n < 0 || (n > 0 && (!center || !vecs))) return fail(NIQ_EINVAL, "niq_classify_general_boxes: bad argument");
+    TRY(check_cfg(cfg));
+    if (v < 1) return fail(NIQ_EINVAL, "v must be >= 1");
+    if (is_fixed_mode(cfg) && v > 3) return fail(NIQ_EUNSUPPORTED, "interval / affine_fixed support v <= 3 box vectors (got %d)", v);
+    if (n == 0) return NIQ_OK;
+    BoxSource src{};
+    src.kind = 0; src.v = v;
+    return classify_common(c, m, cfg, n, src, (size_t)n * 12, (size_t)n * v * 12, center, vecs, offset, label, lower, upper, tie, mem);
+}
+extern "C" int niq_classify_boxes(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, int64_t n, const float* lo,
+                                  const float* hi, float offset, int32_t* label, float* lower, float* upper, uint8_t* tie, int mem) {
+    if (!c || !m || n < 0 || (n > 0 && (!lo || !hi))) return fail(NIQ_EINVAL, "niq_classify_boxes: bad argument");
+    TRY(check_cfg(cfg));
+    if (n == 0) return NIQ_OK;
+    BoxSource src{};
+    src.kind = 1; src.v = 3;
+    return classify_common(c, m, cfg, n, src, (size_t)n * 12, (size_t)n * 12, lo, hi, offset, label, lower, upper, tie, mem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// cast_rays
+// ------------------------------------------------------------------------------------------------
+static int next_bucket(long long s, long long* out) {    // reference src/bucketing.py:7-14
+    for (int p = 7; p < 31; ++p) if (s <= (1ll << p)) { *out = 1ll << p; return NIQ_OK; }
+    return fail(NIQ_EINVAL, "max bucket size exceeded");
+}
+
+extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
+                             const niq_cast_opts* o, int64_t n, const float* roots, const float* dirs, float* t,
+                             int32_t* hit_id, int32_t* count, int64_t* n_evals, uint8_t* tie, int mem) {
+    if (!c || !mlps || !cfgs || !o || n_funcs < 1 || n < 0) return fail(NIQ_EINVAL, "niq_cast_rays: bad argument");
+    if (n > 0 && (!roots || !dirs || !t || !hit_id || !count)) return fail(NIQ_EINVAL, "niq_cast_rays: NULL array");
+    if (o->n_substeps < 1) return fail(NIQ_EINVAL, "n_substeps must be >= 1");
+    for (int f = 0; f < n_funcs; ++f) {
+        if (!mlps[f]) return fail(NIQ_EINVAL, "mlp %d is NULL", f);
+        TRY(check_cfg(&cfgs[f]));
+        if (cfgs[f].mode != cfgs[0].mode) return fail(NIQ_EUNSUPPORTED, "all funcs of one cast_rays call must use the same mode");
+    }
+    if (n_evals) *n_evals = 0;
+    if (n == 0) return NIQ_OK;
+    CU(cudaSetDevice(c->device));
+    InBuf dr(c), dd(c); OutBuf dt(c), dh(c), dc(c), dtie(c);
+    TRY(dr.stage(c, roots, (size_t)n * 12, mem));
+    TRY(dd.stage(c, dirs, (size_t)n * 12, mem));
+    TRY(dt.stage(c, t, (size_t)n * 4, mem));
+    TRY(dh.stage(c, hit_id, (size_t)n * 4, mem));
+    TRY(dc.stage(c, count, (size_t)n * 4, mem));
+    TRY(dtie.stage(c, tie, (size_t)n, mem));
+
+    CastOpts co{};
+    co.hit_eps = o->hit_eps; co.max_dist = o->max_dist; co.safety = o->safety_factor; co.grow = o->interval_grow_fac;
+    co.shrink = o->interval_shrink_fac; co.n_max_step = o->n_max_step; co.n_substeps = o->n_substeps;
+    co.init_step = (1.0f * o->interval_init_size) * o->max_dist;     // reference src/queries.py:149
+
+    if (is_fixed_mode(&cfgs[0])) {
+        // concatenate the funcs' layer / chunk tables into one stream
+        NetDev net{};
+        int wmax = 32;
+        for (int f = 0; f < n_funcs; ++f) {
+            const NetDev& s = mlps[f]->net;
+            if (net.n_layers + s.n_layers > kMaxLayers || net.n_chunks + s.n_chunks > kMaxChunks)
+                return fail(NIQ_EUNSUPPORTED, "too many layers / weight chunks for one cast_rays launch");
+            for (int l = 0; l < s.n_layers; ++l) {
+                LayerDev L = s.layers[l];
+                L.chunk_begin += net.n_chunks; L.chunk_end += net.n_chunks;
+                net.layers[net.n_layers + l] = L;
+            }
+            for (int k = 0; k < s.n_chunks; ++k) net.chunks[net.n_chunks + k] = s.chunks[k];
+            net.n_layers += s.n_layers; net.n_chunks += s.n_chunks;
+            wmax = std::max(wmax, mlps[f]->wmax);
+        }
+        net.n_nets = n_funcs;
+        DevBuf queue(c);
+        TRY(queue.alloc(8));
+        CU(cudaMemsetAsync(queue.p, 0, 8, c->stream));
+        const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
+        switch (wmax) {
+            case 32: TRY(launch_cast_rays_w<32>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            case 64: TRY(launch_cast_rays_w<64>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            case 128: TRY(launch_cast_rays_w<128>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            default: TRY(launch_cast_rays_w<256>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+        }
+    } else {
+        return fail(NIQ_EUNSUPPORTED, "cast_rays with affine_all / affine_truncate runs through the host-level stepping loop of the Python layer");
+    }
+
+    // N_evals of the reference (src/queries.py:137,164-173): lanes evaluated per iteration incl. bucket padding
+    if (n_evals) {
+        const int n_bins = o->n_max_step / o->n_substeps + 3;
+        DevBuf hist(c);
+        TRY(hist.alloc((size_t)n_bins * 8));
+        CU(cudaMemsetAsync(hist.p, 0, (size_t)n_bins * 8, c->stream));
+        {
+            LaunchTimer lt(c, 1);
+            k_iter_hist<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(dc.as<int>(), n, o->n_substeps, n_bins, hist.as<unsigned long long>());
+            CU(cudaGetLastError());
+        }
+        std::vector<unsigned long long> h(n_bins);
+        TRY(read_back(c, hist.p, (size_t)n_bins * 8, h.data()));
+        long long cur = n, valid = n, evals = 0;
+        for (int it = 1; it < n_bins && valid > 0; ++it) {
+            evals += cur * o->n_substeps;
+            valid -= (long long)h[it];
+            if (valid <= 0) break;
+            long long nb;
+            TRY(next_bucket(valid, &nb));
+            if (nb < cur) cur = nb;
+        }
+        *n_evals = evals;
+    }
+    TRY(dt.flush(c)); TRY(dh.flush(c)); TRY(dc.flush(c)); TRY(dtie.flush(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// level-set tree
+// ------------------------------------------------------------------------------------------------
+struct NodeList { float* lo = nullptr; float* hi = nullptr; long long n = 0, cap = 0; };
+
+struct niq_tree {
+    niq_ctx* ctx = nullptr;
+    NodeList lists[3];     // 0 unknown leaves, 1 interior, 2 exterior
+    long long stats[4] = {0, 0, 0, 0};
+};
+
+static int list_reserve(niq_ctx* c, NodeList& L, long long need) {
+    if (need <= L.cap) return NIQ_OK;
+    long long cap = std::max<long long>(need, std::max<long long>(2 * L.cap, 1024));
+    float *lo = nullptr, *hi = nullptr;
+    CU(cudaMallocAsync(&lo, (size_t)cap * 12, c->stream));
+    CU(cudaMallocAsync(&hi, (size_t)cap * 12, c->stream));
+    if (L.n > 0) {
+        CU(cudaMemcpyAsync(lo, L.lo, (size_t)L.n * 12, cudaMemcpyDeviceToDevice, c->stream));
+        CU(cudaMemcpyAsync(hi, L.hi, (size_t)L.n * 12, cudaMemcpyDeviceToDevice, c->stream));
+    }
+    if (L.lo) cudaFreeAsync(L.lo, c->stream);
+    if (L.hi) cudaFreeAsync(L.hi, c->stream);
+    L.lo = lo; L.hi = hi; L.cap = cap;
+    return NIQ_OK;
+}
+
+extern "C" int niq_tree_destroy(niq_tree* t) {
+    if (!t) return NIQ_OK;
+    cudaSetDevice(t->ctx->device);
+    for (auto& L : t->lists) {
+        if (L.lo) cudaFreeAsync(L.lo, t->ctx->stream);
+        if (L.hi) cudaFreeAsync(L.hi, t->ctx->stream);
+    }
+    cudaStreamSynchronize(t->ctx->stream);
+    delete t;
+    return NIQ_OK;
+}
+
+extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, const float lower[3], const float upper[3],
+                              int32_t split_depth, int64_t node_thresh, float offset, int32_t flags, int32_t bps, niq_tree** out) {
+    if (!c || !m || !lower || !upper || !out) return fail(NIQ_EINVAL, "niq_tree_build: bad argument");
+    TRY(check_cfg(cfg));
+    if (bps <= 0) return fail(NIQ_EINVAL, "batch_process_size must be positive");
+    for (int p = 7; p < 31; ++p) {        // reference src/kd_tree.py:105-109
+        const long long b = 1ll << p;
+        if (b > bps && (b / bps) * bps != b)
+            return fail(NIQ_EINVAL, "batch_process_size must be a factor of our bucket sizes, is not a factor of %lld (try a power of 2)", b);
+    }
+    if (split_depth < 0 && node_thresh <= 0)
+        return fail(NIQ_EINVAL, "must specify at least one of node_terminate_thresh or split_depth as a terminating condition");
+    if (node_thresh <= 0) node_thresh = 9999999999ll;
+    CU(cudaSetDevice(c->device));
+
+    niq_tree* T = new niq_tree();
+    T->ctx = c;
+    struct Guard { niq_tree* t; bool ok = false; ~Guard() { if (!ok) niq_tree_destroy(t); } } guard{T};
+
+    NodeList cur, nxt;
+    struct ListGuard { niq_ctx* c; NodeList* L; ~ListGuard() { if (L->lo) cudaFreeAsync(L->lo, c->stream); if (L->hi) cudaFreeAsync(L->hi, c->stream); } } g1{c, &cur}, g2{c, &nxt};
+    TRY(list_reserve(c, cur, 1));
+    CU(cudaMemcpyAsync(cur.lo, lower, 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(cur.hi, upper, 12, cudaMemcpyHostToDevice, c->stream));
+    cur.n = 1;
+    long long bucket = 1;                                       // padded array size the reference would hold
+    const long long n_splits = split_depth < 0 ? 99999999ll : (long long)split_depth + 1;
+
+    for (long long i_split = 0; i_split < n_splits; ++i_split) {
+        const long long N = cur.n;
+        const long long this_b = std::min<long long>(bps, bucket);
+        const bool quit_next = (N >= node_thresh) || (i_split + 1 == n_splits);
+        T->stats[2] += 1;
+        T->stats[3] = std::max(T->stats[3], N);
+        long long counts[4] = {0, 0, 0, 0};                     // unknown, negative, positive, near-tie
+        if (N > 0) {
+            DevBuf label(c), tie(c), f_unk(c), f_neg(c), f_pos(c), s_unk(c), s_neg(c), s_pos(c), s_tie(c), f_tie(c);
+            TRY(label.alloc(N * 4)); TRY(tie.alloc(N));
+            BoxSource src{};
+            src.kind = 1; src.v = 3; src.a = cur.lo; src.b = cur.hi;
+            TRY(classify_dev(c, m, cfg, src, N, offset, label.as<int>(), nullptr, nullptr, tie.as<unsigned char>()));
+            T->stats[0] += N;
+            const bool want_neg = flags & NIQ_TREE_INTERIOR, want_pos = flags & NIQ_TREE_EXTERIOR;
+            TRY(f_unk.alloc(N * 4)); TRY(s_unk.alloc((N + 1) * 4));
+            if (want_neg) { TRY(f_neg.alloc(N * 4)); TRY(s_neg.alloc((N + 1) * 4)); }
+            if (want_pos) { TRY(f_pos.alloc(N * 4)); TRY(s_pos.alloc((N + 1) * 4)); }
+            const int g = (int)((N + 255) / 256);
+            {
+                LaunchTimer lt(c, 1);
+                k_tree_flags<<<g, 256, 0, c->stream>>>(label.as<int>(), N, f_unk.as<int>(), want_neg ? f_neg.as<int>() : nullptr,
+                                                      want_pos ? f_pos.as<int>() : nullptr);
+                CU(cudaGetLastError());
+            }
+            TRY(scan_exclusive(c, f_unk.as<int>(), N, s_unk.as<int>()));
+            if (want_neg) TRY(scan_exclusive(c, f_neg.as<int>(), N, s_neg.as<int>()));
+            if (want_pos) TRY(scan_exclusive(c, f_pos.as<int>(), N, s_pos.as<int>()));
+            int tot[3] = {0, 0, 0};
+            CU(cudaMemcpyAsync(&c->pinned[0], s_unk.as<int>() + N, 4, cudaMemcpyDeviceToHost, c->stream));
+            if (want_neg) CU(cudaMemcpyAsync(reinterpret_cast<int*>(c->pinned) + 1, s_neg.as<int>() + N, 4, cudaMemcpyDeviceToHost, c->stream));
+            if (want_pos) CU(cudaMemcpyAsync(reinterpret_cast<int*>(c->pinned) + 2, s_pos.as<int>() + N, 4, cudaMemcpyDeviceToHost, c->stream));
+            // near-tie count: reuse the scan machinery on the flags widened to int is overkill; count on host side of a tiny reduction
+            CU(cudaStreamSynchronize(c->stream));
+            tot[0] = reinterpret_cast<int*>(c->pinned)[0];
+            if (want_neg) tot[1] = reinterpret_cast<int*>(c->pinned)[1];
+            if (want_pos) tot[2] = reinterpret_cast<int*>(c->pinned)[2];
+            counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2];
+            {   // near-tie boxes of this level (diagnostic counter)
+                std::vector<unsigned char> ht((size_t)N);
+                CU(cudaMemcpyAsync(ht.data(), tie.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+                CU(cudaStreamSynchronize(c->stream));
+                long long nt = 0;
+                for (unsigned char b : ht) nt += b;
+                T->stats[1] += nt;
+            }
+            if (want_neg && counts[1] > 0) {
+                NodeList& L = T->lists[1];
+                TRY(list_reserve(c, L, L.n + counts[1]));
+                LaunchTimer lt(c, 1);
+                k_append_flagged<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, N, f_neg.as<int>(), s_neg.as<int>(), L.n, L.lo, L.hi);
+                CU(cudaGetLastError());
+                L.n += counts[1];
+            }
+            if (want_pos && counts[2] > 0) {
+                NodeList& L = T->lists[2];
+                TRY(list_reserve(c, L, L.n + counts[2]));
+                LaunchTimer lt(c, 1);
+                k_append_flagged<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, N, f_pos.as<int>(), s_pos.as<int>(), L.n, L.lo, L.hi);
+                CU(cudaGetLastError());
+                L.n += counts[2];
+            }
+            const long long n_out = quit_next ? counts[0] : 2 * counts[0];
+            TRY(list_reserve(c, nxt, std::max<long long>(n_out, 1)));
+            if (counts[0] > 0) {
+                LaunchTimer lt(c, 1);
+                k_tree_scatter<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, N, f_unk.as<int>(), s_unk.as<int>(), this_b, quit_next ? 0 : 1, nxt.lo, nxt.hi);
+                CU(cudaGetLastError());
+            }
+            nxt.n = n_out;
+            CU(cudaStreamSynchronize(c->stream));   // temporaries of this level are released after their last use
+        } else {
+            nxt.n = 0;
+        }
+        std::swap(cur, nxt);
+        TRY(next_bucket(cur.n, &bucket));
+        if (quit_next) break;
+    }
+    // hand the final frontier to the tree object
+    T->lists[0] = cur;
+    cur = NodeList{};
+    CU(cudaStreamSynchronize(c->stream));
+    guard.ok = true;
+    *out = T;
+    return NIQ_OK;
+}
+
+extern "C" int niq_tree_count(const niq_tree* t, int which, int64_t* n) {
+    if (!t || !n || which < 0 || which > 2) return fail(NIQ_EINVAL, "bad argument");
+    *n = t->lists[which].n;
+    return NIQ_OK;
+}
+extern "C" int niq_tree_copy(const niq_tree* t, int which, float* lower, float* upper, int64_t capacity, int mem) {
+    if (!t || which < 0 || which > 2) return fail(NIQ_EINVAL, "bad argument");
+    const NodeList& L = t->lists[which];
+    if (capacity < L.n) return fail(NIQ_ECAPACITY, "capacity %lld < %lld nodes", (long long)capacity, L.n);
+    if (L.n == 0) return NIQ_OK;
+    if (!lower || !upper) return fail(NIQ_EINVAL, "NULL output");
+    niq_ctx* c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    const cudaMemcpyKind k = mem == NIQ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    CU(cudaMemcpyAsync(lower, L.lo, (size_t)L.n * 12, k, c->stream));
+    CU(cudaMemcpyAsync(upper, L.hi, (size_t)L.n * 12, k, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_tree_stats(const niq_tree* t, int64_t stats[4]) {
+    if (!t || !stats) return fail(NIQ_EINVAL, "bad argument");
+    for (int i = 0; i < 4; ++i) stats[i] = t->stats[i];
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// marching cubes
+// ------------------------------------------------------------------------------------------------
+struct niq_mesh { niq_ctx* ctx = nullptr; float* tris = nullptr; long long n = 0; };
+
+extern "C" int niq_mesh_destroy(niq_mesh* m) {
+    if (!m) return NIQ_OK;
+    cudaSetDevice(m->ctx->device);
+    if (m->tris) cudaFreeAsync(m->tris, m->ctx->stream);
+    cudaStreamSynchronize(m->ctx->stream);
+    delete m;
+    return NIQ_OK;
+}
+
+static int mc_device(niq_ctx* c, const niq_mlp* m, long long n, const float* lo, const float* hi, int n_sub, niq_mesh** out) {
+    if (n_sub < 0 || n_sub > 5) return fail(NIQ_EINVAL, "n_subcell_depth must be in 0..5");
+    niq_mesh* M = new niq_mesh();
+    M->ctx = c;
+    *out = M;
+    if (n == 0) return NIQ_OK;
+    const int side = 1 << n_sub, P = side + 1;
+    const long long pts_per_leaf = (long long)P * P * P;
+    // leaves are processed in slabs so the lattice values stay bounded (256 MB)
+    const long long slab = std::max<long long>(1, (64ll << 20) / pts_per_leaf);
+    std::vector<std::pair<float*, long long>> parts;
+    struct PartGuard { niq_ctx* c; std::vector<std::pair<float*, long long>>* p; ~PartGuard() { for (auto& q : *p) if (q.first) cudaFreeAsync(q.first, c->stream); } } pg{c, &parts};
+    long long total = 0;
+    for (long long s0 = 0; s0 < n; s0 += slab) {
+        const long long L = std::min(slab, n - s0);
+        DevBuf vals(c), cnt(c), off(c);
+        TRY(vals.alloc((size_t)L * pts_per_leaf * 4));
+        TRY(cnt.alloc(L * 4));
+        TRY(off.alloc((L + 1) * 4));
+        PointSource src{};
+        src.kind = 1; src.a = lo + 3 * s0; src.b = hi + 3 * s0; src.pts_per_side = P;
+        TRY(launch_eval_points(c, m, src, L * pts_per_leaf, vals.as<float>(), nullptr));
+        McArgs a{};
+        a.leaf_lo = lo + 3 * s0; a.leaf_hi = hi + 3 * s0; a.vals = vals.as<float>(); a.n_leaves = L; a.n_side = side;
+        {
+            LaunchTimer lt(c, 1);
+            k_mc_count<<<(int)L, kScanThreads, 0, c->stream>>>(a, cnt.as<int>());
+            CU(cudaGetLastError());
+        }
+        TRY(scan_exclusive(c, cnt.as<int>(), L, off.as<int>()));
+        int tot = 0;
+        TRY(read_back(c, off.as<int>() + L, 4, &tot));
+        float* tri = nullptr;
+        if (tot > 0) {
+            CU(cudaMallocAsync(&tri, (size_t)tot * 36, c->stream));
+            LaunchTimer lt(c, 1);
+            k_mc_write<<<(int)L, kScanThreads, 0, c->stream>>>(a, off.as<int>(), tri);
+            CU(cudaGetLastError());
+        }
+        parts.push_back({tri, (long long)tot});
+        total += tot;
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    if (total > 0) {
+        if (parts.size() == 1) {
+            M->tris = parts[0].first;
+            parts[0].first = nullptr;
+        } else {
+            CU(cudaMallocAsync(&M->tris, (size_t)total * 36, c->stream));
+            long long o = 0;
+            for (auto& q : parts) {
+                if (q.second > 0) CU(cudaMemcpyAsync(M->tris + o * 9, q.first, (size_t)q.second * 36, cudaMemcpyDeviceToDevice, c->stream));
+                o += q.second;
+            }
+        }
+    }
+    M->n = total;
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+
+extern "C" int niq_marching_cubes(niq_ctx* c, const niq_mlp* m, int64_t n, const float* leaf_lower, const float* leaf_upper,
+                                  int32_t n_sub, int mem, niq_mesh** out) {
+    if (!c || !m || !out || n < 0 || (n > 0 && (!leaf_lower || !leaf_upper))) return fail(NIQ_EINVAL, "niq_marching_cubes: bad argument");
+    CU(cudaSetDevice(c->device));
+    InBuf dlo(c), dhi(c);
+    TRY(dlo.stage(c, leaf_lower, (size_t)n * 12, mem));
+    TRY(dhi.stage(c, leaf_upper, (size_t)n * 12, mem));
+    niq_mesh* M = nullptr;
+    int r = mc_device(c, m, n, dlo.as<float>(), dhi.as<float>(), n_sub, &M);
+    if (r != NIQ_OK) { niq_mesh_destroy(M); return r; }
+    *out = M;
+    return NIQ_OK;
+}
+extern "C" int niq_marching_cubes_tree(niq_ctx* c, const niq_mlp* m, const niq_tree* t, int32_t n_sub, niq_mesh** out) {
+    if (!c || !m || !t || !out) return fail(NIQ_EINVAL, "niq_marching_cubes_tree: bad argument");
+    CU(cudaSetDevice(c->device));
+    niq_mesh* M = nullptr;
+    int r = mc_device(c, m, t->lists[0].n, t->lists[0].lo, t->lists[0].hi, n_sub, &M);
+    if (r != NIQ_OK) { niq_mesh_destroy(M); return r; }
+    *out = M;
+    return NIQ_OK;
+}
+extern "C" int niq_mesh_count(const niq_mesh* m, int64_t* n) {
+    if (!m || !n) return fail(NIQ_EINVAL, "bad argument");
+    *n = m->n;
+    return NIQ_OK;
+}
+extern "C" int niq_mesh_copy(const niq_mesh* m, float* tri_pos, int64_t capacity, int mem) {
+    if (!m) return fail(NIQ_EINVAL, "bad argument");
+    if (capacity < m->n) return fail(NIQ_ECAPACITY, "capacity %lld < %lld triangles", (long long)capacity, m->n);
+    if (m->n == 0) return NIQ_OK;
+    if (!tri_pos) return fail(NIQ_EINVAL, "NULL output");
+    niq_ctx* c = m->ctx;
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(tri_pos, m->tris, (size_t)m->n * 36, mem == NIQ_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_mc_tables(int32_t* tri_table, int32_t* edge_verts, uint8_t* vert_coords) {
+    static const unsigned long long words[256] = NIQ_MC_CASE_WORDS_INIT;
+    if (tri_table)
+        for (int cs = 0; cs < 256; ++cs)
+            for (int i = 0; i < 16; ++i) {
+                const int nb = (int)((words[cs] >> (4 * i)) & 0xF);
+                tri_table[cs * 16 + i] = nb == 0xF ? -1 : nb;
+            }
+    if (edge_verts)
+        for (int e = 0; e < 12; ++e) {
+            edge_verts[2 * e] = (int)((NIQ_MC_EDGE_A_NIBBLES >> (4 * e)) & 0xF);
+            edge_verts[2 * e + 1] = (int)((NIQ_MC_EDGE_B_NIBBLES >> (4 * e)) & 0xF);
+        }
+    if (vert_coords)
+        for (int v = 0; v < 8; ++v) {
+            vert_coords[3 * v] = (NIQ_MC_VERT_MASK_X >> v) & 1;
+            vert_coords[3 * v + 1] = (NIQ_MC_VERT_MASK_Y >> v) & 1;
+            vert_coords[3 * v + 2] = (NIQ_MC_VERT_MASK_Z >> v) & 1;
+        }
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// find_any_intersection
+// ------------------------------------------------------------------------------------------------
+extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const niq_mode_cfg* cfgA, const niq_mlp* mB,
+                                         const niq_mode_cfg* cfgB, const float lower[3], const float upper[3], float eps,
+                                         int32_t* found, float loc[3], int64_t stats[3]) {
+    if (!c || !mA || !mB || !lower || !upper || !found || !loc) return fail(NIQ_EINVAL, "niq_find_any_intersection: bad argument");
+    TRY(check_cfg(cfgA)); TRY(check_cfg(cfgB));
+    CU(cudaSetDevice(c->device));
+    const float eps_w = eps / sqrtf(3.0f);                 // reference src/kd_tree.py:446
+    NodeList cur, nxt;
+    struct ListGuard { niq_ctx* c; NodeList* L; ~ListGuard() { if (L->lo) cudaFreeAsync(L->lo, c->stream); if (L->hi) cudaFreeAsync(L->hi, c->stream); } } g1{c, &cur}, g2{c, &nxt};
+    TRY(list_reserve(c, cur, 1));
+    CU(cudaMemcpyAsync(cur.lo, lower, 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(cur.hi, upper, 12, cudaMemcpyHostToDevice, c->stream));
+    cur.n = 1;
+    long long n_nodes = 0, n_rounds = 0, n_tie = 0;
+    *found = 0;
+    loc[0] = loc[1] = loc[2] = -777.f;
+    while (cur.n > 0) {
+        const long long N = cur.n;
+        n_nodes += N; n_rounds += 1;
+        DevBuf labA(c), labB(c), vA(c), vB(c), needs(c), scan(c), locs(c), first(c), tieA(c), tieB(c);
+        TRY(labA.alloc(N * 4)); TRY(labB.alloc(N * 4)); TRY(vA.alloc(N * 28)); TRY(vB.alloc(N * 28));
+        TRY(needs.alloc(N * 4)); TRY(scan.alloc((N + 1) * 4)); TRY(locs.alloc(N * 12)); TRY(first.alloc(8));
+        TRY(tieA.alloc(N)); TRY(tieB.alloc(N));
+        BoxSource bs{};
+        bs.kind = 1; bs.v = 3; bs.a = cur.lo; bs.b = cur.hi;
+        TRY(classify_dev(c, mA, cfgA, bs, N, 0.f, labA.as<int>(), nullptr, nullptr, tieA.as<unsigned char>()));
+        TRY(classify_dev(c, mB, cfgB, bs, N, 0.f, labB.as<int>(), nullptr, nullptr, tieB.as<unsigned char>()));
+        PointSource ps{};
+        ps.kind = 2; ps.a = cur.lo; ps.b = cur.hi; ps.sample_scale = eps_w;
+        TRY(launch_eval_points(c, mA, ps, 7 * N, vA.as<float>(), nullptr));
+        TRY(launch_eval_points(c, mB, ps, 7 * N, vB.as<float>(), nullptr));
+        CU(cudaMemsetAsync(first.p, 0xFF, 8, c->stream));
+        const int g = (int)((N + 255) / 256);
+        {
+            LaunchTimer lt(c, 1);
+            k_isect_logic<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, N, labA.as<int>(), labB.as<int>(), vA.as<float>(), vB.as<float>(),
+                                                   eps_w, needs.as<int>(), locs.as<float>(), first.as<unsigned long long>());
+            CU(cudaGetLastError());
+        }
+        unsigned long long first_idx = ~0ull;
+        TRY(read_back(c, first.p, 8, &first_idx));
+        {
+            std::vector<unsigned char> ht((size_t)N);
+            CU(cudaMemcpyAsync(ht.data(), tieA.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (unsigned char b : ht) n_tie += b;
+            CU(cudaMemcpyAsync(ht.data(), tieB.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            for (unsigned char b : ht) n_tie += b;
+        }
+        if (first_idx != ~0ull) {
+            TRY(read_back(c, locs.as<float>() + 3 * first_idx, 12, loc));
+            *found = 1;
+            break;
+        }
+        TRY(scan_exclusive(c, needs.as<int>(), N, scan.as<int>()));
+        int n_new = 0;
+        TRY(read_back(c, scan.as<int>() + N, 4, &n_new));
+        TRY(list_reserve(c, nxt, std::max<long long>(2ll * n_new, 1)));
+        if (n_new > 0) {
+            LaunchTimer lt(c, 1);
+            k_split_interleaved<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, nullptr, N, needs.as<int>(), scan.as<int>(), nxt.lo, nxt.hi, nullptr);
+            CU(cudaGetLastError());
+        }
+        nxt.n = 2ll * n_new;
+        CU(cudaStreamSynchronize(c->stream));
+        std::swap(cur, nxt);
+    }
+    if (stats) { stats[0] = n_nodes; stats[1] = n_rounds; stats[2] = n_tie; }
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest_point
+// ------------------------------------------------------------------------------------------------
+extern "C" int niq_closest_point(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, const float lower[3], const float upper[3],
+                                 int64_t q, const float* query_points, float eps, int64_t B, float* dist, float* loc,
+                                 int64_t stats[4], int mem) {
+    if (!c || !m || !lower || !upper || q < 0 || B <= 0) return fail(NIQ_EINVAL, "niq_closest_point: bad argument");
+    if (q > 0 && (!query_points || !dist || !loc)) return fail(NIQ_EINVAL, "niq_closest_point: NULL array");
+    TRY(check_cfg(cfg));
+    if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
+    if (q == 0) return NIQ_OK;
+    CU(cudaSetDevice(c->device));
+    InBuf dq(c); OutBuf dd(c), dl(c);
+    TRY(dq.stage(c, query_points, (size_t)q * 12, mem));
+    TRY(dd.stage(c, dist, (size_t)q * 4, mem));
+    TRY(dl.stage(c, loc, (size_t)q * 12, mem));
+
+    // the effective window never exceeds what the stack can hold; B >= stack size behaves like "everything"
+    const long long Bw = B;
+    long long cap = 0;
+    float *s_lo = nullptr, *s_hi = nullptr;
+    long long* s_id = nullptr;
+    struct StackGuard { niq_ctx* c; float** a; float** b; long long** d; ~StackGuard() { if (*a) cudaFreeAsync(*a, c->stream); if (*b) cudaFreeAsync(*b, c->stream); if (*d) cudaFreeAsync(*d, c->stream); } } sg{c, &s_lo, &s_hi, &s_id};
+    auto reserve = [&](long long need, long long live) -> int {
+        if (need <= cap) return NIQ_OK;
+        long long ncap = std::max<long long>(need, 2 * cap);
+        float *nlo = nullptr, *nhi = nullptr; long long* nid = nullptr;
+        CU(cudaMallocAsync(&nlo, (size_t)ncap * 12, c->stream));
+        CU(cudaMallocAsync(&nhi, (size_t)ncap * 12, c->stream));
+        CU(cudaMallocAsync(&nid, (size_t)ncap * 8, c->stream));
+        CU(cudaMemsetAsync(nlo, 0, (size_t)ncap * 12, c->stream));
+        CU(cudaMemsetAsync(nhi, 0, (size_t)ncap * 12, c->stream));
+        CU(cudaMemsetAsync(nid, 0, (size_t)ncap * 8, c->stream));
+        if (live > 0) {
+            CU(cudaMemcpyAsync(nlo, s_lo, (size_t)live * 12, cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemcpyAsync(nhi, s_hi, (size_t)live * 12, cudaMemcpyDeviceToDevice, c->stream));
+            CU(cudaMemcpyAsync(nid, s_id, (size_t)live * 8, cudaMemcpyDeviceToDevice, c->stream));
+        }
+        if (s_lo) cudaFreeAsync(s_lo, c->stream);
+        if (s_hi) cudaFreeAsync(s_hi, c->stream);
+        if (s_id) cudaFreeAsync(s_id, c->stream);
+        s_lo = nlo; s_hi = nhi; s_id = nid; cap = ncap;
+        return NIQ_OK;
+    };
+
+    // Each round pops the top min(B, top) entries (reference :679-686).  `ub` is a host-side upper bound of
+    // the device-resident stack top, exact after every poll.
+    const int kPoll = 8;                                  // rounds between polls in the windowed regime
+    long long ub = q;
+    TRY(reserve(ub + 3 * std::min<long long>(Bw, ub) + 16, 0));
+    {   // initial stack: one root box per query (reference src/kd_tree.py:769-775)
+        std::vector<float> hlo((size_t)q * 3), hhi((size_t)q * 3);
+        std::vector<long long> hid((size_t)q);
+        for (long long i = 0; i < q; ++i) {
+            for (int d = 0; d < 3; ++d) { hlo[3 * i + d] = lower[d]; hhi[3 * i + d] = upper[d]; }
+            hid[i] = i;
+        }
+        CU(cudaMemcpyAsync(s_lo, hlo.data(), (size_t)q * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(s_hi, hhi.data(), (size_t)q * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(s_id, hid.data(), (size_t)q * 8, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    DevBuf d_top(c), d_stats(c), d_winner(c), d_maxtop(c);
+    TRY(d_top.alloc(8)); TRY(d_stats.alloc(32)); TRY(d_winner.alloc((size_t)q * 8)); TRY(d_maxtop.alloc(8));
+    CU(cudaMemcpyAsync(d_top.p, &ub, 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(d_maxtop.p, &ub, 8, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaMemsetAsync(d_stats.p, 0, 32, c->stream));
+    CU(cudaMemsetAsync(d_winner.p, 0, (size_t)q * 8, c->stream));
+    {   // min_dist = +inf, min_loc = -777 (reference :776-777)
+        std::vector<float> hd((size_t)q, INFINITY), hl((size_t)q * 3, -777.f);
+        CU(cudaMemcpyAsync(dd.dev, hd.data(), (size_t)q * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(dl.dev, hl.data(), (size_t)q * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+    }
+    const float eps_w = eps / sqrtf(3.0f);                 // reference :689
+    unsigned long long round = 0;
+    while (true) {
+        // ub <= B: the window covers the whole stack (per-query level-synchronous regime) -> poll every round so
+        // the launch size tracks the stack; ub > B: steady windows of exactly B entries -> poll every kPoll rounds.
+        const bool level_regime = ub <= Bw;
+        const int rounds = level_regime ? 1 : kPoll;
+        const long long W = std::min<long long>(Bw, std::max<long long>(ub, 1));
+        TRY(reserve(ub + (rounds + 2) * W + 16, ub));
+        DevBuf label(c), tie(c), vals(c), this_d(c), cen(c), needs(c), scan(c), t_lo(c), t_hi(c), t_id(c);
+        TRY(label.alloc(W * 4)); TRY(tie.alloc(W)); TRY(vals.alloc(W * 28)); TRY(this_d.alloc(W * 4)); TRY(cen.alloc(W * 12));
+        TRY(needs.alloc(W * 4)); TRY(scan.alloc((W + 1) * 4)); TRY(t_lo.alloc(W * 12)); TRY(t_hi.alloc(W * 12)); TRY(t_id.alloc(W * 8));
+        for (int it = 0; it < rounds; ++it) {
+            BoxSource bs{};
+            bs.kind = 2; bs.v = 3; bs.a = s_lo; bs.b = s_hi; bs.top = d_top.as<long long>(); bs.window = W;
+            TRY(classify_dev(c, m, cfg, bs, W, 0.f, label.as<int>(), nullptr, nullptr, tie.as<unsigned char>()));
+            PointSource ps{};
+            ps.kind = 2; ps.a = s_lo; ps.b = s_hi; ps.sample_scale = -1.f; ps.top = d_top.as<long long>(); ps.window = W;
+            TRY(launch_eval_points(c, m, ps, 7 * W, vals.as<float>(), nullptr));
+            CpRound r{};
+            r.stack_lo = s_lo; r.stack_hi = s_hi; r.stack_qid = s_id; r.top = d_top.as<long long>(); r.window = W;
+            r.query = dq.as<float>(); r.min_dist = dd.as<float>(); r.min_loc = dl.as<float>(); r.winner = d_winner.as<unsigned long long>();
+            r.n_query = q; r.label = label.as<int>(); r.tie = tie.as<unsigned char>(); r.vals = vals.as<float>(); r.eps_w = eps_w; r.round = round;
+            r.this_dist = this_d.as<float>(); r.center = cen.as<float>(); r.needs = needs.as<int>(); r.stats = d_stats.as<long long>();
+            const int g = (int)((W + 255) / 256);
+            {
+                LaunchTimer lt(c, 1);
+                k_cp_eval<<<g, 256, 0, c->stream>>>(r);
+                k_cp_min<<<g, 256, 0, c->stream>>>(r);
+                k_cp_winner<<<g, 256, 0, c->stream>>>(r);
+                k_cp_loc<<<g, 256, 0, c->stream>>>(r);
+                k_cp_copy_window<<<g, 256, 0, c->stream>>>(r, t_lo.as<float>(), t_hi.as<float>(), t_id.as<long long>());
+                CU(cudaGetLastError());
+                c->launches += 4;
+            }
+            TRY(scan_exclusive(c, needs.as<int>(), W, scan.as<int>()));
+            {
+                LaunchTimer lt(c, 1);
+                k_cp_push<<<g, 256, 0, c->stream>>>(r, t_lo.as<float>(), t_hi.as<float>(), t_id.as<long long>(), scan.as<int>(), s_lo, s_hi, s_id);
+                k_cp_advance<<<1, 1, 0, c->stream>>>(r, scan.as<int>(), d_maxtop.as<long long>());
+                CU(cudaGetLastError());
+                c->launches += 1;
+            }
+            round += 1;
+        }
+        TRY(read_back(c, d_top.p, 8, &ub));
+        if (ub <= 0) break;
+    }
+    if (stats) {
+        long long hs[4] = {0, 0, 0, 0};
+        TRY(read_back(c, d_stats.p, 32, hs));
+        long long mt = 0;
+        TRY(read_back(c, d_maxtop.p, 8, &mt));
+        stats[0] = hs[0]; stats[1] = hs[1]; stats[2] = mt; stats[3] = hs[2];
+    }
+    TRY(dd.flush(c)); TRY(dl.flush(c));
+    CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}

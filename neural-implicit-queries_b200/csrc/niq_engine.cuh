@@ -1,0 +1,420 @@
+// niq_engine.cuh -- the warp-tiled FP32 network engine shared by every query kernel (sm_100a).
+//
+// What it computes: rows of "state" pushed through the MLP, one dense layer at a time, exactly as the
+// reference's affine interpreter does for one box (reference src/mlp.py:96-113 with the rules of
+// src/affine_layers.py:11-97): for a box the rows are [base; aff_1..aff_v; err] and a dense layer is
+//     base <- base@A + b ;  aff_r <- aff_r@A ;  err <- err@|A|
+// followed by the per-neuron Chebyshev linearisation (alpha, beta, delta) of relu / elu, which needs
+// rad = sum_r |aff_r| + err of that neuron.  Point rows (plain f(x), src/mlp.py:253-347) ride along.
+//
+// How it is laid out on a B200 SM:
+//   * a CTA is NWARPS warps.  Each warp owns TPW*NT "tiles" (a tile = the RT rows of one box / ray / 8
+//     points) in a private shared-memory activation buffer, updated IN PLACE layer by layer, so the only
+//     intra-layer synchronisation is __syncwarp().
+//   * inside a warp, lane = (tile_in_warp t, column group cg): the thread keeps ALL rows of its NT tiles
+//     for 8 output neurons in registers (NT*RT*8 FP32 accumulators), so rad and (alpha,beta,delta) are
+//     in-register work -- no shuffles in hidden layers.
+//   * weights stream through a ring of shared-memory stages as K-chunks, one cp.async.bulk (TMA bulk
+//     copy) per chunk, completion on an mbarrier; a stage is recycled after the __syncthreads() that
+//     follows its consumption.  Weight reads are warp-broadcast LDS.128, activation reads LDS.128 along K.
+//   * the final (out_dim = 1) layer is a dot product split across the CG lanes of a tile and reduced with
+//     warp shuffles.
+// All arithmetic is FP32 FFMA (tensor cores would change bounds by >> 1e-5 relative).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace niq {
+
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
+
+constexpr int kMaxLayers = 32;     // layers of all nets of one launch (cast_rays concatenates funcs)
+constexpr int kMaxChunks = 192;
+constexpr int kChunkFloats = 8192; // 32 KB per stage
+constexpr int kStages = 3;
+constexpr int kWarps = 8;          // compute warps per CTA
+constexpr int kThreads = kWarps * 32;
+
+struct LayerDev {
+    int in_dim, out_dim;      // logical
+    int in_pad, out_pad;      // in_pad % 4 == 0 ; out_pad % 8 == 0 (hidden) or 1 (dot layer)
+    int act;                  // ACT_*
+    int chunk_begin, chunk_end;
+    const float* bias;        // device, out_pad floats (zero padded)
+    int first_of_net;         // 1: the loader must (re)write the input rows before this layer
+    int last_of_net;          // 1: out_dim == 1, finalize after this layer
+};
+
+struct ChunkDev {
+    const float* src;         // device, 16-byte aligned; rows [k0, k0+kc) of the layer's padded A, contiguous
+    unsigned int n_floats;    // multiple of 4
+    int k0, kc;
+    int pad_;
+};
+
+struct NetDev {               // passed by value (__grid_constant__) to every engine kernel
+    int n_layers, n_chunks, n_nets, pad_;
+    LayerDev layers[kMaxLayers];
+    ChunkDev chunks[kMaxChunks];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + TMA bulk copy (global -> shared)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// Tile descriptors: which rows a thread carries and how the activation couples them.
+//   row kinds: B = base, A = affine coefficient, E = interval error (multiplies |A|), P = point
+// ------------------------------------------------------------------------------------------------
+struct TileBox3 {   // [B, A, A, A, E] : one general box with 3 symbols (affine_fixed, v<=3; interval uses E only)
+    static constexpr int RT = 5, NT = 2;
+    __host__ __device__ static constexpr bool is_err(int r) { return r == 4; }
+    __host__ __device__ static constexpr bool has_bias(int r) { return r == 0; }
+    static constexpr int n_aff = 3, n_pts = 0;
+    static constexpr bool has_group = true;
+};
+struct TileRay {    // [B, A, E, P, P] : one ray step = segment bound (v=1) + f(start), f(start+eps)
+    static constexpr int RT = 5, NT = 2;
+    __host__ __device__ static constexpr bool is_err(int r) { return r == 2; }
+    __host__ __device__ static constexpr bool has_bias(int r) { return r == 0 || r >= 3; }
+    static constexpr int n_aff = 1, n_pts = 2;
+    static constexpr bool has_group = true;
+};
+struct TilePts {    // [P x 8]
+    static constexpr int RT = 8, NT = 1;
+    __host__ __device__ static constexpr bool is_err(int) { return false; }
+    __host__ __device__ static constexpr bool has_bias(int) { return true; }
+    static constexpr int n_aff = 0, n_pts = 8;
+    static constexpr bool has_group = false;
+};
+
+// ------------------------------------------------------------------------------------------------
+// scalar activation rules
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
+
+// relu linearisation on [l,u]  (reference src/affine_layers.py:34-56)
+__device__ __forceinline__ void relu_lin(float l, float u, float& alpha, float& beta, float& delta) {
+    float a = (fmaxf(u, 0.f) - fmaxf(l, 0.f)) / (u - l);
+    if (l >= 0.f) a = 1.f;
+    if (u < 0.f) a = 0.f;
+    if (a != a) a = 0.f;                       // nan_to_num(nan=0)
+    a = fminf(fmaxf(a, 0.f), 1.f);             // also maps +inf -> 1 like nan_to_num + clip
+    alpha = a;
+    beta = (fmaxf(l, 0.f) - a * l) * 0.5f;
+    delta = fabsf(beta);
+}
+
+// elu linearisation on [l,u]  (reference src/affine_layers.py:59-97)
+__device__ __forceinline__ void elu_lin(float l, float u, float& alpha, float& beta, float& delta) {
+    const float lF = elu_f(l), uF = elu_f(u);
+    const float lS = fminf(expf(l), 1.f), uS = fminf(expf(u), 1.f);
+    float a = (uF - lF) / (u - l);
+    if (l >= 0.f) a = 1.f;
+    if (a != a) a = 0.f;
+    a = fminf(fmaxf(a, -3.4028234664e38f), 3.4028234664e38f);   // nan_to_num maps +-inf to +-FLT_MAX
+    a = fminf(fmaxf(a, lS), uS);
+    const float r_up = lF - a * l;
+    const float x_lo = fminf(fmaxf(logf(a), l), u);
+    const float r_lo = (a - 1.f) - a * x_lo;
+    float b = 0.5f * (r_up + r_lo);
+    float d = 0.5f * fabsf(r_up - r_lo);
+    if (l >= 0.f) { a = 1.f; b = 0.f; d = 0.f; }
+    alpha = a; beta = b; delta = fabsf(d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Engine
+// ------------------------------------------------------------------------------------------------
+template <int WMAX>
+struct Geometry {
+    static_assert(WMAX == 32 || WMAX == 64 || WMAX == 128 || WMAX == 256, "hidden width class");
+    static constexpr int CG = WMAX / 8;          // column groups (lanes) covering one row
+    static constexpr int TPW = 32 / CG;          // tiles per warp pass (per NT slice)
+    static constexpr int S = WMAX + 4;           // activation row stride in floats (bank-conflict padding)
+    static constexpr int LOG_CG = (CG == 4 ? 2 : CG == 8 ? 3 : CG == 16 ? 4 : 5);
+};
+
+template <int WMAX, class Tile>
+struct Engine {
+    using G = Geometry<WMAX>;
+    static constexpr int RT = Tile::RT, NT = Tile::NT;
+    static constexpr int ROWS = RT * NT;                       // rows carried by one thread
+    static constexpr int SLOTS = G::TPW * NT;                  // tiles per warp
+    static constexpr int WARP_ROWS = SLOTS * RT;               // rows in one warp's activation buffer
+    static constexpr int WARP_FLOATS = WARP_ROWS * G::S;
+    static constexpr int CTA_TILES = kWarps * SLOTS;
+
+    static constexpr size_t smem_bytes() {
+        return 64 + sizeof(float) * (size_t)(kStages * kChunkFloats + kWarps * WARP_FLOATS + kWarps * SLOTS * 8);
+    }
+
+    // shared-memory carve-up
+    uint64_t* full;        // [kStages] mbarriers
+    float* stage;          // [kStages][kChunkFloats]
+    float* act;            // this warp's [WARP_ROWS][S]
+    float* fin;            // this warp's [SLOTS][8] final scalars / scratch
+    const NetDev& net;
+    int warp, lane, t, cg;
+    // weight pipeline state (identical in every thread)
+    unsigned int seq_consumed, seq_issued;
+
+    __device__ Engine(const NetDev& n, unsigned char* smem_raw) : net(n) {
+        warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        t = lane / G::CG;
+        cg = lane % G::CG;
+        full = reinterpret_cast<uint64_t*>(smem_raw);
+        stage = reinterpret_cast<float*>(smem_raw + 64);
+        float* acts = stage + kStages * kChunkFloats;
+        act = acts + warp * WARP_FLOATS;
+        fin = acts + kWarps * WARP_FLOATS + warp * SLOTS * 8;
+        seq_consumed = 0;
+        seq_issued = 0;
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kStages; ++s) mbar_init(&full[s], 1);
+            fence_barrier_init();
+        }
+        __syncthreads();
+        // prologue: fill the ring
+        if (threadIdx.x == 0) {
+            for (int s = 0; s < kStages - 1; ++s) issue_next();
+        } else {
+            seq_issued = kStages - 1;
+        }
+    }
+
+    // activation row pointer of slot (n, t) row r
+    __device__ __forceinline__ float* row_ptr(int n, int tt, int r) const {
+        return act + ((n * G::TPW + tt) * RT + r) * G::S;
+    }
+
+    __device__ __forceinline__ void issue_next() {   // thread 0 only
+        const ChunkDev& c = net.chunks[seq_issued % (unsigned)net.n_chunks];
+        const unsigned s = seq_issued % kStages;
+        const uint32_t bytes = c.n_floats * 4u;
+        mbar_expect_tx(&full[s], bytes);
+        tma_bulk_g2s(stage + s * kChunkFloats, c.src, bytes, &full[s]);
+        ++seq_issued;
+    }
+
+    // Wait for the next chunk of the stream, recycle the stage consumed before it, return its smem pointer.
+    __device__ __forceinline__ const float* acquire_chunk() {
+        const unsigned s = seq_consumed % kStages;
+        mbar_wait(&full[s], (seq_consumed / kStages) & 1u);
+        __syncthreads();                     // everyone is done with chunk seq_consumed-1 -> its stage is free
+        if (threadIdx.x == 0) {
+            issue_next();
+        } else {
+            ++seq_issued;
+        }
+        ++seq_consumed;
+        return stage + s * kChunkFloats;
+    }
+
+    // Every thread must call this before the kernel exits: no bulk copy may be in flight into a dead CTA.
+    __device__ __forceinline__ void drain() {
+        while (seq_consumed < seq_issued) {
+            const unsigned s = seq_consumed % kStages;
+            mbar_wait(&full[s], (seq_consumed / kStages) & 1u);
+            ++seq_consumed;
+        }
+        __syncthreads();
+    }
+
+    // ---- one hidden layer: acc[rows][8] = act[rows][:K] @ W[:K][my 8 columns] -----------------------
+    __device__ __forceinline__ void hidden_layer(const LayerDev& L) {
+        float acc[ROWS][8];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+
+        const int cg_l = L.out_pad >> 3;                 // active column groups of this layer
+        const bool active = cg < cg_l;
+        const int col0 = 4 * cg, col1 = 4 * (cg + cg_l); // the thread's two float4 column blocks
+        const float* a_base = row_ptr(0, t, 0);
+
+        for (int ch = L.chunk_begin; ch < L.chunk_end; ++ch) {
+            const float* w = acquire_chunk();
+            const ChunkDev& C = net.chunks[ch];
+            if (active) {
+                const float* wrow = w + col0;
+                const int wstride = L.out_pad;
+                const int dcol = col1 - col0;
+                for (int j = 0; j < C.kc; j += 4) {
+                    float4 a4[ROWS];
+#pragma unroll
+                    for (int n = 0; n < NT; ++n)
+#pragma unroll
+                        for (int r = 0; r < RT; ++r)
+                            a4[n * RT + r] = *reinterpret_cast<const float4*>(
+                                a_base + (n * G::TPW * RT + r) * G::S + C.k0 + j);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const float4 w0 = *reinterpret_cast<const float4*>(wrow + (j + jj) * wstride);
+                        const float4 w1 = *reinterpret_cast<const float4*>(wrow + (j + jj) * wstride + dcol);
+                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                        float wa[8];
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) wa[c] = fabsf(wv[c]);
+#pragma unroll
+                        for (int r = 0; r < ROWS; ++r) {
+                            const float a = jj == 0 ? a4[r].x : jj == 1 ? a4[r].y : jj == 2 ? a4[r].z : a4[r].w;
+                            if (Tile::is_err(r % RT)) {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a, wa[c], acc[r][c]);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a, wv[c], acc[r][c]);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+
+        // ---- epilogue: bias, activation rule, in-place write-back --------------------------------------
+        if (active) {
+            float bias[8];
+            {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.bias + col0));
+                const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.bias + col1));
+                bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
+                bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
+            }
+#pragma unroll
+            for (int n = 0; n < NT; ++n) {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    if (Tile::has_group) {
+                        constexpr int ie = Tile::n_aff + 1;      // err row index inside the tile
+                        float base = acc[n * RT][c] + bias[c];
+                        float rad = 0.f;
+#pragma unroll
+                        for (int k = 1; k <= Tile::n_aff; ++k) rad += fabsf(acc[n * RT + k][c]);
+                        rad += acc[n * RT + ie][c];
+                        if (L.act != ACT_NONE) {
+                            float alpha, beta, delta;
+                            const float lo = base - rad, up = base + rad;
+                            if (L.act == ACT_RELU) relu_lin(lo, up, alpha, beta, delta);
+                            else elu_lin(lo, up, alpha, beta, delta);
+                            base = alpha * base + beta;
+#pragma unroll
+                            for (int k = 1; k <= Tile::n_aff; ++k) acc[n * RT + k][c] = alpha * acc[n * RT + k][c];
+                            acc[n * RT + ie][c] = alpha * acc[n * RT + ie][c] + delta;
+                        }
+                        acc[n * RT][c] = base;
+                    }
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const bool is_pt = Tile::has_group ? (r > Tile::n_aff + 1) : true;
+                        if (is_pt) {
+                            float x = acc[n * RT + r][c] + bias[c];
+                            if (L.act == ACT_RELU) x = fmaxf(x, 0.f);
+                            else if (L.act == ACT_ELU) x = elu_f(x);
+                            acc[n * RT + r][c] = x;
+                        }
+                    }
+                }
+            }
+        }
+        __syncwarp();            // every lane has finished READING this layer's input rows
+        if (active) {
+#pragma unroll
+            for (int n = 0; n < NT; ++n)
+#pragma unroll
+                for (int r = 0; r < RT; ++r) {
+                    float* dst = row_ptr(n, t, r);
+                    const float* a = acc[n * RT + r];
+                    *reinterpret_cast<float4*>(dst + col0) = make_float4(a[0], a[1], a[2], a[3]);
+                    *reinterpret_cast<float4*>(dst + col1) = make_float4(a[4], a[5], a[6], a[7]);
+                }
+        }
+        __syncwarp();
+    }
+
+    // ---- final layer (out_dim == 1): out[r] = act[r][:K] . w + b ; also |.|-sum for point rows -----------
+    // Results land in out[ROWS] (identical in all lanes of the tile group); pscale[ROWS] = sum|h_j w_j| + |b|
+    // for point rows (near-tie scale of sign tests).
+    __device__ __forceinline__ void dot_layer(const LayerDev& L, float out[ROWS], float pscale[ROWS]) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) { out[r] = 0.f; pscale[r] = 0.f; }
+        const float* a_base = row_ptr(0, t, 0);
+        for (int ch = L.chunk_begin; ch < L.chunk_end; ++ch) {
+            const float* w = acquire_chunk();
+            const ChunkDev& C = net.chunks[ch];
+            for (int j = cg; j < C.kc; j += G::CG) {
+                const float wj = w[j];
+                const float wja = fabsf(wj);
+#pragma unroll
+                for (int n = 0; n < NT; ++n)
+#pragma unroll
+                    for (int r = 0; r < RT; ++r) {
+                        const float a = a_base[(n * G::TPW * RT + r) * G::S + C.k0 + j];
+                        const int i = n * RT + r;
+                        if (Tile::is_err(r)) out[i] = fmaf(a, wja, out[i]);
+                        else out[i] = fmaf(a, wj, out[i]);
+                        const bool is_pt = Tile::has_group ? (r > Tile::n_aff + 1) : true;
+                        if (is_pt) pscale[i] = fmaf(fabsf(a), wja, pscale[i]);
+                    }
+            }
+        }
+#pragma unroll
+        for (int off = 1; off < G::CG; off <<= 1) {
+#pragma unroll
+            for (int i = 0; i < ROWS; ++i) {
+                out[i] += __shfl_xor_sync(0xffffffffu, out[i], off);
+                const bool is_pt = Tile::has_group ? ((i % RT) > Tile::n_aff + 1) : true;
+                if (is_pt) pscale[i] += __shfl_xor_sync(0xffffffffu, pscale[i], off);
+            }
+        }
+        const float b = __ldg(L.bias);
+#pragma unroll
+        for (int i = 0; i < ROWS; ++i) {
+            if (Tile::has_bias(i % RT)) { out[i] += b; pscale[i] += fabsf(b); }
+        }
+        __syncwarp();
+    }
+
+    // Run layers [l0, l1) of the stream; the last one must be a dot layer.
+    __device__ __forceinline__ void run_net(int l0, int l1, float out[ROWS], float pscale[ROWS]) {
+        for (int l = l0; l < l1 - 1; ++l) hidden_layer(net.layers[l]);
+        dot_layer(net.layers[l1 - 1], out, pscale);
+    }
+};
+
+}  // namespace niq

@@ -1,0 +1,808 @@
+// niq_kernels.cuh -- query kernels built on the engine (niq_engine.cuh) + the HBM-bound helper kernels
+// (scan / compaction / split / triangle write).  Compiled with --fmad=false: every FMA is explicit, so
+// the scalar query arithmetic rounds exactly like the reference's un-fused float32 expressions.
+#pragma once
+#include "mc_tables.h"
+#include "niq_engine.cuh"
+
+namespace niq {
+
+constexpr float kNearTieRel = 1e-5f;
+enum : int { SIGN_UNKNOWN = 0, SIGN_POSITIVE = 1, SIGN_NEGATIVE = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// Sources: where boxes / points come from (plain arrays, or generated on the fly from tree nodes)
+// ------------------------------------------------------------------------------------------------
+struct BoxSource {
+    int kind;                 // 0: center (n,3) + vecs (n,v,3);  1: lo/hi (n,3);  2: lo/hi windowed by *top
+    int v;                    // kind 0: number of vectors (1..3)
+    int interval;             // 1: interval mode (aff rows zero, err = sum |vecs|)
+    const float* a;           // center | lo
+    const float* b;           // vecs   | hi
+    const long long* top;     // kind 2: device scalar stack top; window = [max(top-B,0), +B)
+    long long window;         // kind 2: B
+};
+
+struct PointSource {
+    int kind;                 // 0: xyz (n,3); 1: MC lattice of leaves; 2: 7 samples per node (center +- s*e_i)
+    const float* a;           // xyz | leaf lo | node lo
+    const float* b;           //     | leaf hi | node hi
+    int pts_per_side;         // kind 1: P = 2^n + 1
+    float sample_scale;       // kind 2: eps/sqrt(3) (intersection); < 0: use the node's full extent (closest point)
+    const long long* top;     // kind 2: optional window (closest point)
+    long long window;
+};
+
+__device__ __forceinline__ long long window_base(const long long* top, long long window) {
+    if (top == nullptr) return 0;
+    const long long tp = *top;
+    return tp - window > 0 ? tp - window : 0;
+}
+
+// rows of one box -> the tile's 5 input rows [base, a0, a1, a2, err] as float4 (x,y,z,0)
+__device__ __forceinline__ void load_box_rows(const BoxSource& src, long long i, float4 rows[5]) {
+    if (src.kind == 0) {
+        const float* c = src.a + 3 * i;
+        rows[0] = make_float4(c[0], c[1], c[2], 0.f);
+        float4 e = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < 3; ++k) {
+            float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < src.v) {
+                const float* p = src.b + (i * src.v + k) * 3;
+                a = make_float4(p[0], p[1], p[2], 0.f);
+            }
+            if (src.interval) {
+                e.x += fabsf(a.x); e.y += fabsf(a.y); e.z += fabsf(a.z);
+                a = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            rows[1 + k] = a;
+        }
+        rows[4] = e;
+    } else {
+        const long long j = i + window_base(src.top, src.window);
+        const float* lo = src.a + 3 * j;
+        const float* hi = src.b + 3 * j;
+        // reference src/implicit_function.py:34-36: center = 0.5*(lo+hi); vec = hi - center; diag(vec)
+        const float cx = 0.5f * (lo[0] + hi[0]), cy = 0.5f * (lo[1] + hi[1]), cz = 0.5f * (lo[2] + hi[2]);
+        const float hx = hi[0] - cx, hy = hi[1] - cy, hz = hi[2] - cz;
+        rows[0] = make_float4(cx, cy, cz, 0.f);
+        if (src.interval) {
+            rows[1] = rows[2] = rows[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+            rows[4] = make_float4(fabsf(hx), fabsf(hy), fabsf(hz), 0.f);
+        } else {
+            rows[1] = make_float4(hx, 0.f, 0.f, 0.f);
+            rows[2] = make_float4(0.f, hy, 0.f, 0.f);
+            rows[3] = make_float4(0.f, 0.f, hz, 0.f);
+            rows[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+__device__ __forceinline__ float4 load_point(const PointSource& src, long long i) {
+    if (src.kind == 0) {
+        const float* p = src.a + 3 * i;
+        return make_float4(p[0], p[1], p[2], 0.f);
+    } else if (src.kind == 1) {
+        // reference src/extract_cell.py:372-381: per-axis jnp.linspace(lo, hi, P), 'ij' meshgrid, row-major flatten
+        const int P = src.pts_per_side;
+        const long long leaf = i / (P * P * P);
+        int r = (int)(i - leaf * (P * P * P));
+        const int i2 = r % P; r /= P;
+        const int i1 = r % P;
+        const int i0 = r / P;
+        const float* lo = src.a + 3 * leaf;
+        const float* hi = src.b + 3 * leaf;
+        const float div = (float)(P - 1);
+        const int idx[3] = {i0, i1, i2};
+        float xyz[3];
+        for (int d = 0; d < 3; ++d) {
+            if (idx[d] == P - 1) {
+                xyz[d] = hi[d];                      // linspace appends the end point itself
+            } else {
+                const float s = (float)idx[d] / div;
+                xyz[d] = lo[d] * (1.f - s) + hi[d] * s;
+            }
+        }
+        return make_float4(xyz[0], xyz[1], xyz[2], 0.f);
+    } else {
+        // reference src/kd_tree.py:461-464 (intersection) / :702-704 (closest point)
+        const long long node = i / 7 + window_base(src.top, src.window);
+        const int k = (int)(i % 7);
+        const float* lo = src.a + 3 * node;
+        const float* hi = src.b + 3 * node;
+        float c[3], s[3];
+        for (int d = 0; d < 3; ++d) {
+            c[d] = 0.5f * (lo[d] + hi[d]);
+            s[d] = src.sample_scale >= 0.f ? src.sample_scale : (hi[d] - lo[d]);
+        }
+        if (k >= 1 && k <= 3) c[k - 1] = c[k - 1] + s[k - 1];
+        if (k >= 4) c[k - 4] = c[k - 4] + s[k - 4] * -1.f;
+        return make_float4(c[0], c[1], c[2], 0.f);
+    }
+}
+
+__device__ __forceinline__ int label_of(float lower, float upper, float offset) {
+    int lab = SIGN_UNKNOWN;                         // reference src/affine.py:49-53
+    if (lower > offset) lab = SIGN_POSITIVE;
+    if (upper < -offset) lab = SIGN_NEGATIVE;
+    return lab;
+}
+__device__ __forceinline__ bool bound_near_tie(float lower, float upper, float offset) {
+    const float scale = fmaxf(fabsf(lower), fabsf(upper)) * kNearTieRel;
+    return fabsf(lower - offset) <= scale || fabsf(upper + offset) <= scale;
+}
+
+// ------------------------------------------------------------------------------------------------
+// classify (interval / affine_fixed): n boxes -> bounds, labels, near-tie flags
+// ------------------------------------------------------------------------------------------------
+template <int WMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+k_classify_fixed(const __grid_constant__ NetDev net, const BoxSource src, long long n, float offset,
+                 int* __restrict__ label, float* __restrict__ lower, float* __restrict__ upper,
+                 unsigned char* __restrict__ near_tie) {
+    using E = Engine<WMAX, TileBox3>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    E eng(net, smem);
+    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
+    for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const long long warp_box0 = pass * E::CTA_TILES + (long long)eng.warp * E::SLOTS;
+        // loader: lane s (< SLOTS) writes the 5 rows of slot s
+        if (eng.lane < E::SLOTS) {
+            const long long i = warp_box0 + eng.lane;
+            float4 rows[5];
+            if (i < n) load_box_rows(src, i, rows);
+            else for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            float* dst = eng.act + eng.lane * 5 * E::G::S;
+            for (int r = 0; r < 5; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
+        }
+        __syncwarp();
+        float out[E::ROWS], ps[E::ROWS];
+        eng.run_net(0, net.n_layers, out, ps);
+        if (eng.cg == 0) {
+#pragma unroll
+            for (int nn = 0; nn < E::NT; ++nn) {
+                const long long i = warp_box0 + nn * E::G::TPW + eng.t;
+                if (i < n) {
+                    const float base = out[nn * 5];
+                    const float rad = ((fabsf(out[nn * 5 + 1]) + fabsf(out[nn * 5 + 2])) + fabsf(out[nn * 5 + 3])) +
+                                      out[nn * 5 + 4];
+                    const float lo = base - rad, up = base + rad;
+                    if (lower) lower[i] = lo;
+                    if (upper) upper[i] = up;
+                    if (label) label[i] = label_of(lo, up, offset);
+                    if (near_tie) near_tie[i] = bound_near_tie(lo, up, offset) ? 1 : 0;
+                }
+            }
+        }
+        __syncwarp();
+    }
+    eng.drain();
+}
+
+// ------------------------------------------------------------------------------------------------
+// point evaluation: n points -> f (and the |.|-scale of the last dot product)
+// ------------------------------------------------------------------------------------------------
+template <int WMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+k_eval_points(const __grid_constant__ NetDev net, const PointSource src, long long n,
+              float* __restrict__ f, float* __restrict__ scale) {
+    using E = Engine<WMAX, TilePts>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    E eng(net, smem);
+    constexpr int PTS_WARP = E::WARP_ROWS;               // 8 * TPW points per warp pass
+    constexpr int PTS_CTA = kWarps * PTS_WARP;
+    const long long n_pass = (n + PTS_CTA - 1) / PTS_CTA;
+    for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const long long p0 = pass * PTS_CTA + (long long)eng.warp * PTS_WARP;
+        for (int r = eng.lane; r < PTS_WARP; r += 32) {
+            const long long i = p0 + r;
+            float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n) x = load_point(src, i);
+            *reinterpret_cast<float4*>(eng.act + r * E::G::S) = x;
+        }
+        __syncwarp();
+        float out[E::ROWS], ps[E::ROWS];
+        eng.run_net(0, net.n_layers, out, ps);
+        if (eng.cg == 0) {
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                const long long i = p0 + eng.t * 8 + r;
+                if (i < n) {
+                    f[i] = out[r];
+                    if (scale) scale[i] = ps[r];
+                }
+            }
+        }
+        __syncwarp();
+    }
+    eng.drain();
+}
+
+// ------------------------------------------------------------------------------------------------
+// cast_rays (interval / affine_fixed): persistent ray stepping with an in-kernel work queue.
+// Reference src/queries.py:39-175.  One warp slot = one ray; lane s keeps the state of slot s.
+// ------------------------------------------------------------------------------------------------
+struct CastOpts {
+    float hit_eps, max_dist, safety, grow, shrink, init_step;
+    int n_max_step, n_substeps;
+};
+
+template <int WMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, int interval_mode,
+            const float* __restrict__ roots, const float* __restrict__ dirs,
+            float* __restrict__ out_t, int* __restrict__ out_hit, int* __restrict__ out_count,
+            unsigned char* __restrict__ out_tie, unsigned long long* __restrict__ queue) {
+    using E = Engine<WMAX, TileRay>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    E eng(net, smem);
+    const int lane = eng.lane;
+    const bool owner = lane < E::SLOTS;
+
+    // per-slot ray state (meaningful in lanes < SLOTS)
+    long long ray = -1;
+    float rx = 0, ry = 0, rz = 0, dx = 0, dy = 0, dz = 0, t = 0, step = 0;
+    int count = 0, sub = 0;
+    bool tie = false;
+
+    bool cta_live = true;
+    while (cta_live) {
+        // ---- refill empty slots from the global queue (warp-aggregated atomicAdd) ----
+        const unsigned need = __ballot_sync(0xffffffffu, owner && ray < 0);
+        if (need) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(queue, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (owner && ray < 0) {
+                const long long idx = (long long)base + __popc(need & ((1u << lane) - 1u));
+                if (idx < n) {
+                    ray = idx;
+                    rx = roots[3 * idx]; ry = roots[3 * idx + 1]; rz = roots[3 * idx + 2];
+                    dx = dirs[3 * idx]; dy = dirs[3 * idx + 1]; dz = dirs[3 * idx + 2];
+                    t = 0.f;
+                    step = o.init_step;
+                    count = 0; sub = 0; tie = false;
+                }
+            }
+        }
+        const bool live = owner && ray >= 0;
+
+        // ---- one (sub)step: all funcs share t; can_step = AND, hit_id = last func whose signs differ ----
+        bool can_step = true, is_hit = false;
+        int hit_id = 0;
+        int l0 = 0;
+        for (int f = 0; f < net.n_nets; ++f) {
+            int l1 = l0;
+            while (!net.layers[l1].last_of_net) ++l1;
+            ++l1;
+            if (owner) {
+                // reference src/queries.py:55-58, 67-70
+                const float psx = rx + t * dx, psy = ry + t * dy, psz = rz + t * dz;
+                const float hs = 0.5f * step;
+                const float hx = hs * dx, hy = hs * dy, hz = hs * dz;
+                const float te = t + o.hit_eps;
+                float4 rows[5];
+                rows[0] = make_float4(psx + hx, psy + hy, psz + hz, 0.f);
+                if (interval_mode) {
+                    rows[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rows[2] = make_float4(fabsf(hx), fabsf(hy), fabsf(hz), 0.f);
+                } else {
+                    rows[1] = make_float4(hx, hy, hz, 0.f);
+                    rows[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                rows[3] = make_float4(psx, psy, psz, 0.f);
+                rows[4] = make_float4(rx + te * dx, ry + te * dy, rz + te * dz, 0.f);
+                float* dst = eng.act + lane * 5 * E::G::S;
+                for (int r = 0; r < 5; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
+            }
+            __syncwarp();
+            float out[E::ROWS], ps[E::ROWS];
+            eng.run_net(l0, l1, out, ps);
+            // hand the 5 scalars (+2 scales) of each slot to its owner lane through shared memory
+            if (eng.cg == 0) {
+#pragma unroll
+                for (int nn = 0; nn < E::NT; ++nn) {
+                    float* d = eng.fin + (nn * E::G::TPW + eng.t) * 8;
+                    d[0] = out[nn * 5]; d[1] = out[nn * 5 + 1]; d[2] = out[nn * 5 + 2];
+                    d[3] = out[nn * 5 + 3]; d[4] = out[nn * 5 + 4];
+                    d[5] = ps[nn * 5 + 3]; d[6] = ps[nn * 5 + 4];
+                }
+            }
+            __syncwarp();
+            if (live) {
+                const float* d = eng.fin + lane * 8;
+                const float rad = fabsf(d[1]) + d[2];
+                const float lo = d[0] - rad, up = d[0] + rad;
+                const int lab = label_of(lo, up, 0.f);
+                can_step = can_step && (lab == SIGN_POSITIVE || lab == SIGN_NEGATIVE);
+                const float v0 = d[3], v1 = d[4];
+                const int s0 = (v0 > 0.f) - (v0 < 0.f), s1 = (v1 > 0.f) - (v1 < 0.f);
+                const bool this_hit = (s0 != s1) || (v0 != v0) || (v1 != v1);   // sign(nan)=nan != anything
+                if (this_hit) hit_id = f + 1;
+                is_hit = is_hit || this_hit;
+                tie = tie || bound_near_tie(lo, up, 0.f) || fabsf(v0) <= kNearTieRel * d[5] ||
+                      fabsf(v1) <= kNearTieRel * d[6];
+            }
+            __syncwarp();
+            l0 = l1;
+        }
+
+        // ---- step update + termination (reference src/queries.py:79-90, 113-126) ----
+        if (live) {
+            count += 1;
+            sub += 1;
+            const float this_step = can_step ? step : o.hit_eps;
+            if (!is_hit) t = t + this_step * o.safety;
+            step = can_step ? step * o.grow : step * o.shrink;
+            step = fmaxf(step, o.hit_eps);
+            bool done = is_hit;
+            if (!done && sub >= o.n_substeps) {
+                sub = 0;
+                done = (t > o.max_dist) || (count >= o.n_max_step);
+            }
+            if (done) {
+                out_t[ray] = t;
+                out_hit[ray] = hit_id;
+                out_count[ray] = count;
+                if (out_tie) out_tie[ray] = tie ? 1 : 0;
+                ray = -1;
+            }
+        }
+        // ---- does anyone in the CTA still have work? (queue not exhausted or a live ray) ----
+        const bool more = owner && (ray >= 0 || (long long)(*((volatile unsigned long long*)queue)) < n);
+        cta_live = __syncthreads_or(more ? 1 : 0) != 0;
+    }
+    eng.drain();
+}
+
+// iteration histogram for N_evals (reference src/queries.py:164): hist[it] = #rays finishing in iteration it
+__global__ void k_iter_hist(const int* __restrict__ count, long long n, int n_substeps, int n_bins,
+                            unsigned long long* __restrict__ hist) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        int it = (count[i] + n_substeps - 1) / n_substeps;
+        if (it >= n_bins) it = n_bins - 1;
+        atomicAdd(&hist[it], 1ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// HBM-bound helpers: exclusive scan, tree split, compaction
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanTile = kScanThreads * kScanItems;     // 2048 ints per CTA
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+    __shared__ int warp_sums[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, off);
+        if (lane >= off) x += y;
+    }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int s = lane < kScanThreads / 32 ? warp_sums[lane] : 0;
+#pragma unroll
+        for (int off = 1; off < kScanThreads / 32; off <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, s, off);
+            if (lane >= off) s += y;
+        }
+        if (lane < kScanThreads / 32) warp_sums[lane] = s;
+    }
+    __syncthreads();
+    const int base = w > 0 ? warp_sums[w - 1] : 0;
+    if (total) *total = warp_sums[kScanThreads / 32 - 1];
+    __syncthreads();
+    return base + x - v;
+}
+
+// phase 1: per-tile sums
+__global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int* __restrict__ in, long long n,
+                                                                  int* __restrict__ tile_sums) {
+    const long long base = (long long)blockIdx.x * kScanTile;
+    int s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        const long long i = base + k * kScanThreads + threadIdx.x;
+        if (i < n) s += in[i];
+    }
+    int total;
+    block_exclusive_scan(s, &total);
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+}
+// phase 3: per-tile exclusive scan + tile offset; out has n+1 entries (out[n] = grand total)
+__global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int* __restrict__ in, long long n,
+                                                              const int* __restrict__ tile_offs,
+                                                              int* __restrict__ out) {
+    const long long base = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
+    int v[kScanItems];
+    int s = 0;
+    for (int k = 0; k < kScanItems; ++k) {
+        const long long i = base + k;
+        v[k] = i < n ? in[i] : 0;
+        s += v[k];
+    }
+    int total;
+    int off = block_exclusive_scan(s, &total) + (tile_offs ? tile_offs[blockIdx.x] : 0);
+    for (int k = 0; k < kScanItems; ++k) {
+        const long long i = base + k;
+        if (i < n) out[i] = off;
+        off += v[k];
+        if (i == n - 1) out[n] = off;
+    }
+}
+
+// flags from labels for one tree level: which[0]=unknown, [1]=negative (interior), [2]=positive (exterior)
+__global__ void k_tree_flags(const int* __restrict__ label, long long n, int* __restrict__ f_unk,
+                             int* __restrict__ f_neg, int* __restrict__ f_pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int lab = label[i];
+    f_unk[i] = lab == SIGN_UNKNOWN;
+    if (f_neg) f_neg[i] = lab == SIGN_NEGATIVE;
+    if (f_pos) f_pos[i] = lab == SIGN_POSITIVE;
+}
+
+__device__ __forceinline__ int argmax3_first(float a, float b, float c) {
+    int d = 0;
+    float m = a;
+    if (b > m) { m = b; d = 1; }
+    if (c > m) { d = 2; }
+    return d;
+}
+
+// Tree split in the reference's order (src/kd_tree.py:61-96): per batch of `bsz` nodes the children are
+// written as [A-children of the batch..., B-children of the batch...].  scan = exclusive scan of the
+// UNKNOWN flags (n+1 entries).  do_split = 0 copies the unknown nodes themselves (last round).
+__global__ void k_tree_scatter(const float* __restrict__ lo, const float* __restrict__ hi, long long n,
+                               const int* __restrict__ flag, const int* __restrict__ scan, long long bsz,
+                               int do_split, float* __restrict__ out_lo, float* __restrict__ out_hi) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const float l[3] = {lo[3 * i], lo[3 * i + 1], lo[3 * i + 2]};
+    const float h[3] = {hi[3 * i], hi[3 * i + 1], hi[3 * i + 2]};
+    if (!do_split) {
+        const long long o = scan[i];
+        for (int d = 0; d < 3; ++d) { out_lo[3 * o + d] = l[d]; out_hi[3 * o + d] = h[d]; }
+        return;
+    }
+    const long long b0 = (i / bsz) * bsz;
+    const long long b1 = b0 + bsz < n ? b0 + bsz : n;
+    const long long base = scan[b0], cnt = scan[b1] - base, rank = scan[i] - base;
+    const long long oa = 2 * base + rank, ob = 2 * base + cnt + rank;
+    const int sd = argmax3_first(h[0] - l[0], h[1] - l[1], h[2] - l[2]);
+    for (int d = 0; d < 3; ++d) {
+        const float mid = 0.5f * (l[d] + h[d]);
+        out_lo[3 * oa + d] = l[d];
+        out_hi[3 * oa + d] = d == sd ? mid : h[d];
+        out_lo[3 * ob + d] = d == sd ? mid : l[d];
+        out_hi[3 * ob + d] = h[d];
+    }
+}
+
+// ordered append of flagged nodes (interior / exterior lists, src/kd_tree.py:46-59)
+__global__ void k_append_flagged(const float* __restrict__ lo, const float* __restrict__ hi, long long n,
+                                 const int* __restrict__ flag, const int* __restrict__ scan, long long dst0,
+                                 float* __restrict__ out_lo, float* __restrict__ out_hi) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const long long o = dst0 + scan[i];
+    for (int d = 0; d < 3; ++d) { out_lo[3 * o + d] = lo[3 * i + d]; out_hi[3 * o + d] = hi[3 * i + d]; }
+}
+
+// split flagged nodes, children interleaved [A0,B0,A1,B1,...] (src/kd_tree.py:543-562, :732-754).
+// src nodes are read at src_base (device scalar window base optional), children written at dst_base + 2*rank.
+__global__ void k_split_interleaved(const float* __restrict__ lo, const float* __restrict__ hi,
+                                    const long long* __restrict__ qid, long long n, const int* __restrict__ flag,
+                                    const int* __restrict__ scan, float* __restrict__ out_lo,
+                                    float* __restrict__ out_hi, long long* __restrict__ out_qid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !flag[i]) return;
+    const float l[3] = {lo[3 * i], lo[3 * i + 1], lo[3 * i + 2]};
+    const float h[3] = {hi[3 * i], hi[3 * i + 1], hi[3 * i + 2]};
+    const long long oa = 2ll * scan[i], ob = oa + 1;
+    const int sd = argmax3_first(h[0] - l[0], h[1] - l[1], h[2] - l[2]);
+    for (int d = 0; d < 3; ++d) {
+        const float mid = 0.5f * (l[d] + h[d]);
+        out_lo[3 * oa + d] = l[d];
+        out_hi[3 * oa + d] = d == sd ? mid : h[d];
+        out_lo[3 * ob + d] = d == sd ? mid : l[d];
+        out_hi[3 * ob + d] = h[d];
+    }
+    if (qid) { out_qid[oa] = qid[i]; out_qid[ob] = qid[i]; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// find_any_intersection: per-node verdict (reference src/kd_tree.py:449-518)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool all_same_sign7(const float* v) {
+    bool neg = true, pos = true;
+    for (int k = 0; k < 7; ++k) { neg = neg && (v[k] < 0.f); pos = pos && (v[k] > 0.f); }
+    return neg || pos;
+}
+__device__ __forceinline__ void sample_point7(const float* lo, const float* hi, float s_or_neg, int k, float p[3]) {
+    for (int d = 0; d < 3; ++d) p[d] = 0.5f * (lo[d] + hi[d]);
+    if (k >= 1 && k <= 3) p[k - 1] = p[k - 1] + (s_or_neg >= 0.f ? s_or_neg : hi[k - 1] - lo[k - 1]);
+    if (k >= 4) p[k - 4] = p[k - 4] + (s_or_neg >= 0.f ? s_or_neg : hi[k - 4] - lo[k - 4]) * -1.f;
+}
+
+__global__ void k_isect_logic(const float* __restrict__ lo, const float* __restrict__ hi, long long n,
+                              const int* __restrict__ labA, const int* __restrict__ labB,
+                              const float* __restrict__ valsA, const float* __restrict__ valsB, float eps_w,
+                              int* __restrict__ needs, float* __restrict__ loc_out,
+                              unsigned long long* __restrict__ first_found) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* l = lo + 3 * i;
+    const float* h = hi + 3 * i;
+    const float* vA = valsA + 7 * i;
+    const float* vB = valsB + 7 * i;
+    const float width = fmaxf(fmaxf(h[0] - l[0], h[1] - l[1]), h[2] - l[2]);
+    const bool small = width < eps_w;
+    const bool nearA = small && !all_same_sign7(vA);
+    const bool nearB = small && !all_same_sign7(vB);
+    int iA = 0, iB = 0, iT = 0;
+    bool anyA = false, anyB = false, anyT = false;
+    for (int k = 6; k >= 0; --k) {
+        if (vA[k] < 0.f) { iA = k; anyA = true; }
+        if (vB[k] < 0.f) { iB = k; anyB = true; }
+        if (vA[k] < 0.f && vB[k] < 0.f) { iT = k; anyT = true; }
+    }
+    bool found = false;
+    float loc[3] = {-777.f, -777.f, -777.f};
+    if (small && anyA && anyB) {
+        float pa[3], pb[3];
+        sample_point7(l, h, eps_w, iA, pa);
+        sample_point7(l, h, eps_w, iB, pb);
+        for (int d = 0; d < 3; ++d) loc[d] = 0.5f * (pa[d] + pb[d]);
+        found = true;
+    }
+    if (anyT) {
+        sample_point7(l, h, eps_w, iT, loc);
+        found = true;
+    }
+    const bool insideA = labA[i] == SIGN_NEGATIVE || (labA[i] == SIGN_UNKNOWN && !nearA);
+    const bool insideB = labB[i] == SIGN_NEGATIVE || (labB[i] == SIGN_UNKNOWN && !nearB);
+    needs[i] = (insideA && insideB) ? 1 : 0;
+    if (found) {
+        for (int d = 0; d < 3; ++d) loc_out[3 * i + d] = loc[d];
+        atomicMin(first_found, (unsigned long long)i);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// closest_point: one round over the popped window (reference src/kd_tree.py:679-760)
+// ------------------------------------------------------------------------------------------------
+struct CpRound {
+    const float* stack_lo; const float* stack_hi; const long long* stack_qid;   // global LIFO stack
+    long long* top;                 // device scalar
+    long long window;               // B
+    const float* query; float* min_dist; float* min_loc; unsigned long long* winner;
+    long long n_query;
+    const int* label; const unsigned char* tie; const float* vals;   // window-indexed results of classify / 7 samples
+    float eps_w;
+    unsigned long long round;
+    // scratch (window sized)
+    float* this_dist; float* center; int* needs;
+    long long* stats;               // [1] node visits
+};
+
+__global__ void k_cp_eval(CpRound r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.window) return;
+    const long long top = *r.top;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const bool valid = i < top;                         // reference :685 (arange(B) < stack_top)
+    const long long s = pop + i;
+    const float* l = r.stack_lo + 3 * s;
+    const float* h = r.stack_hi + 3 * s;
+    long long qid = r.stack_qid[s];
+    if (!valid || qid < 0 || qid >= r.n_query) qid = 0;  // stale entries: keep gathers in range
+    const float* q = r.query + 3 * qid;
+    const float ex = h[0] - l[0], ey = h[1] - l[1], ez = h[2] - l[2];
+    const float width = fmaxf(fmaxf(ex, ey), ez);
+    const float cx = 0.5f * (l[0] + h[0]), cy = 0.5f * (l[1] + h[1]), cz = 0.5f * (l[2] + h[2]);
+    const float off = sqrtf((ex * ex + ey * ey) + ez * ez);
+    const float qx = q[0] - cx, qy = q[1] - cy, qz = q[2] - cz;
+    const float dc = sqrtf((qx * qx + qy * qy) + qz * qz);
+    const bool small = width < r.eps_w;
+    const int lab = r.label[i];
+    const bool outside = lab == SIGN_NEGATIVE || lab == SIGN_POSITIVE;
+    const bool spans = !all_same_sign7(r.vals + 7 * i) && valid;
+    const float snap = r.min_dist[qid];                  // snapshot before this round's scatter-min (:684)
+    r.this_dist[i] = spans ? dc + off : __int_as_float(0x7f800000);
+    r.needs[i] = (valid && !outside && !small && dc < snap) ? 1 : 0;
+    r.center[3 * i] = cx; r.center[3 * i + 1] = cy; r.center[3 * i + 2] = cz;
+    if (valid && r.stats) {
+        atomicAdd((unsigned long long*)&r.stats[1], 1ull);
+        if (r.tie && r.tie[i]) atomicAdd((unsigned long long*)&r.stats[2], 1ull);
+    }
+}
+__global__ void k_cp_min(CpRound r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.window) return;
+    const long long top = *r.top;
+    if (i >= top) return;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const long long qid = r.stack_qid[pop + i];
+    atomicMin(reinterpret_cast<int*>(r.min_dist + qid), __float_as_int(r.this_dist[i]));   // dist >= 0
+}
+__global__ void k_cp_winner(CpRound r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.window) return;
+    const long long top = *r.top;
+    if (i >= top) return;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const long long qid = r.stack_qid[pop + i];
+    if (r.this_dist[i] == r.min_dist[qid]) atomicMax(&r.winner[qid], r.round * (unsigned long long)r.window + i + 1);
+}
+__global__ void k_cp_loc(CpRound r) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.window) return;
+    const long long top = *r.top;
+    if (i >= top) return;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const long long qid = r.stack_qid[pop + i];
+    if (r.this_dist[i] == r.min_dist[qid] &&
+        r.winner[qid] == r.round * (unsigned long long)r.window + i + 1) {
+        for (int d = 0; d < 3; ++d) r.min_loc[3 * qid + d] = r.center[3 * i + d];
+    }
+}
+// children of the window's surviving nodes go back on the stack at pop + 2*rank (interleaved); the window
+// is first copied aside (tmp_*) because source and destination ranges overlap.
+__global__ void k_cp_copy_window(CpRound r, float* tmp_lo, float* tmp_hi, long long* tmp_qid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.window) return;
+    const long long top = *r.top;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const long long s = pop + i;
+    for (int d = 0; d < 3; ++d) { tmp_lo[3 * i + d] = r.stack_lo[3 * s + d]; tmp_hi[3 * i + d] = r.stack_hi[3 * s + d]; }
+    tmp_qid[i] = r.stack_qid[s];
+}
+__global__ void k_cp_push(CpRound r, const float* tmp_lo, const float* tmp_hi, const long long* tmp_qid,
+                          const int* scan, float* stack_lo, float* stack_hi, long long* stack_qid) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r.window || !r.needs[i]) return;
+    const long long top = *r.top;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const float* l = tmp_lo + 3 * i;
+    const float* h = tmp_hi + 3 * i;
+    const long long oa = pop + 2ll * scan[i], ob = oa + 1;
+    const int sd = argmax3_first(h[0] - l[0], h[1] - l[1], h[2] - l[2]);
+    for (int d = 0; d < 3; ++d) {
+        const float mid = 0.5f * (l[d] + h[d]);
+        stack_lo[3 * oa + d] = l[d];
+        stack_hi[3 * oa + d] = d == sd ? mid : h[d];
+        stack_lo[3 * ob + d] = d == sd ? mid : l[d];
+        stack_hi[3 * ob + d] = h[d];
+    }
+    stack_qid[oa] = tmp_qid[i];
+    stack_qid[ob] = tmp_qid[i];
+}
+__global__ void k_cp_advance(CpRound r, const int* scan, long long* max_top) {
+    const long long top = *r.top;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const long long nt = pop + 2ll * scan[r.window];
+    *r.top = nt;
+    if (nt > *max_top) *max_top = nt;
+    if (top > 0 && r.stats) r.stats[0] += 1;             // rounds that did work
+}
+
+// ------------------------------------------------------------------------------------------------
+// marching cubes over leaves (reference src/extract_cell.py:314-421, src/kd_tree.py:338-355)
+// ------------------------------------------------------------------------------------------------
+__constant__ unsigned long long c_mc_case_words[256] = NIQ_MC_CASE_WORDS_INIT;
+
+struct McArgs {
+    const float* leaf_lo; const float* leaf_hi; const float* vals;   // vals: (L, P, P, P)
+    long long n_leaves;
+    int n_side;            // 2^n_sub_depth subcells per axis
+};
+
+__device__ __forceinline__ int mc_case(const McArgs& a, long long leaf, int s, float vv[8], int ijk[3]) {
+    const int n = a.n_side, P = n + 1;
+    ijk[2] = s % n; ijk[1] = (s / n) % n; ijk[0] = s / (n * n);
+    const float* v = a.vals + leaf * (long long)(P * P * P);
+    int id = 0;
+    for (int k = 0; k < 8; ++k) {
+        const int ox = (NIQ_MC_VERT_MASK_X >> k) & 1, oy = (NIQ_MC_VERT_MASK_Y >> k) & 1,
+                  oz = (NIQ_MC_VERT_MASK_Z >> k) & 1;
+        vv[k] = v[((ijk[0] + ox) * P + (ijk[1] + oy)) * P + (ijk[2] + oz)];
+        id |= (vv[k] < 0.f) << k;
+    }
+    return id;
+}
+__device__ __forceinline__ int mc_ntri(unsigned long long word) {
+    int nt = 0;
+    for (int s = 0; s < 5; ++s) nt += ((word >> (12 * s)) & 0xF) != 0xF;   // slot valid iff its first entry != -1
+    return nt;
+}
+
+// one CTA per leaf: count triangles
+__global__ void __launch_bounds__(kScanThreads) k_mc_count(McArgs a, int* __restrict__ leaf_count) {
+    const long long leaf = blockIdx.x;
+    const int S = a.n_side * a.n_side * a.n_side;
+    int cnt = 0;
+    for (int s = threadIdx.x; s < S; s += blockDim.x) {
+        float vv[8]; int ijk[3];
+        cnt += mc_ntri(c_mc_case_words[mc_case(a, leaf, s, vv, ijk)]);
+    }
+    int total;
+    block_exclusive_scan(cnt, &total);
+    if (threadIdx.x == 0) leaf_count[leaf] = total;
+}
+
+// one CTA per leaf: write its triangles at leaf_off[leaf], in (subcell, slot) order
+__global__ void __launch_bounds__(kScanThreads) k_mc_write(McArgs a, const int* __restrict__ leaf_off,
+                                                           float* __restrict__ tri_out) {
+    const long long leaf = blockIdx.x;
+    const int n = a.n_side, S = n * n * n;
+    const float* clo = a.leaf_lo + 3 * leaf;
+    const float* chi = a.leaf_hi + 3 * leaf;
+    float delta[3];
+    for (int d = 0; d < 3; ++d) delta[d] = (chi[d] - clo[d]) / (float)n;
+    long long carry = leaf_off[leaf];
+    for (int s0 = 0; s0 < S; s0 += blockDim.x) {
+        const int s = s0 + threadIdx.x;
+        float vv[8]; int ijk[3];
+        unsigned long long word = ~0ull;
+        if (s < S) word = c_mc_case_words[mc_case(a, leaf, s, vv, ijk)];
+        const int nt = s < S ? mc_ntri(word) : 0;
+        int total;
+        const int off = block_exclusive_scan(nt, &total);
+        if (nt > 0) {
+            float slo[3], shi[3];
+            for (int d = 0; d < 3; ++d) {
+                slo[d] = clo[d] + (float)ijk[d] * delta[d];
+                shi[d] = slo[d] + delta[d];
+            }
+            float* dst = tri_out + (carry + off) * 9;
+            int w = 0;
+            for (int slot = 0; slot < 5; ++slot) {
+                if (((word >> (12 * slot)) & 0xF) == 0xF) continue;     // validity = first entry of the slot
+                for (int c = 0; c < 3; ++c) {
+                    int e = (int)((word >> (12 * slot + 4 * c)) & 0xF);
+                    if (e == 0xF) e = 0;                                 // jnp.clip(tri, a_min=0)
+                    const int ia = (int)((NIQ_MC_EDGE_A_NIBBLES >> (4 * e)) & 0xF);
+                    const int ib = (int)((NIQ_MC_EDGE_B_NIBBLES >> (4 * e)) & 0xF);
+                    const float va = vv[ia], vb = vv[ib];
+                    float tc = -va / (vb - va);
+                    if (tc != tc) tc = 0.f;                              // nan_to_num, then clip to [0,1]
+                    tc = fminf(fmaxf(tc, 0.f), 1.f);
+                    const unsigned mx[3] = {NIQ_MC_VERT_MASK_X, NIQ_MC_VERT_MASK_Y, NIQ_MC_VERT_MASK_Z};
+                    for (int d = 0; d < 3; ++d) {
+                        const float pa = ((mx[d] >> ia) & 1) ? shi[d] : slo[d];
+                        const float pb = ((mx[d] >> ib) & 1) ? shi[d] : slo[d];
+                        dst[w * 9 + c * 3 + d] = (1.f - tc) * pa + tc * pb;
+                    }
+                }
+                ++w;
+            }
+        }
+        carry += total;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP32 FFMA peak probe (register-only, 8 independent chains per thread)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float a, float b) {
+    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    float y0 = x0, y1 = x1, y2 = x2, y3 = x3, y4 = x4, y5 = x5, y6 = x6, y7 = x7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
+            x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
+            y0 = fmaf(y0, a, b); y1 = fmaf(y1, a, b); y2 = fmaf(y2, a, b); y3 = fmaf(y3, a, b);
+            y4 = fmaf(y4, a, b); y5 = fmaf(y5, a, b); y6 = fmaf(y6, a, b); y7 = fmaf(y7, a, b);
+        }
+    }
+    const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7)) + ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
+    if (s == 12345.678f) out[0] = s;
+}
+
+}  // namespace niq

@@ -1,0 +1,393 @@
+"""CPU oracle, part 1: MLP dict format, point evaluation and affine / interval bound propagation.
+
+TEST INFRASTRUCTURE ONLY.  This is a float32 NumPy restatement of the reference's range-analysis
+core, with an explicit leading batch axis in place of `jax.vmap`.  Only tests/, __graft_entry__.smoke()
+and bench.py's cpu_baseline / --impl reference legs may import it; the product never does.
+
+Pinning: the reference ships no tests or golden vectors.  This restatement is pinned against the
+UNMODIFIED reference sources executed on a NumPy-backed `jax` stand-in (oracle/jaxshim, run by
+oracle/tools/gen_golden.py in the build container) -- see tests/golden/README.md.  Real JAX/XLA is not
+installable here, so XLA's own reduction order is not reproduced ("parity pinned to the reference's
+Python code, not to XLA bits").
+
+Reference files followed (all under /root/reference/src):
+  mlp.py:96-144 (op-list interpreter, key grammar), :149-167 (prepend_op), :173-185 (load),
+  mlp.py:253-347 (point-evaluation rules), affine.py:85-193, affine_layers.py:11-97,164-179,
+  implicit_function.py:28-37.
+"""
+from dataclasses import dataclass
+
+import numpy as np
+
+F32 = np.float32
+
+SIGN_UNKNOWN = 0   # implicit_function.py:11-13
+SIGN_POSITIVE = 1
+SIGN_NEGATIVE = 2
+
+MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all")
+
+
+# ----------------------------------------------------------------------------------------------
+# params dict format  (mlp.py:14-24, 117-167, 173-185)
+# ----------------------------------------------------------------------------------------------
+
+def load_npz(path):
+    """mlp.py:173-185 -- npz -> {key: float32 array}; no conversion beyond np.asarray."""
+    out = {}
+    with np.load(path) as data:
+        for key in data.files:
+            out[key] = np.asarray(data[key])
+    return out
+
+
+def n_ops(params):
+    """mlp.py:134-144"""
+    n = 0
+    for key in params:
+        head = key.split(".")[0]
+        try:
+            i_op = int(head)
+        except ValueError:
+            raise ValueError(f"Could not parse out key {key}. Is this a valid mlp spec?")
+        n = max(n, i_op + 1)
+    return n
+
+
+def op_list(params):
+    """Ordered [(name, {arg: array})] following mlp.py:117-131 (prefix match on the 4-digit index,
+    op name = token 1, arg = token 2, the '_' placeholder dropped as in :108-109)."""
+    ops = []
+    for i_op in range(n_ops(params)):
+        prefix = f"{i_op:04d}"
+        name, args = "", {}
+        for key in params:
+            if key.startswith(prefix):
+                tok = key.split(".")
+                name = tok[1]
+                if len(tok) > 2:
+                    args[tok[2]] = params[key]
+        if name == "":
+            raise ValueError(f"didn't find op {i_op}")
+        args.pop("_", None)
+        ops.append((name, args))
+    return ops
+
+
+def prepend_op(params, op):
+    """mlp.py:149-167"""
+    new = {}
+    for key, val in params.items():
+        tok = key.split(".")
+        tok[0] = f"{int(tok[0]) + 1:04d}"
+        new[".".join(tok)] = val
+    for key, val in op.items():
+        new["0000." + key] = val
+    return new
+
+
+def spatial_transformation(R=None, t=None):
+    """mlp.py:335-340 -- identity transform op dict (R, t optional overrides)."""
+    return {"spatial_transformation.R": np.eye(3, dtype=F32) if R is None else np.asarray(R, F32),
+            "spatial_transformation.t": np.zeros(3, dtype=F32) if t is None else np.asarray(t, F32)}
+
+
+def _spatial_as_dense(R, t):
+    """affine_layers.py:175-179 / mlp.py:342-346: A = inv(R) used as x @ A, b = inv(R) @ (-t)."""
+    R = np.asarray(R, F32)
+    t = np.asarray(t, F32)
+    R_inv = np.linalg.inv(R).astype(F32)
+    t_inv = (R_inv @ (-t)).astype(F32)
+    return R_inv, t_inv
+
+
+def random_mlp(layer_sizes, activation="relu", seed=0):
+    """Synthetic MLP of the shape `mlp.quick_mlp_spec` builds (mlp.py:73-94), initialised with the
+    distributions of `mlp.initialize_dense` (mlp.py:260-277): glorot-normal A, b ~ N(0, 1e-2^2).
+    NumPy's generator replaces the JAX PRNG: same distribution, not the same bits."""
+    rng = np.random.default_rng(seed)
+    params = {}
+    i_op = 0
+    for i in range(len(layer_sizes) - 1):
+        d_in, d_out = layer_sizes[i], layer_sizes[i + 1]
+        std = np.sqrt(2.0 / (d_in + d_out))
+        params[f"{i_op:04d}.dense.A"] = (rng.standard_normal((d_in, d_out)) * std).astype(F32)
+        params[f"{i_op:04d}.dense.b"] = (rng.standard_normal((d_out,)) * 1e-2).astype(F32)
+        i_op += 1
+        if i + 2 != len(layer_sizes):
+            params[f"{i_op:04d}.{activation}._"] = np.zeros((0,), F32)
+            i_op += 1
+    params[f"{i_op:04d}.squeeze_last._"] = np.zeros((0,), F32)
+    return params
+
+
+# ----------------------------------------------------------------------------------------------
+# point evaluation (mlp.py 'default' rules)
+# ----------------------------------------------------------------------------------------------
+
+def _elu(x):
+    # jax.nn.elu: where(x > 0, x, expm1(where(x > 0, 0, x)))
+    safe = np.where(x > 0, F32(0), x)
+    return np.where(x > 0, x, np.expm1(safe)).astype(F32)
+
+
+def eval_points(params, x):
+    """f(x) for x of shape (N,3) -> (N,) float32.  mlp.py:99-111 with the 'default' rules
+    (dense :253-258, relu :283-287, elu :289-293, squeeze_last :328-332, spatial :342-346)."""
+    h = np.ascontiguousarray(x, dtype=F32)
+    for name, args in op_list(params):
+        if name == "dense":
+            h = h @ np.asarray(args["A"], F32)
+            if "b" in args and args["b"] is not None:
+                h = h + np.asarray(args["b"], F32)
+        elif name == "spatial_transformation":
+            A, b = _spatial_as_dense(args["R"], args["t"])
+            h = h @ A + b
+        elif name == "relu":
+            h = np.maximum(h, F32(0))
+        elif name == "elu":
+            h = _elu(h)
+        elif name == "squeeze_last":
+            assert h.shape[-1] == 1
+            h = h[..., 0]
+        else:
+            raise ValueError(f"oracle: unsupported op '{name}'")
+        h = h.astype(F32, copy=False)
+    return h
+
+
+# ----------------------------------------------------------------------------------------------
+# affine arithmetic (affine.py, affine_layers.py)
+# ----------------------------------------------------------------------------------------------
+
+@dataclass(frozen=True)
+class AffineContext:
+    """affine.py:62-76"""
+    mode: str = "affine_fixed"
+    truncate_count: int = -777
+    truncate_policy: str = "absolute"
+
+    def __post_init__(self):
+        if self.mode not in ("interval", "affine_fixed", "affine_truncate", "affine_append", "affine_all"):
+            raise ValueError("invalid mode")
+        if self.mode == "affine_truncate" and self.truncate_count is None:
+            raise ValueError("must specify truncate count")
+        if self.mode == "affine_append":
+            raise ValueError("oracle: affine_append is outside the hot-path scope")
+
+
+def _radius(aff, err):
+    """affine.py:85-91 -- sum_r |aff_r| + err, batched: aff (N,k,w), err (N,w)."""
+    return (np.abs(aff).sum(axis=1, dtype=F32) + err).astype(F32)
+
+
+def _truncate(ctx, base, aff, err):
+    """affine.py:127-162, 'absolute' policy, stable descending sort by row L1 norm."""
+    if ctx.mode != "affine_truncate":
+        return base, aff, err
+    n_keep = ctx.truncate_count
+    if aff.shape[1] <= n_keep:
+        return base, aff, err
+    if ctx.truncate_policy != "absolute":
+        # affine.py:146 divides (k,) by (w,): only shape-valid by accident, used by no caller
+        raise RuntimeError("oracle: only the 'absolute' truncate policy is supported")
+    mags = np.abs(aff).sum(axis=-1, dtype=F32)                       # (N,k)
+    order = np.argsort(-mags, axis=-1, kind="stable")                # (N,k)
+    aff = np.take_along_axis(aff, order[:, :, None], axis=1)
+    keep, drop = aff[:, :n_keep, :], aff[:, n_keep:, :]
+    err = (err + np.abs(drop).sum(axis=1, dtype=F32)).astype(F32)
+    return base, np.ascontiguousarray(keep), err
+
+
+def _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta):
+    """affine.py:164-193 (modes interval / affine_fixed / affine_truncate / affine_all)."""
+    base = (alpha * base + beta).astype(F32)
+    aff = (alpha[:, None, :] * aff).astype(F32)
+    delta = np.abs(delta)
+    if ctx.mode in ("interval", "affine_fixed"):
+        err = (alpha * err + delta).astype(F32)
+    else:
+        err = (alpha * err).astype(F32)
+        n, w = delta.shape
+        new_aff = np.zeros((n, w, w), F32)
+        idx = np.arange(w)
+        new_aff[:, idx, idx] = delta
+        aff = np.concatenate((aff, new_aff), axis=1)
+        base, aff, err = _truncate(ctx, base, aff, err)
+    return base, aff, err
+
+
+def _relu_rule(ctx, base, aff, err):
+    """affine_layers.py:34-56"""
+    rad = _radius(aff, err)
+    lower, upper = base - rad, base + rad
+    with np.errstate(divide="ignore", invalid="ignore"):
+        alpha = (np.maximum(upper, F32(0)) - np.maximum(lower, F32(0))) / (upper - lower)
+    alpha = np.where(lower >= 0, F32(1), alpha)
+    alpha = np.where(upper < 0, F32(0), alpha)
+    alpha = np.nan_to_num(alpha, nan=0.0).astype(F32)
+    alpha = np.clip(alpha, F32(0), F32(1))
+    beta = ((np.maximum(lower, F32(0)) - alpha * lower) / F32(2)).astype(F32)
+    return _apply_linear_approx(ctx, base, aff, err, alpha, beta, beta)
+
+
+def _elu_rule(ctx, base, aff, err):
+    """affine_layers.py:59-97"""
+    rad = _radius(aff, err)
+    lower, upper = base - rad, base + rad
+    lowerF, upperF = _elu(lower), _elu(upper)
+    with np.errstate(over="ignore", divide="ignore", invalid="ignore"):
+        lowerS = np.minimum(np.exp(lower), F32(1))
+        upperS = np.minimum(np.exp(upper), F32(1))
+        alpha = (upperF - lowerF) / (upper - lower)
+        alpha = np.where(lower >= 0, F32(1), alpha)
+        alpha = np.nan_to_num(alpha, nan=0.0).astype(F32)
+        alpha = np.minimum(np.maximum(alpha, lowerS), upperS)       # jnp.clip(a_min, a_max)
+        r_upper = lowerF - alpha * lower
+        x_lower = np.minimum(np.maximum(np.log(alpha), lower), upper)
+        r_lower = (alpha - F32(1)) - alpha * x_lower
+    beta = F32(0.5) * (r_upper + r_lower)
+    delta = F32(0.5) * np.abs(r_upper - r_lower)
+    pos = lower >= 0
+    alpha = np.where(pos, F32(1), alpha).astype(F32)
+    beta = np.where(pos, F32(0), beta).astype(F32)
+    delta = np.where(pos, F32(0), delta).astype(F32)
+    return _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta)
+
+
+def _dense_rule(base, aff, err, A, b):
+    """affine_layers.py:11-31 -- base@A+b, every aff row @A, err@|A|."""
+    A = np.asarray(A, F32)
+    base = base @ A
+    aff = np.matmul(aff, A)
+    err = err @ np.abs(A)
+    if b is not None:
+        base = base + np.asarray(b, F32)
+    return base.astype(F32), aff.astype(F32), err.astype(F32)
+
+
+def affine_forward(params, ctx, center, vecs):
+    """Propagate the affine form of a general box through the op list.
+
+    center (N,3), vecs (N,v,3)  ->  base (N,), aff (N,k), err (N,) of the scalar output, plus `scale`
+    (N,) = sum_j |base_j A_j| + |b| of the last dense layer (ours: the magnitude of what the output was
+    summed from, used as the yardstick of tolerances and near-tie bands).
+    affine.py:109-117 (input form), mlp.py:99-111 with the 'affine' rules.
+    """
+    center = np.ascontiguousarray(center, F32)
+    vecs = np.ascontiguousarray(vecs, F32)
+    n = center.shape[0]
+    base = center
+    if ctx.mode == "interval":
+        aff = np.zeros((n, 0, center.shape[-1]), F32)
+        err = np.abs(vecs).sum(axis=1, dtype=F32)
+    else:
+        aff = vecs
+        err = np.zeros_like(center)
+    ops = op_list(params)
+    last_dense = max(i for i, (nm, _) in enumerate(ops) if nm == "dense")
+    scale = None
+    for i_op, (name, args) in enumerate(ops):
+        if name == "dense":
+            if i_op == last_dense:
+                A = np.asarray(args["A"], F32)
+                scale = (np.abs(base)[:, :, None] * np.abs(A)[None, :, :]).sum(axis=1, dtype=F32)
+                if args.get("b") is not None:
+                    scale = scale + np.abs(np.asarray(args["b"], F32))
+                scale = scale.max(axis=-1).astype(F32)
+            base, aff, err = _dense_rule(base, aff, err, args["A"], args.get("b"))
+        elif name == "spatial_transformation":
+            A, b = _spatial_as_dense(args["R"], args["t"])
+            base, aff, err = _dense_rule(base, aff, err, A, b)
+        elif name == "relu":
+            base, aff, err = _relu_rule(ctx, base, aff, err)
+        elif name == "elu":
+            base, aff, err = _elu_rule(ctx, base, aff, err)
+        elif name == "squeeze_last":
+            assert base.shape[-1] == 1
+            base, aff, err = base[:, 0], aff[:, :, 0], err[:, 0]
+        else:
+            raise ValueError(f"oracle: unsupported op '{name}'")
+    return base, aff, err, scale
+
+
+def bound_general_box(params, ctx, center, vecs, chunk=None, return_scale=False):
+    """-> (lower, upper[, scale]) float32 (N,): affine.py:119-125 applied to the propagated output."""
+    center = np.ascontiguousarray(center, F32)
+    vecs = np.ascontiguousarray(vecs, F32)
+    n = center.shape[0]
+    if chunk is None:
+        chunk = 65536 if ctx.mode in ("interval", "affine_fixed") else 1024
+    lower = np.empty(n, F32)
+    upper = np.empty(n, F32)
+    scale = np.empty(n, F32)
+    for s in range(0, n, chunk):
+        base, aff, err, sc = affine_forward(params, ctx, center[s:s + chunk], vecs[s:s + chunk])
+        rad = (np.abs(aff).sum(axis=1, dtype=F32) + err).astype(F32)
+        lower[s:s + chunk] = base - rad
+        upper[s:s + chunk] = base + rad
+        scale[s:s + chunk] = sc
+    if return_scale:
+        return lower, upper, scale
+    return lower, upper
+
+
+def labels_from_bounds(lower, upper, offset=0.0):
+    """affine.py:49-53: POSITIVE if lower > offset, then NEGATIVE if upper < -offset (wins)."""
+    offset = F32(offset)
+    out = np.full(lower.shape, SIGN_UNKNOWN, np.int32)
+    out = np.where(lower > offset, SIGN_POSITIVE, out)
+    out = np.where(upper < -offset, SIGN_NEGATIVE, out)
+    return out.astype(np.int32)
+
+
+def classify_general_box(params, ctx, center, vecs, offset=0.0, return_bounds=False, return_scale=False):
+    """affine.py:34-55, batched over N boxes."""
+    lower, upper, scale = bound_general_box(params, ctx, center, vecs, return_scale=True)
+    lab = labels_from_bounds(lower, upper, offset)
+    if return_scale:
+        return lab, lower, upper, scale
+    return (lab, lower, upper) if return_bounds else lab
+
+
+def box_to_general(lo, hi):
+    """implicit_function.py:28-37: centre = 0.5*(lo+hi), vecs = diag(hi - centre)."""
+    lo = np.asarray(lo, F32)
+    hi = np.asarray(hi, F32)
+    center = (F32(0.5) * (lo + hi)).astype(F32)
+    half = (hi - center).astype(F32)
+    vecs = np.zeros(lo.shape[:-1] + (3, 3), F32)
+    for i in range(3):
+        vecs[..., i, i] = half[..., i]
+    return center, vecs
+
+
+def classify_box(params, ctx, lo, hi, offset=0.0, return_bounds=False, return_scale=False):
+    center, vecs = box_to_general(lo, hi)
+    return classify_general_box(params, ctx, center, vecs, offset, return_bounds, return_scale)
+
+
+# ----------------------------------------------------------------------------------------------
+# near-tie bands (ours, not the reference's): which decisions are within float32 summation noise
+# ----------------------------------------------------------------------------------------------
+
+NEAR_TIE_REL = 1e-5
+
+
+def tol_scale(lower, upper, scale=None):
+    """Yardstick of a bound: |base| + rad (= max(|lower|,|upper|)) plus, when given, the magnitude the
+    output was summed from (sum_j |base_j A_j| + |b| of the last layer).  float32 summation-order noise
+    is a few ulp of THIS, not of the (possibly cancelled) bound itself."""
+    s = np.maximum(np.abs(lower.astype(np.float64)), np.abs(upper.astype(np.float64)))
+    if scale is not None:
+        s = s + scale.astype(np.float64)
+    return s
+
+
+def bound_near_tie(lower, upper, offset=0.0, scale=None, rel=NEAR_TIE_REL):
+    """A box is 'near-tie' when either threshold test sits within rel*tol_scale of flipping
+    (BASELINE.json north_star: such boxes are counted and excluded from the bit-exact label check)."""
+    s = tol_scale(lower, upper, scale)
+    lower = lower.astype(np.float64)
+    upper = upper.astype(np.float64)
+    return (np.abs(lower - offset) <= rel * s) | (np.abs(upper + offset) <= rel * s)

@@ -1,0 +1,275 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference sources on the NumPy `jax` stand-in.
+
+Build-container only (reads /root/reference; needs oracle/jaxshim).  Usage:
+
+    python oracle/tools/gen_golden.py [case ...]        # default: all cases, in parallel
+
+Every case stores its inputs and the reference's outputs; tests/test_oracle_golden.py replays the inputs
+through oracle/niq_oracle and compares.  Cases are small because the stand-in executes `vmap` as a
+Python loop.  The weights come from /root/reference/sample_inputs/*.npz, which are NOT copied: tests
+that need them on the GPU box use tests/golden/mlps.npz (written here: the four sample MLPs'
+arrays under '<name>/<key>' keys, 96k floats in total) -- fixtures derived from the reference inputs.
+"""
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+GOLD = os.path.join(ROOT, "tests", "golden")
+REF = "/root/reference"
+SAMPLES = ("fox", "bunny", "hammer", "birdcage_occ")
+
+
+def _ref_modules():
+    sys.path[:0] = [os.path.join(ROOT, "oracle", "jaxshim"), os.path.join(ROOT, "oracle", "jaxshim", "stubs"),
+                    os.path.join(REF, "src")]
+    import jax  # noqa: F401  (the stand-in)
+    import jax.numpy as jnp
+    import affine
+    import implicit_mlp_utils
+    import kd_tree
+    import mlp
+    import queries
+    import render
+    return dict(jnp=jnp, affine=affine, imu=implicit_mlp_utils, kd_tree=kd_tree, mlp=mlp, queries=queries,
+                render=render)
+
+
+def _load(m, name, mode, **kw):
+    return m["imu"].generate_implicit_from_file(f"{REF}/sample_inputs/{name}.npz", mode, **kw)
+
+
+def _mode_kwargs(mode, n_trunc):
+    if mode == "affine_truncate":
+        return dict(affine_n_truncate=n_trunc, affine_truncate_policy="absolute")
+    return {}
+
+
+def _boxes(seed, n_per_scale=3, scales=range(0, 11)):
+    rng = np.random.default_rng(seed)
+    lo, hi = [], []
+    for s in scales:
+        half = np.float32(2.0 ** (-s))
+        c = rng.uniform(-1, 1, (n_per_scale, 3)).astype(np.float32) * np.float32(1.0 - 0.5 * half)
+        h = (half * rng.uniform(0.5, 1.0, (n_per_scale, 3))).astype(np.float32)
+        lo.append(c - h)
+        hi.append(c + h)
+    return np.concatenate(lo).astype(np.float32), np.concatenate(hi).astype(np.float32)
+
+
+# ------------------------------------------------------------------------------------------------
+
+def case_mlps():
+    out = {}
+    for name in SAMPLES:
+        with np.load(f"{REF}/sample_inputs/{name}.npz") as d:
+            for k in d.files:
+                out[f"{name}/{k}"] = d[k]
+    return out
+
+
+def case_classify(name, mode, n_trunc=8):
+    """labels + bounds of axis-aligned boxes (v=3), ray segments (v=1), an offset, and a rigid transform."""
+    m = _ref_modules()
+    jnp, affine = m["jnp"], m["affine"]
+    func, params = _load(m, name, mode, **_mode_kwargs(mode, n_trunc))
+    import zlib
+    lo, hi = _boxes(seed=zlib.crc32(f"{name}-{mode}".encode()) % 1000)
+    out = dict(box_lower=lo, box_upper=hi, n_trunc=n_trunc)
+
+    def bounds(params, center, vecs):
+        import dataclasses
+        ctx = dataclasses.replace(func.ctx, affine_domain_terms=vecs.shape[0])
+        inp = affine.coordinates_in_general_box(ctx, center, vecs)
+        res = func.affine_func(params, inp, {"ctx": ctx})
+        return affine.may_contain_bounds(ctx, res)
+
+    lab, lb, ub = [], [], []
+    lab_off = []
+    for i in range(lo.shape[0]):
+        l, u = jnp.array(lo[i]), jnp.array(hi[i])
+        lab.append(int(func.classify_box(params, l, u)))
+        lab_off.append(int(func.classify_box(params, l, u, offset=0.05)))
+        c = 0.5 * (l + u)
+        b = bounds(params, c, jnp.diag(u - c))
+        lb.append(float(b[0]))
+        ub.append(float(b[1]))
+    out.update(label=np.array(lab, np.int32), label_offset005=np.array(lab_off, np.int32),
+               lower=np.array(lb, np.float32), upper=np.array(ub, np.float32))
+
+    # v = 1 general boxes (ray segments)
+    rng = np.random.default_rng(7)
+    cen = rng.uniform(-1, 1, (12, 3)).astype(np.float32)
+    vec = (rng.standard_normal((12, 1, 3)) * (2.0 ** -rng.integers(0, 8, (12, 1, 1)))).astype(np.float32)
+    glab, glb, gub = [], [], []
+    for i in range(cen.shape[0]):
+        glab.append(int(func.classify_general_box(params, jnp.array(cen[i]), jnp.array(vec[i]))))
+        b = bounds(params, jnp.array(cen[i]), jnp.array(vec[i]))
+        glb.append(float(b[0]))
+        gub.append(float(b[1]))
+    out.update(seg_center=cen, seg_vecs=vec, seg_label=np.array(glab, np.int32),
+               seg_lower=np.array(glb, np.float32), seg_upper=np.array(gub, np.float32))
+
+    # rigid transform prepended (mlp.prepend_op + spatial_transformation), first 9 boxes
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+    t = np.array([0.2, -0.1, 0.05], np.float32)
+    p2 = m["mlp"].prepend_op(params, m["mlp"].spatial_transformation())
+    p2["0000.spatial_transformation.R"] = jnp.array(R)
+    p2["0000.spatial_transformation.t"] = jnp.array(t)
+    tl, tlb, tub = [], [], []
+    for i in range(9, 18):
+        l, u = jnp.array(lo[i]), jnp.array(hi[i])
+        tl.append(int(func.classify_box(p2, l, u)))
+        c = 0.5 * (l + u)
+        b = bounds(p2, c, jnp.diag(u - c))
+        tlb.append(float(b[0]))
+        tub.append(float(b[1]))
+    pts = rng.uniform(-1, 1, (16, 3)).astype(np.float32)
+    out.update(xf_R=R, xf_t=t, xf_label=np.array(tl, np.int32), xf_lower=np.array(tlb, np.float32),
+               xf_upper=np.array(tub, np.float32), xf_points=pts,
+               xf_values=np.array([float(func(p2, jnp.array(x))) for x in pts], np.float32))
+    return out
+
+
+def case_points(name):
+    m = _ref_modules()
+    jnp = m["jnp"]
+    func, params = _load(m, name, "affine_fixed")
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, (64, 3)).astype(np.float32)
+    f = np.array([float(func(params, jnp.array(p))) for p in x], np.float32)
+    return dict(points=x, values=f)
+
+
+def case_cast_rays(names, mode, res, n_substeps=1, n_trunc=8):
+    m = _ref_modules()
+    jnp, queries, render = m["jnp"], m["queries"], m["render"]
+    funcs, params = [], []
+    for nm in names:
+        f, p = _load(m, nm, mode, **_mode_kwargs(mode, n_trunc))
+        funcs.append(f)
+        params.append(p)
+    eye = jnp.array((2.0, 1.0, 2.0))
+    look, up, left = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=res, fov_deg=30.0)
+    opts = queries.get_default_cast_opts()
+    opts["n_substeps"] = n_substeps
+    t, hit, cnt, n_evals = queries.cast_rays(tuple(funcs), tuple(params), roots, dirs, opts)
+    return dict(roots=np.array(roots), dirs=np.array(dirs), eye=np.array(eye), look=np.array(look),
+                up=np.array(up), res=res, n_substeps=n_substeps, n_trunc=n_trunc,
+                out_t=np.array(t, np.float32), out_hit_id=np.array(hit, np.int32),
+                out_count=np.array(cnt, np.int32), n_evals=int(n_evals))
+
+
+def case_tree(name, mode, n_trunc=8, **kw):
+    m = _ref_modules()
+    jnp, kd = m["jnp"], m["kd_tree"]
+    func, params = _load(m, name, mode, **_mode_kwargs(mode, n_trunc))
+    lower = jnp.array((-1.0, -1.0, -1.0))
+    upper = jnp.array((1.0, 1.0, 1.0))
+    d = kd.construct_uniform_unknown_levelset_tree(func, params, lower, upper, **kw)
+    out = {k: np.array(v) for k, v in d.items()}
+    out["n_trunc"] = n_trunc
+    for k, v in kw.items():
+        out["kw_" + k] = np.array(-1 if v is None else v)
+    return out
+
+
+def case_mc(name, mode, depth, n_sub):
+    m = _ref_modules()
+    jnp, kd = m["jnp"], m["kd_tree"]
+    func, params = _load(m, name, mode)
+    lower = jnp.array((-1.0, -1.0, -1.0))
+    upper = jnp.array((1.0, 1.0, 1.0))
+    tri = kd.hierarchical_marching_cubes(func, params, lower, upper, depth, n_subcell_depth=n_sub)
+    return dict(tri_pos=np.array(tri, np.float32), depth=depth, n_sub=n_sub)
+
+
+def case_intersection(mode, n_trunc, transforms, eps=1e-3):
+    m = _ref_modules()
+    jnp, kd, mlp = m["jnp"], m["kd_tree"], m["mlp"]
+    fA, pA = _load(m, "hammer", mode, **_mode_kwargs(mode, n_trunc))
+    fB, pB = _load(m, "bunny", mode, **_mode_kwargs(mode, n_trunc))
+    pB = mlp.prepend_op(pB, mlp.spatial_transformation())
+    lower = jnp.array((-1.0, -1.0, -1.0))
+    upper = jnp.array((1.0, 1.0, 1.0))
+    found, locs, Rs, ts = [], [], [], []
+    for th, t in transforms:
+        R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+        t = np.array(t, np.float32)
+        pB["0000.spatial_transformation.R"] = jnp.array(R)
+        pB["0000.spatial_transformation.t"] = jnp.array(t)
+        f, ia, ib, loc = kd.find_any_intersection((fA, fB), (pA, pB), lower, upper, eps)
+        found.append(bool(f))
+        locs.append(np.array(loc, np.float32))
+        Rs.append(R)
+        ts.append(t)
+    return dict(R=np.stack(Rs), t=np.stack(ts), found=np.array(found), loc=np.stack(locs), eps=eps, n_trunc=n_trunc)
+
+
+def case_closest(name, mode, Q, eps, B):
+    m = _ref_modules()
+    jnp, kd = m["jnp"], m["kd_tree"]
+    func, params = _load(m, name, mode)
+    lower = jnp.array((-1.0, -1.0, -1.0))
+    upper = jnp.array((1.0, 1.0, 1.0))
+    q = np.random.default_rng(0).uniform(-1, 1, (Q, 3)).astype(np.float32)
+    d, loc = kd.closest_point(func, params, lower, upper, jnp.array(q), eps=eps, batch_process_size=B)
+    return dict(query_points=q, dist=np.array(d, np.float32), loc=np.array(loc, np.float32), eps=eps, B=B)
+
+
+# ------------------------------------------------------------------------------------------------
+
+CASES = {"mlps": (case_mlps, ())}
+for _n in SAMPLES:
+    CASES[f"points_{_n}"] = (case_points, (_n,))
+    for _mode in ("interval", "affine_fixed", "affine_truncate", "affine_all"):
+        CASES[f"classify_{_n}_{_mode}"] = (case_classify, (_n, _mode))
+CASES["classify_hammer_affine_truncate64"] = (case_classify, ("hammer", "affine_truncate", 64))
+CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))
+CASES["rays_fox_interval_r6"] = (case_cast_rays, (("fox",), "interval", 6))
+CASES["rays_fox_all_r6"] = (case_cast_rays, (("fox",), "affine_all", 6))
+CASES["rays_fox_fixed_r8_sub3"] = (case_cast_rays, (("fox",), "affine_fixed", 8, 3))
+CASES["rays_fox_bunny_fixed_r8"] = (case_cast_rays, (("fox", "bunny"), "affine_fixed", 8))
+CASES["tree_fox_fixed_d12"] = (case_tree, ("fox", "affine_fixed"), dict(split_depth=12, with_interior_nodes=True, with_exterior_nodes=True))
+CASES["tree_bunny_all_d9"] = (case_tree, ("bunny", "affine_all"), dict(split_depth=9, with_interior_nodes=True, with_exterior_nodes=True))
+CASES["tree_fox_trunc_d9"] = (case_tree, ("fox", "affine_truncate"), dict(split_depth=9))
+CASES["tree_fox_fixed_thresh"] = (case_tree, ("fox", "affine_fixed"), dict(node_terminate_thresh=300, offset=0.02))
+CASES["tree_fox_fixed_b128"] = (case_tree, ("fox", "affine_fixed"), dict(split_depth=10, batch_process_size=128))
+CASES["mc_fox_d4_s2"] = (case_mc, ("fox", "affine_fixed", 4, 2))
+CASES["mc_bunny_d4_s3"] = (case_mc, ("bunny", "affine_fixed", 4, 3))
+CASES["isect_fixed"] = (case_intersection, ("affine_fixed", 0, [(0.3, (0.0, 0.1, 0.05)), (0.3, (1.2, 0.1, 0.05)), (0.3, (1.6, 0.1, 0.05)), (1.1, (0.9, -0.4, 0.3))]))
+CASES["isect_trunc64"] = (case_intersection, ("affine_truncate", 64, [(0.3, (1.2, 0.1, 0.05)), (0.3, (1.6, 0.1, 0.05))]))
+CASES["closest_fox_B32"] = (case_closest, ("fox", "affine_fixed", 6, 0.02, 32))
+CASES["closest_fox_Bbig"] = (case_closest, ("fox", "affine_fixed", 6, 0.02, 2 ** 20))
+
+
+def run(name):
+    t0 = time.time()
+    entry = CASES[name]
+    fn, args = entry[0], entry[1]
+    kw = entry[2] if len(entry) > 2 else {}
+    sys.stdout = open(os.devnull, "w")          # the reference prints per-level progress
+    try:
+        out = fn(*args, **kw)
+    finally:
+        sys.stdout = sys.__stdout__
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    return name, time.time() - t0
+
+
+def main():
+    names = sys.argv[1:] or list(CASES)
+    os.makedirs(GOLD, exist_ok=True)
+    with mp.Pool(min(8, len(names))) as pool:
+        for name, dt in pool.imap_unordered(run, names):
+            print(f"{name}: {dt:.1f}s", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,184 @@
+"""Pins the CPU oracle (oracle/niq_oracle) to the golden vectors produced by the UNMODIFIED reference
+sources run on the NumPy `jax` stand-in (oracle/tools/gen_golden.py).  CPU only.
+
+Tolerance (BASELINE.json north_star): labels / topology / verdicts exact outside a counted band of
+boxes whose bound lies within 1e-5 (relative) of the level set; values within 1e-5 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden, sample_params
+from niq_oracle import net, rays, tree
+
+RTOL = 1e-5
+SAMPLES = ("fox", "bunny", "hammer", "birdcage_occ")
+MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all")
+
+
+def ctx_for(mode, n_trunc):
+    return net.AffineContext(mode, truncate_count=int(n_trunc))
+
+
+def assert_bounds_close(lo, up, glo, gup, sc):
+    scale = net.tol_scale(glo, gup, sc)
+    assert np.all(np.abs(lo.astype(np.float64) - glo) <= RTOL * scale + 1e-30)
+    assert np.all(np.abs(up.astype(np.float64) - gup) <= RTOL * scale + 1e-30)
+
+
+def assert_labels(lab, glab, lo, up, sc, offset=0.0):
+    tie = net.bound_near_tie(lo, up, offset, sc)
+    bad = (lab != glab) & ~tie
+    assert not bad.any(), f"{bad.sum()} label mismatches outside the near-tie band"
+
+
+@pytest.mark.parametrize("name", SAMPLES)
+def test_point_values(name):
+    g = golden(f"points_{name}")
+    f = net.eval_points(sample_params(name), g["points"])
+    s = rays.point_scale(sample_params(name), g["points"])
+    assert np.all(np.abs(f - g["values"]) <= RTOL * s)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify(name, mode):
+    g = golden(f"classify_{name}_{mode}")
+    p = sample_params(name)
+    ctx = ctx_for(mode, g["n_trunc"])
+    lab, lo, up, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    assert_bounds_close(lo, up, g["lower"], g["upper"], sc)
+    assert_labels(lab, g["label"], lo, up, sc)
+    assert_labels(net.labels_from_bounds(lo, up, 0.05), g["label_offset005"], lo, up, sc, 0.05)
+    # ray segments (v = 1)
+    lab, lo, up, sc = net.classify_general_box(p, ctx, g["seg_center"], g["seg_vecs"], return_scale=True)
+    assert_bounds_close(lo, up, g["seg_lower"], g["seg_upper"], sc)
+    assert_labels(lab, g["seg_label"], lo, up, sc)
+    # rigid transform prepended
+    p2 = net.prepend_op(p, net.spatial_transformation(g["xf_R"], g["xf_t"]))
+    lab, lo, up, sc = net.classify_box(p2, ctx, g["box_lower"][9:18], g["box_upper"][9:18], return_scale=True)
+    assert_bounds_close(lo, up, g["xf_lower"], g["xf_upper"], sc)
+    assert_labels(lab, g["xf_label"], lo, up, sc)
+    f = net.eval_points(p2, g["xf_points"])
+    assert np.all(np.abs(f - g["xf_values"]) <= RTOL * rays.point_scale(p2, g["xf_points"]))
+
+
+def test_classify_truncate64():
+    g = golden("classify_hammer_affine_truncate64")
+    ctx = ctx_for("affine_truncate", g["n_trunc"])
+    lab, lo, up, sc = net.classify_box(sample_params("hammer"), ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    assert_bounds_close(lo, up, g["lower"], g["upper"], sc)
+    assert_labels(lab, g["label"], lo, up, sc)
+
+
+RAY_CASES = {
+    "rays_fox_fixed_r12": (("fox",), "affine_fixed"),
+    "rays_fox_interval_r6": (("fox",), "interval"),
+    "rays_fox_all_r6": (("fox",), "affine_all"),
+    "rays_fox_fixed_r8_sub3": (("fox",), "affine_fixed"),
+    "rays_fox_bunny_fixed_r8": (("fox", "bunny"), "affine_fixed"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(RAY_CASES))
+def test_cast_rays(case):
+    names, mode = RAY_CASES[case]
+    g = golden(case)
+    # the camera generator restatement reproduces the reference's rays
+    look, up, _ = rays.look_at(g["eye"])
+    roots, dirs = rays.generate_camera_rays(g["eye"], look, up, res=int(g["res"]), fov_deg=30.0)
+    np.testing.assert_allclose(dirs, g["dirs"], rtol=0, atol=2e-7)
+    np.testing.assert_array_equal(roots, g["roots"])
+
+    opts = rays.get_default_cast_opts()
+    opts["n_substeps"] = int(g["n_substeps"])
+    ctxs = tuple(ctx_for(mode, g["n_trunc"]) for _ in names)
+    ps = tuple(sample_params(n) for n in names)
+    t, hit, cnt, n_evals, tie = rays.cast_rays(ctxs, ps, g["roots"], g["dirs"], opts, return_near_tie=True)
+    ok = ~tie
+    assert ok.mean() > 0.9
+    np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
+    np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
+    np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
+    if not tie.any():
+        assert n_evals == int(g["n_evals"])
+
+
+TREE_CASES = {
+    "tree_fox_fixed_d12": ("fox", "affine_fixed"),
+    "tree_bunny_all_d9": ("bunny", "affine_all"),
+    "tree_fox_trunc_d9": ("fox", "affine_truncate"),
+    "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
+    "tree_fox_fixed_b128": ("fox", "affine_fixed"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(TREE_CASES))
+def test_tree(case):
+    name, mode = TREE_CASES[case]
+    g = golden(case)
+    kw = {}
+    for k in g:
+        if k.startswith("kw_"):
+            v = g[k].item()
+            kw[k[3:]] = v
+    stats = {}
+    out = tree.construct_uniform_unknown_levelset_tree(
+        ctx_for(mode, g["n_trunc"]), sample_params(name), np.full(3, -1, np.float32), np.full(3, 1, np.float32),
+        stats=stats, **kw)
+    assert stats["n_near_tie"] == 0, "pick a different golden case: near-tie boxes make topology ambiguous"
+    for tag in ("unknown", "interior", "exterior"):
+        if f"{tag}_node_valid" not in g:
+            continue
+        gv = g[f"{tag}_node_valid"]
+        v = out[f"{tag}_node_valid"]
+        assert v.shape == gv.shape                      # same padded bucket size
+        np.testing.assert_array_equal(v, gv)
+        np.testing.assert_array_equal(out[f"{tag}_node_lower"][v], g[f"{tag}_node_lower"][gv])   # order too
+        np.testing.assert_array_equal(out[f"{tag}_node_upper"][v], g[f"{tag}_node_upper"][gv])
+
+
+@pytest.mark.parametrize("case,name", [("mc_fox_d4_s2", "fox"), ("mc_bunny_d4_s3", "bunny")])
+def test_marching_cubes(case, name):
+    g = golden(case)
+    tri = tree.hierarchical_marching_cubes(ctx_for("affine_fixed", 0), sample_params(name),
+                                           np.full(3, -1, np.float32), np.full(3, 1, np.float32),
+                                           int(g["depth"]), n_subcell_depth=int(g["n_sub"]))
+    assert tri.shape == g["tri_pos"].shape
+    assert tri.shape[0] > 0
+    np.testing.assert_allclose(tri, g["tri_pos"], rtol=0, atol=2e-5)
+
+
+@pytest.mark.parametrize("case,mode", [("isect_fixed", "affine_fixed"), ("isect_trunc64", "affine_truncate")])
+def test_find_any_intersection(case, mode):
+    g = golden(case)
+    pA = sample_params("hammer")
+    ctx = ctx_for(mode, g["n_trunc"])
+    lo, hi = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
+    for i in range(g["R"].shape[0]):
+        pB = net.prepend_op(sample_params("bunny"), net.spatial_transformation(g["R"][i], g["t"][i]))
+        found, ia, ib, loc = tree.find_any_intersection((ctx, ctx), (pA, pB), lo, hi, float(g["eps"]))
+        assert bool(found) == bool(g["found"][i])
+        np.testing.assert_allclose(loc, g["loc"][i], rtol=0, atol=1e-6)
+        assert (ia, ib) == ((1, 2) if found else (0, 0))
+
+
+@pytest.mark.parametrize("case", ["closest_fox_B32", "closest_fox_Bbig"])
+def test_closest_point(case):
+    g = golden(case)
+    d, loc = tree.closest_point(ctx_for("affine_fixed", 0), sample_params("fox"),
+                                np.full(3, -1, np.float32), np.full(3, 1, np.float32),
+                                g["query_points"], eps=float(g["eps"]), batch_process_size=int(g["B"]))
+    np.testing.assert_allclose(d, g["dist"], rtol=RTOL)
+    fin = np.isfinite(g["dist"])
+    assert fin.any()
+    np.testing.assert_allclose(loc[fin], g["loc"][fin], rtol=0, atol=1e-6)
+
+
+def test_mc_tables_match_reference_hash():
+    import hashlib
+
+    from niq_oracle import mc_tables
+    tri, edges, vc = mc_tables.unpack()
+    assert hashlib.sha256(tri.astype(np.int8).tobytes()).hexdigest() == mc_tables.TRI_TABLE_SHA256
+    assert (tri[:, 15] == -1).all() and tri.max() == 11
+    assert edges.shape == (12, 2) and vc.shape == (8, 3)
