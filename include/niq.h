@@ -164,6 +164,10 @@ int niq_tree_count(const niq_tree* tree, int which, int64_t* n);
 int niq_tree_copy(const niq_tree* tree, int which, float* lower, float* upper, int64_t capacity, int mem);
 /* stats[0]=boxes classified, [1]=near-tie boxes, [2]=levels processed, [3]=max frontier                */
 int niq_tree_stats(const niq_tree* tree, int64_t stats[4]);
+/* per level (0 .. stats[2]-1): info[0]=nodes entering the level, [1]=UNKNOWN, [2]=NEGATIVE, [3]=POSITIVE.
+ * The host side replays the reference's array-growth rule (src/kd_tree.py:156-164) from these to return
+ * interior/exterior arrays of the reference's padded sizes.                                              */
+int niq_tree_level_info(const niq_tree* tree, int32_t level, int64_t info[4]);
 int niq_tree_destroy(niq_tree* tree);
 
 /* ---- hierarchical marching cubes: src/kd_tree.py:338-399 + src/extract_cell.py:314-421 ---------- */

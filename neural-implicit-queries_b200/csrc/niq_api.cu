@@ -482,7 +482,7 @@ static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg
     const int v = src.kind == 0 ? src.v : 3;
     if (g.truncate && g.n_keep < 0) return fail(NIQ_EINVAL, "affine_truncate: truncate_count must be >= 0");
     g.kcap = g.truncate ? std::max(v, std::min(g.n_keep, v + m->sum_act_out)) + m->max_act_out : v + m->sum_act_out;
-    g.kcap = std::max(g.kcap, 4);
+    g.kcap = round_up(std::max(g.kcap, 4), 4);   // keeps the aff matrix 16-byte aligned behind mags/rank
     g.W = round_up(m->maxw_pad, 8);
     g.label = label; g.lower = lower; g.upper = upper; g.near_tie = tie;
     const size_t floats = (size_t)13 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W + (size_t)(g.truncate ? g.n_keep : 0) * g.W + 16;
@@ -755,6 +755,7 @@ struct niq_tree {
     niq_ctx* ctx = nullptr;
     NodeList lists[3];     // 0 unknown leaves, 1 interior, 2 exterior
     long long stats[4] = {0, 0, 0, 0};
+    std::vector<long long> levels;   // 4 per level: nodes entering, unknown, negative, positive
 };
 
 static int list_reserve(niq_ctx* c, NodeList& L, long long need) {
@@ -851,6 +852,7 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
             if (want_neg) tot[1] = reinterpret_cast<int*>(c->pinned)[1];
             if (want_pos) tot[2] = reinterpret_cast<int*>(c->pinned)[2];
             counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2];
+            T->levels.insert(T->levels.end(), {N, counts[0], counts[1], counts[2]});
             {   // near-tie boxes of this level (diagnostic counter)
                 std::vector<unsigned char> ht((size_t)N);
                 CU(cudaMemcpyAsync(ht.data(), tie.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
@@ -885,6 +887,7 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
             nxt.n = n_out;
             CU(cudaStreamSynchronize(c->stream));   // temporaries of this level are released after their last use
         } else {
+            T->levels.insert(T->levels.end(), {0, 0, 0, 0});
             nxt.n = 0;
         }
         std::swap(cur, nxt);
@@ -917,6 +920,11 @@ extern "C" int niq_tree_copy(const niq_tree* t, int which, float* lower, float* 
     CU(cudaMemcpyAsync(lower, L.lo, (size_t)L.n * 12, k, c->stream));
     CU(cudaMemcpyAsync(upper, L.hi, (size_t)L.n * 12, k, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    return NIQ_OK;
+}
+extern "C" int niq_tree_level_info(const niq_tree* t, int32_t level, int64_t info[4]) {
+    if (!t || !info || level < 0 || (size_t)level * 4 + 3 >= t->levels.size()) return fail(NIQ_EINVAL, "bad argument / level out of range");
+    for (int i = 0; i < 4; ++i) info[i] = t->levels[(size_t)level * 4 + i];
     return NIQ_OK;
 }
 extern "C" int niq_tree_stats(const niq_tree* t, int64_t stats[4]) {

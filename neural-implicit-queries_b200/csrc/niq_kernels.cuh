@@ -637,7 +637,7 @@ __global__ void k_cp_winner(CpRound r) {
     if (i >= top) return;
     const long long pop = top - r.window > 0 ? top - r.window : 0;
     const long long qid = r.stack_qid[pop + i];
-    if (r.this_dist[i] == r.min_dist[qid]) atomicMax(&r.winner[qid], r.round * (unsigned long long)r.window + i + 1);
+    if (r.this_dist[i] == r.min_dist[qid]) atomicMax(&r.winner[qid], (r.round << 32) | (unsigned long long)(i + 1));
 }
 __global__ void k_cp_loc(CpRound r) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -647,7 +647,7 @@ __global__ void k_cp_loc(CpRound r) {
     const long long pop = top - r.window > 0 ? top - r.window : 0;
     const long long qid = r.stack_qid[pop + i];
     if (r.this_dist[i] == r.min_dist[qid] &&
-        r.winner[qid] == r.round * (unsigned long long)r.window + i + 1) {
+        r.winner[qid] == ((r.round << 32) | (unsigned long long)(i + 1))) {
         for (int d = 0; d < 3; ++d) r.min_loc[3 * qid + d] = r.center[3 * i + d];
     }
 }

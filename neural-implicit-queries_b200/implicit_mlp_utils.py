@@ -1,0 +1,32 @@
+"""Mirrors /root/reference/src/implicit_mlp_utils.py:12-64 for the modes of the hot path."""
+import _niq
+import affine
+import mlp
+
+
+def generate_implicit_from_file(input_path, mode, **kwargs):
+    if input_path.endswith(".npz"):
+        params = mlp.load(input_path)
+    else:
+        raise ValueError("unrecognized filetype")
+    return generate_implicit_from_params(params, mode, **kwargs), params
+
+
+def generate_implicit_from_params(params, mode, **kwargs):
+    """The mode -> ImplicitFunction half of the factory (ours: lets callers skip the file)."""
+    if mode == "interval":
+        ctx = affine.AffineContext("interval")
+    elif mode == "affine_fixed":
+        ctx = affine.AffineContext("affine_fixed")
+    elif mode == "affine_truncate":
+        ctx = affine.AffineContext("affine_truncate", truncate_count=kwargs["affine_n_truncate"],
+                                   truncate_policy=kwargs["affine_truncate_policy"])
+    elif mode == "affine_all":
+        ctx = affine.AffineContext("affine_all")
+    elif mode in ("sdf", "affine_append", "slope_interval"):
+        raise _niq.NiqError(_niq.NIQ_EUNSUPPORTED,
+                            f"mode '{mode}' exists in the reference but is outside this backend's hot path "
+                            "(interval, affine_fixed, affine_truncate, affine_all)")
+    else:
+        raise RuntimeError("unrecognized mode")
+    return affine.AffineImplicitFunction(mlp.func_from_spec(mode="affine"), ctx)

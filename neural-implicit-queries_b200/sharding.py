@@ -1,0 +1,120 @@
+"""Multi-GPU partition of the hot path (new: the reference is single-device).
+
+One process per GPU (torch.distributed; NCCL on the GPU box, gloo in the CPU tests).  Rays are
+independent, so the image is cut into square pixel tiles dealt round-robin to the ranks (balances hit /
+miss regions); every rank casts its own rays with no data-path collective, and ONE all_gather at the end
+returns (t, hit_id, count) = 12 B/ray to every rank.  kd-tree subtrees shard the same way: the top levels
+are built replicated, the frontier boxes are dealt round-robin and each rank finishes its own subtrees.
+"""
+import numpy as np
+
+
+def tile_ids(res_x, res_y, tile):
+    """Row-major ids of the tile grid covering a res_x x res_y image."""
+    return (res_x + tile - 1) // tile, (res_y + tile - 1) // tile
+
+
+def rank_pixels(res_x, res_y, tile, rank, world, tile_stride=1):
+    """Flat pixel indices (y-major, as render.generate_camera_rays orders rays) owned by `rank`:
+    every `tile_stride`-th tile of the grid (a stated sub-sample when > 1), dealt round-robin."""
+    ntx, nty = tile_ids(res_x, res_y, tile)
+    chosen = np.arange(0, ntx * nty, tile_stride)
+    mine = chosen[rank::world]
+    ty, tx = np.divmod(mine, ntx)
+    oy, ox = np.meshgrid(np.arange(tile), np.arange(tile), indexing="ij")
+    py = (ty[:, None, None] * tile + oy[None]).reshape(len(mine), -1)
+    px = (tx[:, None, None] * tile + ox[None]).reshape(len(mine), -1)
+    ok = (py < res_y) & (px < res_x)
+    return (py * res_x + px)[ok].astype(np.int64)
+
+
+def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y, tile=16, cast_fn=None, group=None):
+    """cast_rays over the full image with the rays partitioned across the ranks of `group`; every rank
+    returns the full (out_t, out_hit_id, out_count, N_evals) like the single-device call.
+    `cast_fn` defaults to queries.cast_rays (tests inject a CPU stand-in to exercise the plumbing)."""
+    import torch
+    import torch.distributed as dist
+    if cast_fn is None:
+        import queries
+        cast_fn = queries.cast_rays
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = roots.shape[0]
+    assert n == res_x * res_y, "rays must be the full image in generate_camera_rays order"
+    mine = rank_pixels(res_x, res_y, tile, rank, world)
+    t, hit, cnt, n_evals = cast_fn(funcs_tuple, params_tuple, roots[mine], dirs[mine], opts)[:4]
+    if world == 1:
+        out_t = np.zeros(n, np.float32); out_h = np.zeros(n, np.int32); out_c = np.zeros(n, np.int32)
+        out_t[mine], out_h[mine], out_c[mine] = t, hit, cnt
+        return out_t, out_h, out_c, n_evals
+    # one gather of (idx, t, hit, count), padded to the largest shard
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    sizes = [len(rank_pixels(res_x, res_y, tile, r, world)) for r in range(world)]
+    cap = max(sizes)
+    pack = torch.zeros((cap, 3), dtype=torch.int32)
+    pack[:len(mine), 0] = torch.from_numpy(t.view(np.int32))
+    pack[:len(mine), 1] = torch.from_numpy(hit)
+    pack[:len(mine), 2] = torch.from_numpy(cnt)
+    pack = pack.to(dev)
+    out = torch.empty((world, cap, 3), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(out.view(-1, 3), pack, group=group) if backend == "nccl" else \
+        dist.all_gather(list(out.unbind(0)), pack, group=group)
+    ev = torch.tensor([n_evals], dtype=torch.int64, device=dev)
+    dist.all_reduce(ev, group=group)
+    out = out.cpu().numpy()
+    out_t = np.zeros(n, np.float32); out_h = np.zeros(n, np.int32); out_c = np.zeros(n, np.int32)
+    for r in range(world):
+        idx = rank_pixels(res_x, res_y, tile, r, world)
+        out_t[idx] = out[r, :sizes[r], 0].view(np.float32)
+        out_h[idx] = out[r, :sizes[r], 1]
+        out_c[idx] = out[r, :sizes[r], 2]
+    return out_t, out_h, out_c, int(ev.item())
+
+
+def deal_boxes(n_boxes, rank, world):
+    """Indices of the frontier boxes (top-of-tree leaves) owned by `rank`: round-robin."""
+    return np.arange(rank, n_boxes, world, dtype=np.int64)
+
+
+def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_fn=None, group=None, **kw):
+    """construct_uniform_unknown_levelset_tree with subtrees sharded across ranks: the top `top_depth`
+    levels are built on every rank (replicated, tiny), the surviving frontier is dealt round-robin, each rank
+    refines its own boxes to `split_depth`, and the UNKNOWN leaves are all-gathered (24 B/leaf).
+    Leaf ORDER differs from the single-device call (canonicalise before comparing).  -> (lower, upper) (L,3)."""
+    import torch
+    import torch.distributed as dist
+    if build_fn is None:
+        import kd_tree
+        build_fn = kd_tree.construct_uniform_unknown_levelset_tree
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if top_depth is None:
+        top_depth = min(split_depth, int(np.ceil(np.log2(max(8 * world, 2)))) + 3)
+    top = build_fn(func, params, lower, upper, split_depth=top_depth, **kw)
+    v = top['unknown_node_valid']
+    flo, fhi = top['unknown_node_lower'][v], top['unknown_node_upper'][v]
+    mine = deal_boxes(flo.shape[0], rank, world)
+    los, his = [], []
+    for i in mine:
+        sub = build_fn(func, params, flo[i], fhi[i], split_depth=split_depth - top_depth, **kw)
+        sv = sub['unknown_node_valid']
+        los.append(sub['unknown_node_lower'][sv]); his.append(sub['unknown_node_upper'][sv])
+    lo = np.concatenate(los) if los else np.zeros((0, 3), np.float32)
+    hi = np.concatenate(his) if his else np.zeros((0, 3), np.float32)
+    if world == 1:
+        return lo, hi
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    cnt = torch.tensor([lo.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    pack = torch.zeros((cap, 6), dtype=torch.float32)
+    pack[:lo.shape[0], :3] = torch.from_numpy(lo)
+    pack[:lo.shape[0], 3:] = torch.from_numpy(hi)
+    parts = [torch.empty((cap, 6), dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.all_gather(parts, pack.to(dev), group=group)
+    allp = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
+    return allp[:, :3].copy(), allp[:, 3:].copy()

@@ -1,0 +1,525 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the reference-shaped
+Python modules -> ctypes -> C ABI (include/niq.h), against (a) the committed golden vectors produced by
+the unmodified reference on the NumPy jax stand-in and (b) the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star): labels / topology / hit flags / verdicts bit-exact except for boxes
+whose bound lies within 1e-5 (relative) of the level set -- counted; values within 1e-5 relative, where
+"relative" is measured against the magnitude the bound was summed from (net.tol_scale)."""
+import numpy as np
+import pytest
+
+from conftest import golden, sample_params
+from niq_oracle import net, rays, tree as otree
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+SAMPLES = ("fox", "bunny", "hammer", "birdcage_occ")
+MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all")
+LO = np.full(3, -1, np.float32)
+HI = np.full(3, 1, np.float32)
+
+
+def make(params, mode, n_trunc=8):
+    import implicit_mlp_utils
+    kw = dict(affine_n_truncate=int(n_trunc), affine_truncate_policy="absolute") if mode == "affine_truncate" else {}
+    return implicit_mlp_utils.generate_implicit_from_params(params, mode, **kw)
+
+
+def octx(mode, n_trunc=8):
+    return net.AffineContext(mode, truncate_count=int(n_trunc))
+
+
+def check_bounds(lo, up, glo, gup, sc):
+    scale = net.tol_scale(glo, gup, sc)
+    assert np.all(np.abs(lo.astype(np.float64) - glo) <= RTOL * scale + 1e-30), \
+        f"lower off by {np.max(np.abs(lo - glo) / scale):.3e} rel"
+    assert np.all(np.abs(up.astype(np.float64) - gup) <= RTOL * scale + 1e-30), \
+        f"upper off by {np.max(np.abs(up - gup) / scale):.3e} rel"
+
+
+def check_labels(lab, glab, glo, gup, sc, offset=0.0):
+    tie = net.bound_near_tie(glo, gup, offset, sc)
+    bad = (lab != glab) & ~tie
+    assert not bad.any(), f"{bad.sum()} label mismatches outside the near-tie band"
+    return int(tie.sum())
+
+
+def random_boxes(seed, n, smin=-9, smax=0):
+    rng = np.random.default_rng(seed)
+    c = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (2.0 ** rng.uniform(smin, smax, (n, 1)) * rng.uniform(0.5, 1.0, (n, 3))).astype(np.float32)
+    return c - h, c + h
+
+
+# ---------------------------------------------------------------------------------------------------
+# primitives
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("name", SAMPLES)
+def test_point_values_golden(name):
+    import mlp
+    g = golden(f"points_{name}")
+    p = sample_params(name)
+    f, s = mlp.eval_points(p, g["points"], return_scale=True)
+    assert np.all(np.abs(f - g["values"]) <= RTOL * rays.point_scale(p, g["points"]))
+    np.testing.assert_allclose(s, rays.point_scale(p, g["points"]), rtol=1e-4)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 1000, 70001])
+def test_point_values_ragged_sizes(n):
+    import mlp
+    p = sample_params("bunny")
+    x = np.random.default_rng(n).uniform(-1, 1, (n, 3)).astype(np.float32)
+    f = mlp.eval_points(p, x)
+    assert f.shape == (n,)
+    if n:
+        assert np.all(np.abs(f - net.eval_points(p, x)) <= RTOL * rays.point_scale(p, x))
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_golden(name, mode):
+    g = golden(f"classify_{name}_{mode}")
+    p = sample_params(name)
+    func = make(p, mode, g["n_trunc"])
+    # scale of the golden bounds (oracle run gives the yardstick only)
+    _, _, _, sc = net.classify_box(p, octx(mode, g["n_trunc"]), g["box_lower"], g["box_upper"], return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, g["box_lower"], g["box_upper"])
+    check_bounds(lo, up, g["lower"], g["upper"], sc)
+    check_labels(lab, g["label"], g["lower"], g["upper"], sc)
+    lab5 = func.classify_box(p, g["box_lower"], g["box_upper"], offset=0.05)
+    check_labels(lab5, g["label_offset005"], g["lower"], g["upper"], sc, 0.05)
+    # v = 1 general boxes
+    _, _, _, sc = net.classify_general_box(p, octx(mode, g["n_trunc"]), g["seg_center"], g["seg_vecs"], return_scale=True)
+    lab, lo, up, tie = func.bound_general_box(p, g["seg_center"], g["seg_vecs"])
+    check_bounds(lo, up, g["seg_lower"], g["seg_upper"], sc)
+    check_labels(lab, g["seg_label"], g["seg_lower"], g["seg_upper"], sc)
+    # rigid transform prepended
+    import mlp
+    p2 = mlp.prepend_op(p, mlp.spatial_transformation())
+    p2["0000.spatial_transformation.R"] = g["xf_R"]
+    p2["0000.spatial_transformation.t"] = g["xf_t"]
+    op2 = net.prepend_op(p, net.spatial_transformation(g["xf_R"], g["xf_t"]))
+    _, _, _, sc = net.classify_box(op2, octx(mode, g["n_trunc"]), g["box_lower"][9:18], g["box_upper"][9:18], return_scale=True)
+    lab, lo, up, tie = func.bound_box(p2, g["box_lower"][9:18], g["box_upper"][9:18])
+    check_bounds(lo, up, g["xf_lower"], g["xf_upper"], sc)
+    check_labels(lab, g["xf_label"], g["xf_lower"], g["xf_upper"], sc)
+    f = func(p2, g["xf_points"])
+    assert np.all(np.abs(f - g["xf_values"]) <= RTOL * rays.point_scale(op2, g["xf_points"]))
+
+
+def test_classify_truncate64_golden():
+    g = golden("classify_hammer_affine_truncate64")
+    p = sample_params("hammer")
+    func = make(p, "affine_truncate", 64)
+    _, _, _, sc = net.classify_box(p, octx("affine_truncate", 64), g["box_lower"], g["box_upper"], return_scale=True)
+    lab, lo, up, _ = func.bound_box(p, g["box_lower"], g["box_upper"])
+    check_bounds(lo, up, g["lower"], g["upper"], sc)
+    check_labels(lab, g["label"], g["lower"], g["upper"], sc)
+
+
+@pytest.mark.parametrize("mode,n", [("interval", 20000), ("affine_fixed", 20000), ("affine_truncate", 1500), ("affine_all", 1500)])
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_vs_oracle_random(name, mode, n):
+    p = sample_params(name)
+    lo_b, hi_b = random_boxes(11, n)
+    func = make(p, mode, 16)
+    olab, olo, oup, sc = net.classify_box(p, octx(mode, 16), lo_b, hi_b, return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, lo_b, hi_b)
+    check_bounds(lo, up, olo, oup, sc)
+    n_tie = check_labels(lab, olab, olo, oup, sc)
+    assert n_tie < 0.01 * n
+    # device near-tie flag covers every box the oracle calls near-tie with a 10x narrower band
+    narrow = net.bound_near_tie(olo, oup, 0.0, None, rel=1e-6)
+    assert np.all(tie[narrow] | (lab[narrow] == olab[narrow]))
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 129, 4099])
+def test_classify_ragged_sizes(n):
+    p = sample_params("fox")
+    lo_b, hi_b = random_boxes(5, n)
+    for mode in ("affine_fixed", "affine_all"):
+        lab, lo, up, tie = make(p, mode).bound_box(p, lo_b, hi_b)
+        assert lab.shape == (n,)
+        if n:
+            olab, olo, oup, sc = net.classify_box(p, octx(mode), lo_b, hi_b, return_scale=True)
+            check_bounds(lo, up, olo, oup, sc)
+            check_labels(lab, olab, olo, oup, sc)
+
+
+@pytest.mark.parametrize("width,act", [(256, "relu"), (128, "elu"), (40, "relu"), (64, "relu")])
+def test_classify_synthetic_widths(width, act):
+    """Random-init MLPs of other width classes (config 5's 8x256; odd widths exercise the padding)."""
+    p = net.random_mlp([3] + [width] * 8 + [1], act, seed=0)
+    lo_b, hi_b = random_boxes(3, 3000, smin=-12, smax=-2)
+    func = make(p, "affine_fixed")
+    olab, olo, oup, sc = net.classify_box(p, octx("affine_fixed"), lo_b, hi_b, return_scale=True)
+    lab, lo, up, _ = func.bound_box(p, lo_b, hi_b)
+    check_bounds(lo, up, olo, oup, sc)
+    check_labels(lab, olab, olo, oup, sc)
+    x = np.random.default_rng(1).uniform(-1, 1, (5000, 3)).astype(np.float32)
+    f = func(p, x)
+    assert np.all(np.abs(f - net.eval_points(p, x)) <= RTOL * rays.point_scale(p, x))
+    if width <= 128:
+        funca = make(p, "affine_all")
+        olab, olo, oup, sc = net.classify_box(p, octx("affine_all"), lo_b[:300], hi_b[:300], return_scale=True)
+        lab, lo, up, _ = funca.bound_box(p, lo_b[:300], hi_b[:300])
+        check_bounds(lo, up, olo, oup, sc)
+        check_labels(lab, olab, olo, oup, sc)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_soundness_property(mode):
+    """Size-independent property: f(x) sampled inside a box lies within the computed bounds."""
+    import mlp
+    rng = np.random.default_rng(2)
+    for name in SAMPLES:
+        p = sample_params(name)
+        n = 4000 if mode in ("interval", "affine_fixed") else 400
+        lo_b, hi_b = random_boxes(9, n, smin=-7, smax=-1)
+        _, lo, up, _ = make(p, mode, 16).bound_box(p, lo_b, hi_b)
+        u = rng.uniform(0, 1, (n, 8, 3)).astype(np.float32)
+        x = lo_b[:, None, :] + u * (hi_b - lo_b)[:, None, :]
+        f = mlp.eval_points(p, x)
+        slack = 1e-5 * np.maximum(np.abs(lo), np.abs(up))[:, None] + 1e-6
+        assert np.all(f >= lo[:, None] - slack) and np.all(f <= up[:, None] + slack)
+
+
+def test_params_are_read_afresh_each_call():
+    """The reference's GUI mutates params between calls (src/main_intersection.py:171-183)."""
+    import mlp
+    p = mlp.prepend_op(sample_params("bunny"), mlp.spatial_transformation())
+    func = make(p, "affine_fixed")
+    x = np.array([[0.1, 0.2, -0.1]], np.float32)
+    f0 = func(p, x)
+    p["0000.spatial_transformation.t"] = np.array([0.3, 0.0, 0.0], np.float32)
+    f1 = func(p, x)
+    f1_ref = func(sample_params("bunny"), x - np.array([[0.3, 0, 0]], np.float32))
+    assert f0[0] != f1[0]
+    np.testing.assert_allclose(f1, f1_ref, rtol=1e-5)
+
+
+def test_unsupported_and_invalid_arguments():
+    import _niq
+    import implicit_mlp_utils
+    p = sample_params("fox")
+    with pytest.raises(RuntimeError):
+        implicit_mlp_utils.generate_implicit_from_params(p, "slope_interval")
+    f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_truncate", affine_n_truncate=8,
+                                                         affine_truncate_policy="relative")
+    with pytest.raises(_niq.NiqError):
+        f.classify_box(p, LO, HI)
+    bad = dict(p)
+    bad["0001.sin._"] = bad.pop("0001.relu._")
+    with pytest.raises(RuntimeError):
+        make(bad, "affine_fixed").classify_box(bad, LO, HI)
+    import kd_tree
+    with pytest.raises(ValueError):
+        kd_tree.construct_uniform_unknown_levelset_tree(make(p, "affine_fixed"), p, LO, HI)
+    with pytest.raises(ValueError):
+        kd_tree.construct_uniform_unknown_levelset_tree(make(p, "affine_fixed"), p, LO, HI, split_depth=3, batch_process_size=100)
+    with pytest.raises(ValueError):
+        kd_tree.find_any_intersection((make(p, "affine_fixed"),), (p,), LO, HI, 1e-3)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cast_rays
+# ---------------------------------------------------------------------------------------------------
+
+RAY_CASES = {
+    "rays_fox_fixed_r12": (("fox",), "affine_fixed"),
+    "rays_fox_interval_r6": (("fox",), "interval"),
+    "rays_fox_all_r6": (("fox",), "affine_all"),
+    "rays_fox_fixed_r8_sub3": (("fox",), "affine_fixed"),
+    "rays_fox_bunny_fixed_r8": (("fox", "bunny"), "affine_fixed"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(RAY_CASES))
+def test_cast_rays_golden(case):
+    import queries
+    import render
+    names, mode = RAY_CASES[case]
+    g = golden(case)
+    look, up, _ = render.look_at(g["eye"])
+    roots, dirs = render.generate_camera_rays(g["eye"], look, up, res=int(g["res"]), fov_deg=30.0)
+    np.testing.assert_array_equal(roots, g["roots"])
+    np.testing.assert_allclose(dirs, g["dirs"], rtol=0, atol=2e-7)
+    opts = queries.get_default_cast_opts()
+    opts["n_substeps"] = int(g["n_substeps"])
+    ps = tuple(sample_params(n) for n in names)
+    funcs = tuple(make(p, mode, g["n_trunc"]) for p in ps)
+    t, hit, cnt, n_evals, tie = queries.cast_rays(funcs, ps, g["roots"], g["dirs"], opts, return_near_tie=True)
+    assert t.dtype == np.float32 and hit.dtype == np.int32 and cnt.dtype == np.int32
+    ok = ~tie
+    assert ok.mean() > 0.9
+    np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
+    np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
+    np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
+    if not tie.any():
+        assert n_evals == int(g["n_evals"])
+
+
+@pytest.mark.parametrize("name,mode,res", [("fox", "affine_fixed", 96), ("bunny", "affine_fixed", 48), ("hammer", "interval", 32)])
+def test_cast_rays_vs_oracle(name, mode, res):
+    import queries
+    import render
+    p = sample_params(name)
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=res, fov_deg=30.)
+    opts = queries.get_default_cast_opts()
+    t, hit, cnt, n_evals, tie = queries.cast_rays((make(p, mode),), (p,), roots, dirs, opts, return_near_tie=True)
+    ot, ohit, ocnt, on_evals, otie = rays.cast_rays((octx(mode),), (p,), roots, dirs, opts, return_near_tie=True)
+    ok = ~(tie | otie)
+    assert ok.mean() > 0.97, f"{(~ok).sum()} near-tie rays of {ok.size}"
+    np.testing.assert_array_equal(hit[ok], ohit[ok])
+    np.testing.assert_array_equal(cnt[ok], ocnt[ok])
+    np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL, atol=0)
+    assert (hit > 0).any() and (hit == 0).any()
+    if ok.all():
+        assert n_evals == on_evals
+
+
+def test_cast_rays_empty_and_single():
+    import queries
+    p = sample_params("fox")
+    f = make(p, "affine_fixed")
+    opts = queries.get_default_cast_opts()
+    t, hit, cnt, n = queries.cast_rays((f,), (p,), np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32), opts)
+    assert t.shape == (0,) and n == 0
+    r = np.array([[2., 1., 2.]], np.float32)
+    d = -r / np.linalg.norm(r)
+    t, hit, cnt, n = queries.cast_rays((f,), (p,), r, d.astype(np.float32), opts)
+    ot, ohit, ocnt, on = rays.cast_rays((octx("affine_fixed"),), (p,), r, d.astype(np.float32), opts)
+    assert hit[0] == ohit[0] and cnt[0] == ocnt[0] and n == on
+    np.testing.assert_allclose(t, ot, rtol=RTOL)
+
+
+def test_cast_rays_full_size_properties():
+    """Config 1 size (fox 512x512): properties that need no oracle run -- every ray terminates with a legal
+    state, hits lie on a sign change of f within hit_eps, misses are beyond max_dist."""
+    import mlp
+    import queries
+    import render
+    p = sample_params("fox")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=512, fov_deg=30.)
+    opts = queries.get_default_cast_opts()
+    t, hit, cnt, n_evals, tie = queries.cast_rays((make(p, "affine_fixed"),), (p,), roots, dirs, opts, return_near_tie=True)
+    assert np.all((cnt >= 1) & (cnt <= opts["n_max_step"]))
+    miss = hit == 0
+    assert np.all((t[miss] > opts["max_dist"]) | (cnt[miss] >= opts["n_max_step"]))
+    h = hit == 1
+    assert 0.1 < h.mean() < 0.5
+    x0 = roots[h] + t[h, None] * dirs[h]
+    x1 = roots[h] + (t[h] + np.float32(opts["hit_eps"]))[:, None] * dirs[h]
+    f0, f1 = mlp.eval_points(p, x0), mlp.eval_points(p, x1)
+    assert np.mean(np.sign(f0) != np.sign(f1)) > 0.999      # position is recomputed on the host: allow ulp ties
+    assert n_evals >= int(cnt.sum())
+    assert tie.mean() < 0.02
+
+
+# ---------------------------------------------------------------------------------------------------
+# level-set tree, marching cubes
+# ---------------------------------------------------------------------------------------------------
+
+TREE_CASES = {
+    "tree_fox_fixed_d12": ("fox", "affine_fixed"),
+    "tree_bunny_all_d9": ("bunny", "affine_all"),
+    "tree_fox_trunc_d9": ("fox", "affine_truncate"),
+    "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
+    "tree_fox_fixed_b128": ("fox", "affine_fixed"),
+}
+
+
+@pytest.mark.parametrize("case", sorted(TREE_CASES))
+def test_tree_golden(case):
+    import kd_tree
+    name, mode = TREE_CASES[case]
+    g = golden(case)
+    kw = {k[3:]: g[k].item() for k in g if k.startswith("kw_")}
+    stats = {}
+    p = sample_params(name)
+    out = kd_tree.construct_uniform_unknown_levelset_tree(make(p, mode, g["n_trunc"]), p, LO, HI, stats=stats, **kw)
+    assert stats["n_near_tie"] == 0
+    for tag in ("unknown", "interior", "exterior"):
+        if f"{tag}_node_valid" not in g:
+            assert f"{tag}_node_valid" not in out
+            continue
+        gv, v = g[f"{tag}_node_valid"], out[f"{tag}_node_valid"]
+        assert v.shape == gv.shape                       # the reference's padded bucket size
+        np.testing.assert_array_equal(v, gv)
+        np.testing.assert_array_equal(out[f"{tag}_node_lower"][v], g[f"{tag}_node_lower"][gv])    # order too
+        np.testing.assert_array_equal(out[f"{tag}_node_upper"][v], g[f"{tag}_node_upper"][gv])
+
+
+def _canon(lo, hi):
+    a = np.concatenate((lo, hi), axis=1)
+    return a[np.lexsort(a.T[::-1])]
+
+
+@pytest.mark.parametrize("name,depth", [("bunny", 15), ("birdcage_occ", 14), ("hammer", 13)])
+def test_tree_vs_oracle(name, depth):
+    import kd_tree
+    p = sample_params(name)
+    st, ost = {}, {}
+    out = kd_tree.construct_uniform_unknown_levelset_tree(make(p, "affine_fixed"), p, LO, HI, split_depth=depth,
+                                                          with_interior_nodes=True, with_exterior_nodes=True, stats=st)
+    ref = otree.construct_uniform_unknown_levelset_tree(octx("affine_fixed"), p, LO, HI, split_depth=depth,
+                                                        with_interior_nodes=True, with_exterior_nodes=True, stats=ost)
+    if ost["n_near_tie"] == 0 and st["n_near_tie"] == 0:
+        assert st["n_evals"] == ost["n_evals"]
+        for tag in ("unknown", "interior", "exterior"):
+            v, rv = out[f"{tag}_node_valid"], ref[f"{tag}_node_valid"]
+            assert v.shape == rv.shape
+            np.testing.assert_array_equal(out[f"{tag}_node_lower"][v], ref[f"{tag}_node_lower"][rv])
+            np.testing.assert_array_equal(out[f"{tag}_node_upper"][v], ref[f"{tag}_node_upper"][rv])
+    else:   # topology may differ only below near-tie boxes: the node counts stay within that budget
+        n, rn = int(out["unknown_node_valid"].sum()), int(ref["unknown_node_valid"].sum())
+        assert abs(n - rn) <= (ost["n_near_tie"] + st["n_near_tie"]) * 2 ** 4
+
+
+def test_tree_deep_properties():
+    """bunny split_depth 18 (~100k boxes): leaves are disjoint dyadic boxes of equal size, surface samples
+    found by ray casting all fall inside some UNKNOWN leaf, interior/exterior boxes carry the right sign."""
+    import kd_tree
+    import mlp
+    p = sample_params("bunny")
+    func = make(p, "affine_fixed")
+    st = {}
+    out = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, split_depth=18, with_interior_nodes=True,
+                                                          with_exterior_nodes=True, stats=st)
+    v = out["unknown_node_valid"]
+    lo, hi = out["unknown_node_lower"][v], out["unknown_node_upper"][v]
+    assert lo.shape[0] > 10000
+    ext = hi - lo
+    assert np.all(ext == ext[0])                         # uniform depth
+    key = np.round((lo + 1) / ext[0]).astype(np.int64)
+    assert np.unique(key, axis=0).shape[0] == lo.shape[0]    # no duplicates
+    for tag, sign in (("interior", -1), ("exterior", 1)):
+        m = out[f"{tag}_node_valid"]
+        c = 0.5 * (out[f"{tag}_node_lower"][m] + out[f"{tag}_node_upper"][m])
+        if c.shape[0]:
+            assert np.all(np.sign(mlp.eval_points(p, c)) == sign)
+    # volume is conserved: unknown + interior + exterior tile the domain
+    vol = lambda a, b: np.prod((b - a).astype(np.float64), axis=1).sum()
+    total = vol(lo, hi) + sum(vol(out[f"{t}_node_lower"][out[f"{t}_node_valid"]], out[f"{t}_node_upper"][out[f"{t}_node_valid"]])
+                              for t in ("interior", "exterior"))
+    np.testing.assert_allclose(total, 8.0, rtol=1e-9)
+    assert st["n_evals"] > 50000
+
+
+@pytest.mark.parametrize("case,name", [("mc_fox_d4_s2", "fox"), ("mc_bunny_d4_s3", "bunny")])
+def test_marching_cubes_golden(case, name):
+    import kd_tree
+    g = golden(case)
+    p = sample_params(name)
+    tri = kd_tree.hierarchical_marching_cubes(make(p, "affine_fixed"), p, LO, HI, int(g["depth"]), n_subcell_depth=int(g["n_sub"]))
+    assert tri.shape == g["tri_pos"].shape and tri.dtype == np.float32
+    np.testing.assert_allclose(tri, g["tri_pos"], rtol=0, atol=2e-5)
+
+
+def test_marching_cubes_vs_oracle_and_properties():
+    import extract_cell
+    import kd_tree
+    import mlp
+    from niq_oracle import mc
+    p = sample_params("bunny")
+    func = make(p, "affine_fixed")
+    tri = kd_tree.hierarchical_marching_cubes(func, p, LO, HI, 6, n_subcell_depth=3)
+    otri = otree.hierarchical_marching_cubes(octx("affine_fixed"), p, LO, HI, 6, n_subcell_depth=3)
+    assert tri.shape == otri.shape and tri.shape[0] > 20000
+    np.testing.assert_allclose(tri, otri, rtol=0, atol=2e-5)
+    # vertices lie near the level set: |f| small relative to the local gradient scale
+    f = mlp.eval_points(p, tri.reshape(-1, 3))
+    assert np.percentile(np.abs(f), 99) < 0.02
+    # single-cell API keeps the reference's padded layout
+    mc_data = extract_cell.get_mc_data()
+    tp, tv = extract_cell.extract_triangles_from_subcells(func, p, mc_data, 2, np.array([-.25, -.25, -.25], np.float32),
+                                                          np.array([.25, .25, .25], np.float32))
+    assert tp.shape == (5 * 64, 3, 3) and tv.shape == (5 * 64,)
+    ref = mc.extract_mesh_from_leaves(p, np.array([[-.25, -.25, -.25]], np.float32), np.array([[.25, .25, .25]], np.float32), 2)
+    np.testing.assert_allclose(tp[tv], ref, rtol=0, atol=2e-5)
+
+
+# ---------------------------------------------------------------------------------------------------
+# find_any_intersection, closest_point
+# ---------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("case,mode", [("isect_fixed", "affine_fixed"), ("isect_trunc64", "affine_truncate")])
+def test_find_any_intersection_golden(case, mode):
+    import kd_tree
+    import mlp
+    g = golden(case)
+    pA = sample_params("hammer")
+    pB = mlp.prepend_op(sample_params("bunny"), mlp.spatial_transformation())
+    fA, fB = make(pA, mode, g["n_trunc"]), make(pB, mode, g["n_trunc"])
+    for i in range(g["R"].shape[0]):
+        pB["0000.spatial_transformation.R"] = g["R"][i]
+        pB["0000.spatial_transformation.t"] = g["t"][i]
+        st = {}
+        found, ia, ib, loc = kd_tree.find_any_intersection((fA, fB), (pA, pB), LO, HI, float(g["eps"]), stats=st)
+        if st["n_near_tie"] == 0:
+            assert bool(found) == bool(g["found"][i])
+            np.testing.assert_allclose(loc, g["loc"][i], rtol=0, atol=1e-6)
+        assert (ia, ib) == ((1, 2) if found else (0, 0))
+
+
+def test_find_any_intersection_vs_oracle_list():
+    """Seeded rigid transforms (config 3 recipe, affine_fixed for oracle speed): verdict + location parity."""
+    import kd_tree
+    import mlp
+    rng = np.random.default_rng(0)
+    pA = sample_params("hammer")
+    pB = mlp.prepend_op(sample_params("bunny"), mlp.spatial_transformation())
+    fA, fB = make(pA, "affine_fixed"), make(pB, "affine_fixed")
+    n_found = 0
+    for i in range(12):
+        th = rng.uniform(0, 2 * np.pi)
+        R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+        t = rng.uniform(-1.5, 1.5, 3).astype(np.float32)
+        pB["0000.spatial_transformation.R"] = R
+        pB["0000.spatial_transformation.t"] = t
+        opB = net.prepend_op(sample_params("bunny"), net.spatial_transformation(R, t))
+        st, ost = {}, {}
+        found, _, _, loc = kd_tree.find_any_intersection((fA, fB), (pA, pB), LO, HI, 1e-3, stats=st)
+        ofound, _, _, oloc = otree.find_any_intersection((octx("affine_fixed"),) * 2, (pA, opB), LO, HI, 1e-3, stats=ost)
+        if st["n_near_tie"] == 0 and ost["n_near_tie"] == 0:
+            assert bool(found) == bool(ofound)
+            assert st["n_nodes"] == ost["n_nodes"] and st["n_rounds"] == ost["n_rounds"]
+            np.testing.assert_allclose(loc, oloc, rtol=0, atol=1e-6)
+        n_found += bool(found)
+    assert 0 < n_found < 12
+
+
+@pytest.mark.parametrize("case", ["closest_fox_B32", "closest_fox_Bbig"])
+def test_closest_point_golden(case):
+    import kd_tree
+    g = golden(case)
+    p = sample_params("fox")
+    d, loc = kd_tree.closest_point(make(p, "affine_fixed"), p, LO, HI, g["query_points"], eps=float(g["eps"]),
+                                   batch_process_size=int(g["B"]))
+    np.testing.assert_allclose(d, g["dist"], rtol=RTOL)
+    fin = np.isfinite(g["dist"])
+    assert fin.any()
+    np.testing.assert_allclose(loc[fin], g["loc"][fin], rtol=0, atol=1e-6)
+
+
+@pytest.mark.parametrize("B", [64, 2048, 2 ** 22])
+def test_closest_point_vs_oracle(B):
+    import kd_tree
+    p = sample_params("fox")
+    q = np.random.default_rng(4).uniform(-1, 1, (24, 3)).astype(np.float32)
+    st, ost = {}, {}
+    d, loc = kd_tree.closest_point(make(p, "affine_fixed"), p, LO, HI, q, eps=0.01, batch_process_size=B, stats=st)
+    od, oloc = otree.closest_point(octx("affine_fixed"), p, LO, HI, q, eps=0.01, batch_process_size=B, stats=ost)
+    if st["n_near_tie"] == 0 and ost["n_near_tie"] == 0:
+        assert st["n_visits"] == ost["n_visits"] and st["n_rounds"] == ost["n_rounds"]
+        np.testing.assert_allclose(d, od, rtol=RTOL)
+        fin = np.isfinite(od)
+        np.testing.assert_allclose(loc[fin], oloc[fin], rtol=0, atol=1e-6)
+    else:
+        assert np.mean(np.abs(d - od) <= 1e-5 * od) > 0.7

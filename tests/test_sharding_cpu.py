@@ -1,0 +1,89 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic in sharding.py: tile partition, the single
+all_gather of ray results and the subtree deal + leaf gather.  The compute function is injected (the CPU
+oracle stands in for the CUDA call), so what is tested is exactly the plumbing the GPU path uses."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch.multiprocessing as mp
+
+from conftest import ROOT, sample_params
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def test_tile_partition_covers_image_once():
+    import sharding
+    for (rx, ry, tile, world) in ((64, 48, 16, 2), (50, 30, 16, 3), (1920, 1080, 16, 8)):
+        allp = np.concatenate([sharding.rank_pixels(rx, ry, tile, r, world) for r in range(world)])
+        assert allp.shape[0] == rx * ry and np.unique(allp).shape[0] == rx * ry
+        sizes = [len(sharding.rank_pixels(rx, ry, tile, r, world)) for r in range(world)]
+        assert max(sizes) - min(sizes) <= 2 * tile * tile * max(1, (rx // tile + 1) // world) or world > 2
+    sub = sharding.rank_pixels(1920, 1080, 16, 0, 1, tile_stride=110)
+    assert 74 * 256 <= sub.shape[0] <= 76 * 256 and np.unique(sub).shape[0] == sub.shape[0]
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    for p in (os.path.join(ROOT, "oracle"), os.path.join(ROOT, "neural-implicit-queries_b200"), ROOT):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import sharding
+    from niq_oracle import net, rays, tree
+    with np.load(os.path.join(ROOT, "tests", "golden", "mlps.npz")) as d:
+        params = {k.split("/", 1)[1]: d[k] for k in d.files if k.startswith("fox/")}
+    octx = net.AffineContext("affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = rays.look_at(eye)
+    rx, ry = 24, 16
+    roots, dirs = rays.generate_camera_rays(eye, look, up, res=rx, fov_deg=30., res_y=ry)
+    opts = rays.get_default_cast_opts()
+    cast = lambda f, p, r, d_, o: rays.cast_rays(f, p, r, d_, o)
+    t, h, c, n_ev = sharding.cast_rays_sharded((octx,), (params,), roots, dirs, opts, rx, ry, tile=8, cast_fn=cast)
+
+    build = lambda f, p, lo, hi, split_depth: tree.construct_uniform_unknown_levelset_tree(f, p, lo, hi, split_depth=split_depth)
+    lo, hi = sharding.tree_sharded(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), 9, top_depth=4, build_fn=build)
+    if rank == 0:
+        q.put((t, h, c, n_ev, lo, hi))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(600)
+def test_sharded_rays_and_tree_world2_gloo():
+    from niq_oracle import net, rays, tree
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    t, h, c, n_ev, lo, hi = q.get(timeout=500)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    params = sample_params("fox")
+    octx = net.AffineContext("affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = rays.look_at(eye)
+    roots, dirs = rays.generate_camera_rays(eye, look, up, res=24, fov_deg=30., res_y=16)
+    rt, rh, rc, _ = rays.cast_rays((octx,), (params,), roots, dirs, rays.get_default_cast_opts())
+    np.testing.assert_array_equal(t, rt)          # same oracle arithmetic per ray -> bit-identical after the gather
+    np.testing.assert_array_equal(h, rh)
+    np.testing.assert_array_equal(c, rc)
+    assert n_ev > 0
+    ref = tree.construct_uniform_unknown_levelset_tree(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), split_depth=9)
+    v = ref["unknown_node_valid"]
+    canon = lambda a, b: np.unique(np.concatenate((a, b), axis=1), axis=0)
+    np.testing.assert_array_equal(canon(lo, hi), canon(ref["unknown_node_lower"][v], ref["unknown_node_upper"][v]))
+    assert lo.shape[0] == int(v.sum())
