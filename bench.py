@@ -55,46 +55,62 @@ def camera_rays():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled every 200 ms
+    in-process through NVML (pynvml) -- a polling nvidia-smi process measurably delays kernel launches."""
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
 
     def __init__(self, device):
-        self.device, self.proc, self.lines = device, None, []
+        self.device, self.samples, self.stop_flag, self.thread, self.err = device, [], threading.Event(), None, None
+
+    def _resolve_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.device < len(ids) and ids[self.device].isdigit():
+                return int(ids[self.device])
+        return self.device
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
-                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self._resolve_index())
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception as e:           # noqa: BLE001
+            self.err = f"nvml unavailable: {e}"
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line)
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                mhz = float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    reasons = int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:        # noqa: BLE001
+                    reasons = int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                power = self.nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((mhz, reasons, power))
+            except Exception as e:       # noqa: BLE001
+                self.err = str(e)
+            self.stop_flag.wait(0.2)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.25)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
-        for line in self.lines:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons), "samples": len(sm)}
+        if self.thread is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no sampler"]}
+        self.stop_flag.set()
+        self.thread.join(2)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "no samples"]}
+        mhz = [s[0] for s in self.samples]
+        mask = 0
+        for s in self.samples:
+            mask |= s[1]
+        return {"sm_mhz": float(np.median(mhz)), "sm_max_mhz": self.smax,
+                "reasons": sorted(k for k, bit in self.REASONS.items() if mask & bit),
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(mhz)}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -123,6 +123,11 @@ int niq_mlp_create(niq_ctx* ctx, int32_t n_ops, const niq_op_desc* ops, niq_mlp*
 int niq_mlp_destroy(niq_mlp* mlp);
 /* MACs of one row through the net (sum of in*out over dense/spatial layers) -- SURVEY.md 8(d) "M"     */
 int niq_mlp_macs(const niq_mlp* mlp, int64_t* macs);
+/* relative half-width of the near-tie band this MLP's bounds are flagged with: 1e-5 for relu-only nets, 2e-4
+ * for nets with elu (the reference's elu rule, src/affine_layers.py:59-97, is ill-conditioned in float32:
+ * delta = |r_upper - r_lower|/2 cancels O(1) terms).  A bound is near-tie iff it lies within
+ * rel * (max(|lower|,|upper|) + sum_j|base_j A_j| + |b|) of +-offset.                                      */
+int niq_mlp_tie_rel(const niq_mlp* mlp, float* rel);
 
 /* ---- primitives ------------------------------------------------------------------------------ */
 /* f(x): src/mlp.py:96-113 with the 'default' rules.  x (n,3) -> f (n).  `scale` (n) optional (NULL): the
@@ -133,7 +138,7 @@ int niq_eval_points(niq_ctx* ctx, const niq_mlp* mlp, int64_t n, const float* x,
 /* classify_general_box: src/affine.py:34-55 (+ :109-125).  center (n,3), vecs (n,v,3), v in 1..3 for the
  * fixed-row modes (interval / affine_fixed), any v >= 1 for affine_all / affine_truncate.
  * Outputs (each optional, NULL to skip): label (n) int32 SIGN_*, lower/upper (n) float32 bounds,
- * near_tie (n) uint8 = bound within 1e-5*(|base|+rad) of +-offset.                                     */
+ * near_tie (n) uint8 = bound within the band of niq_mlp_tie_rel of +-offset.                             */
 int niq_classify_general_boxes(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, int64_t n,
                                const float* center, const float* vecs, int32_t v, float offset,
                                int32_t* label, float* lower, float* upper, uint8_t* near_tie, int mem);

@@ -28,7 +28,7 @@ SYMBOLS = (
     "niq_last_error", "niq_version", "niq_ctx_create", "niq_ctx_destroy", "niq_ctx_sync", "niq_ctx_device_info",
     "niq_ctx_launch_count", "niq_ctx_timer_start", "niq_ctx_timer_stop", "niq_ctx_kernel_ms",
     "niq_ctx_kernel_timing", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
-    "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_eval_points",
+    "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
     "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_tree_build", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
     "niq_mesh_count", "niq_mesh_copy", "niq_mesh_destroy", "niq_mc_tables", "niq_find_any_intersection",
@@ -259,6 +259,9 @@ class Mlp:
         macs = C.c_int64()
         check(lib().niq_mlp_macs(self.handle, C.byref(macs)))
         self.macs = macs.value
+        rel = C.c_float()
+        check(lib().niq_mlp_tie_rel(self.handle, C.byref(rel)))
+        self.tie_rel = rel.value
 
     def close(self):
         if self.handle:

@@ -233,6 +233,28 @@ extern "C" int niq_measure_fp32_peak(niq_ctx* c, float* tflops) {
     return NIQ_OK;
 }
 
+// development probe (tools/): FFMA rate at a given occupancy -- blocks per SM x threads per block
+extern "C" int niq_probe_ffma(niq_ctx* c, int blocks_per_sm, int threads, float* tflops) {
+    if (!c || !tflops || threads <= 0 || threads > 256) return fail(NIQ_EINVAL, "bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf out(c);
+    TRY(out.alloc(16));
+    const int iters = 8192, blocks = c->prop.multiProcessorCount * blocks_per_sm;
+    float best = 0.f;
+    for (int rep = 0; rep < 4; ++rep) {
+        CU(cudaEventRecord(c->t0, c->stream));
+        k_ffma_peak<<<blocks, threads, 0, c->stream>>>(out.as<float>(), iters, 0.999f, 0.001f);
+        CU(cudaEventRecord(c->t1, c->stream));
+        CU(cudaEventSynchronize(c->t1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->t0, c->t1));
+        const double flop = 2.0 * 16 * 8 * (double)iters * threads * (double)blocks;
+        if (rep > 0) best = std::max(best, (float)(flop / (ms * 1e-3) / 1e12));
+    }
+    *tflops = best;
+    return NIQ_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // MLP packing
 // ------------------------------------------------------------------------------------------------
@@ -367,6 +389,8 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
     NetDev& nd = m->net;
     nd.n_layers = (int)m->layers.size();
     nd.n_nets = 1;
+    nd.tie_rel = 1e-5f;
+    for (const HostLayer& L : m->layers) if (L.act == ACT_ELU) nd.tie_rel = 2e-4f;   // ELU rule conditioning
     for (size_t l = 0; l < m->layers.size(); ++l) {
         const HostLayer& L = m->layers[l];
         LayerDev& D = nd.layers[l];
@@ -375,7 +399,7 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
         D.first_of_net = l == 0; D.last_of_net = L.dot;
         D.chunk_begin = n_chunks;
         const int row = L.dot ? 1 : L.out_pad;
-        int kc_max = L.dot ? L.in_pad : std::max(4, (kChunkFloats / row) / 4 * 4);
+        int kc_max = L.dot ? L.in_pad : std::max(8, (kChunkFloats / row) / 8 * 8);   // multiple of 8: pipelined main loop
         for (int k0 = 0; k0 < L.in_pad; k0 += kc_max) {
             if (n_chunks >= kMaxChunks) { niq_mlp_destroy(m); return fail(NIQ_EUNSUPPORTED, "weight stream needs more than %d chunks", kMaxChunks); }
             ChunkDev& C = nd.chunks[n_chunks++];
@@ -397,6 +421,11 @@ extern "C" int niq_mlp_destroy(niq_mlp* m) {
     if (m->d_weights) cudaFree(m->d_weights);
     if (m->d_bias) cudaFree(m->d_bias);
     delete m;
+    return NIQ_OK;
+}
+extern "C" int niq_mlp_tie_rel(const niq_mlp* m, float* rel) {
+    if (!m || !rel) return fail(NIQ_EINVAL, "bad argument");
+    *rel = m->net.tie_rel;
     return NIQ_OK;
 }
 extern "C" int niq_mlp_macs(const niq_mlp* m, int64_t* macs) {
@@ -700,6 +729,7 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
             }
             for (int k = 0; k < s.n_chunks; ++k) net.chunks[net.n_chunks + k] = s.chunks[k];
             net.n_layers += s.n_layers; net.n_chunks += s.n_chunks;
+            net.tie_rel = std::max(net.tie_rel, s.tie_rel);
             wmax = std::max(wmax, mlps[f]->wmax);
         }
         net.n_nets = n_funcs;

@@ -24,14 +24,18 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef NIQ_VARIANT
+#define NIQ_VARIANT 0      // development probes only (tools/engine_probe.py); the product is variant 0
+#endif
+
 namespace niq {
 
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
 
 constexpr int kMaxLayers = 32;     // layers of all nets of one launch (cast_rays concatenates funcs)
 constexpr int kMaxChunks = 192;
-constexpr int kChunkFloats = 8192; // 32 KB per stage
-constexpr int kStages = 3;
+constexpr int kChunkFloats = 16384; // 64 KB per stage (a 256-wide layer is 4 chunks; layers up to 128 wide are 1)
+constexpr int kStages = 2;
 constexpr int kWarps = 8;          // compute warps per CTA
 constexpr int kThreads = kWarps * 32;
 
@@ -53,7 +57,8 @@ struct ChunkDev {
 };
 
 struct NetDev {               // passed by value (__grid_constant__) to every engine kernel
-    int n_layers, n_chunks, n_nets, pad_;
+    int n_layers, n_chunks, n_nets;
+    float tie_rel;            // near-tie band: 1e-5 (relu-only nets) or 2e-4 (nets with elu)
     LayerDev layers[kMaxLayers];
     ChunkDev chunks[kMaxChunks];
 };
@@ -95,6 +100,24 @@ __device__ __forceinline__ void fence_barrier_init() {
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// Packed FP32 (Blackwell FFMA2, PTX fma.rn.f32x2): two IEEE fp32 FMAs per instruction on a 64-bit register pair.
+// Same results as two fmaf(); half the issue slots and register-file reads per FMA.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float x, float y) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& x, float& y) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v));
+}
+__device__ __forceinline__ f32x2 ffma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 abs2(f32x2 v) { return v & 0x7fffffff7fffffffull; }
+
 // ------------------------------------------------------------------------------------------------
 // Tile descriptors: which rows a thread carries and how the activation couples them.
 //   row kinds: B = base, A = affine coefficient, E = interval error (multiplies |A|), P = point
@@ -128,10 +151,15 @@ __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x)
 
 // relu linearisation on [l,u]  (reference src/affine_layers.py:34-56)
 __device__ __forceinline__ void relu_lin(float l, float u, float& alpha, float& beta, float& delta) {
-    float a = (fmaxf(u, 0.f) - fmaxf(l, 0.f)) / (u - l);
+    // alpha = (relu(u) - relu(l)) / (u - l), then the l >= 0 / u < 0 overrides.  Only the straddling case
+    // l < 0 < u needs the quotient, and there relu(u) - relu(l) == u exactly; dividing 1/1 elsewhere keeps
+    // the IEEE division on its fast path (0/x and x/0 take the slow subroutine) without changing any result:
+    //   l >= 0 -> 1 ; u < 0 -> 0 ; u == 0 (l < 0) -> 0/(0-l) = 0 ; l == u == 0 is covered by l >= 0.
+    const bool straddle = (l < 0.f) && (u > 0.f);
+    float a = (straddle ? u : 1.f) / (straddle ? (u - l) : 1.f);
+    if (!straddle) a = 0.f;                    // u <= 0 (and nan bounds: comparisons false -> nan_to_num -> 0)
     if (l >= 0.f) a = 1.f;
-    if (u < 0.f) a = 0.f;
-    if (a != a) a = 0.f;                       // nan_to_num(nan=0)
+    if (a != a) a = 0.f;                       // inf/inf -> nan -> 0 (nan_to_num(nan=0))
     a = fminf(fmaxf(a, 0.f), 1.f);             // also maps +inf -> 1 like nan_to_num + clip
     alpha = a;
     beta = (fmaxf(l, 0.f) - a * l) * 0.5f;
@@ -255,13 +283,51 @@ struct Engine {
         __syncthreads();
     }
 
+    // activation fragment: 4 consecutive k of every row this thread carries
+    __device__ __forceinline__ void load_act(float4 (&a)[ROWS], const float* p) const {
+#pragma unroll
+        for (int n = 0; n < NT; ++n)
+#pragma unroll
+            for (int r = 0; r < RT; ++r)
+                a[n * RT + r] = *reinterpret_cast<const float4*>(p + (n * G::TPW * RT + r) * G::S);
+    }
+    // 4 k-steps of the outer product on packed column pairs: acc[r][p] holds columns (2p, 2p+1) of the thread's
+    // 8.  (w0,w1) hold the weight row of the first k on entry and of the k AFTER the group on exit; wnext points
+    // at the weight row of the group's second k.  The err row multiplies |A| (reference src/affine_layers.py:27).
+    __device__ __forceinline__ void fma_group(f32x2 (&acc)[ROWS][4], const float4 (&a)[ROWS], ulonglong2& w0, ulonglong2& w1,
+                                              const float* wnext, int wstride, int dcol) const {
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const ulonglong2 n0 = *reinterpret_cast<const ulonglong2*>(wnext + jj * wstride);
+            const ulonglong2 n1 = *reinterpret_cast<const ulonglong2*>(wnext + jj * wstride + dcol);
+            const f32x2 wv[4] = {w0.x, w0.y, w1.x, w1.y};
+            f32x2 wa[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wa[c] = abs2(wv[c]);
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const float av = jj == 0 ? a[r].x : jj == 1 ? a[r].y : jj == 2 ? a[r].z : a[r].w;
+                const f32x2 ap = pack2(av, av);
+                if (Tile::is_err(r % RT)) {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = ffma2(ap, wa[c], acc[r][c]);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) acc[r][c] = ffma2(ap, wv[c], acc[r][c]);
+                }
+            }
+            w0 = n0;
+            w1 = n1;
+        }
+    }
+
     // ---- one hidden layer: acc[rows][8] = act[rows][:K] @ W[:K][my 8 columns] -----------------------
     __device__ __forceinline__ void hidden_layer(const LayerDev& L) {
-        float acc[ROWS][8];
+        f32x2 acc2[ROWS][4];
 #pragma unroll
         for (int r = 0; r < ROWS; ++r)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[r][c] = 0.f;
+            for (int c = 0; c < 4; ++c) acc2[r][c] = 0ull;
 
         const int cg_l = L.out_pad >> 3;                 // active column groups of this layer
         const bool active = cg < cg_l;
@@ -275,37 +341,42 @@ struct Engine {
                 const float* wrow = w + col0;
                 const int wstride = L.out_pad;
                 const int dcol = col1 - col0;
-                for (int j = 0; j < C.kc; j += 4) {
-                    float4 a4[ROWS];
-#pragma unroll
-                    for (int n = 0; n < NT; ++n)
-#pragma unroll
-                        for (int r = 0; r < RT; ++r)
-                            a4[n * RT + r] = *reinterpret_cast<const float4*>(
-                                a_base + (n * G::TPW * RT + r) * G::S + C.k0 + j);
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float4 w0 = *reinterpret_cast<const float4*>(wrow + (j + jj) * wstride);
-                        const float4 w1 = *reinterpret_cast<const float4*>(wrow + (j + jj) * wstride + dcol);
-                        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-                        float wa[8];
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) wa[c] = fabsf(wv[c]);
-#pragma unroll
-                        for (int r = 0; r < ROWS; ++r) {
-                            const float a = jj == 0 ? a4[r].x : jj == 1 ? a4[r].y : jj == 2 ? a4[r].z : a4[r].w;
-                            if (Tile::is_err(r % RT)) {
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a, wa[c], acc[r][c]);
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 8; ++c) acc[r][c] = fmaf(a, wv[c], acc[r][c]);
-                            }
-                        }
+                const float* arow = a_base + C.k0;
+                if ((C.kc & 7) == 0) {
+                    // Software-pipelined main loop, 8 k per trip: register double buffers for the activation
+                    // fragments (two float4 sets, 4 k each) and for the weight row of the NEXT k, so every LDS
+                    // is issued one stage ahead of the FFMAs that consume it (a warp covers its own latency).
+                    // The loads of the last trip run past the chunk / row end into padding or the neighbouring
+                    // stage: in-bounds of the CTA's shared memory, never consumed.
+                    float4 aA[ROWS], aB[ROWS];
+                    ulonglong2 w0, w1;
+                    load_act(aA, arow);
+                    w0 = *reinterpret_cast<const ulonglong2*>(wrow);
+                    w1 = *reinterpret_cast<const ulonglong2*>(wrow + dcol);
+                    for (int j = 0; j < C.kc; j += 8) {
+                        load_act(aB, arow + j + 4);
+                        fma_group(acc2, aA, w0, w1, wrow + (j + 1) * wstride, wstride, dcol);
+                        load_act(aA, arow + j + 8);
+                        fma_group(acc2, aB, w0, w1, wrow + (j + 5) * wstride, wstride, dcol);
+                    }
+                } else {
+                    // short / odd K (the 3-D input layer, in_pad = 4): plain loop
+                    for (int j = 0; j < C.kc; j += 4) {
+                        float4 a4[ROWS];
+                        load_act(a4, arow + j);
+                        ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(wrow + j * wstride);
+                        ulonglong2 w1 = *reinterpret_cast<const ulonglong2*>(wrow + j * wstride + dcol);
+                        fma_group(acc2, a4, w0, w1, wrow + (j + 1) * wstride, wstride, dcol);
                     }
                 }
             }
         }
+
+        float acc[ROWS][8];
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) unpack2(acc2[r][c], acc[r][2 * c], acc[r][2 * c + 1]);
 
         // ---- epilogue: bias, activation rule, in-place write-back --------------------------------------
         if (active) {
@@ -369,7 +440,7 @@ struct Engine {
 
     // ---- final layer (out_dim == 1): out[r] = act[r][:K] . w + b ; also |.|-sum for point rows -----------
     // Results land in out[ROWS] (identical in all lanes of the tile group); pscale[ROWS] = sum|h_j w_j| + |b|
-    // for point rows (near-tie scale of sign tests).
+    // for point rows and for the base row (the magnitude the output was summed from: near-tie yardstick).
     __device__ __forceinline__ void dot_layer(const LayerDev& L, float out[ROWS], float pscale[ROWS]) {
 #pragma unroll
         for (int r = 0; r < ROWS; ++r) { out[r] = 0.f; pscale[r] = 0.f; }
@@ -388,8 +459,8 @@ struct Engine {
                         const int i = n * RT + r;
                         if (Tile::is_err(r)) out[i] = fmaf(a, wja, out[i]);
                         else out[i] = fmaf(a, wj, out[i]);
-                        const bool is_pt = Tile::has_group ? (r > Tile::n_aff + 1) : true;
-                        if (is_pt) pscale[i] = fmaf(fabsf(a), wja, pscale[i]);
+                        const bool want_scale = Tile::has_group ? (r > Tile::n_aff + 1 || r == 0) : true;
+                        if (want_scale) pscale[i] = fmaf(fabsf(a), wja, pscale[i]);
                     }
             }
         }
@@ -398,8 +469,8 @@ struct Engine {
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) {
                 out[i] += __shfl_xor_sync(0xffffffffu, out[i], off);
-                const bool is_pt = Tile::has_group ? ((i % RT) > Tile::n_aff + 1) : true;
-                if (is_pt) pscale[i] += __shfl_xor_sync(0xffffffffu, pscale[i], off);
+                const bool want_scale = Tile::has_group ? ((i % RT) > Tile::n_aff + 1 || (i % RT) == 0) : true;
+                if (want_scale) pscale[i] += __shfl_xor_sync(0xffffffffu, pscale[i], off);
             }
         }
         const float b = __ldg(L.bias);

@@ -236,9 +236,10 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                 for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
                 if (lane == 0) red[warp] = part;
                 if (tid == 32) {
-                    float s = 0.f;
-                    for (int j = 0; j < K; ++j) s = fmaf(base[j], __ldg(A + j), s);
+                    float s = 0.f, sa = 0.f;
+                    for (int j = 0; j < K; ++j) { s = fmaf(base[j], __ldg(A + j), s); sa = fmaf(fabsf(base[j]), fabsf(__ldg(A + j)), sa); }
                     s_fin[0] = s + __ldg(L.bias);
+                    s_fin[2] = sa + fabsf(__ldg(L.bias));
                 }
                 if (tid == 64) {
                     float s = 0.f;
@@ -254,7 +255,7 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                     if (g.lower) g.lower[box] = lo;
                     if (g.upper) g.upper[box] = up;
                     if (g.label) g.label[box] = label_of(lo, up, g.offset);
-                    if (g.near_tie) g.near_tie[box] = bound_near_tie(lo, up, g.offset) ? 1 : 0;
+                    if (g.near_tie) g.near_tie[box] = bound_near_tie(lo, up, g.offset, s_fin[2], net.tie_rel) ? 1 : 0;
                 }
                 __syncthreads();
             }

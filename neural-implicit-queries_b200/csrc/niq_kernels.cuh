@@ -7,7 +7,7 @@
 
 namespace niq {
 
-constexpr float kNearTieRel = 1e-5f;
+constexpr float kNearTieRel = 1e-5f;      // sign tests of point values; bounds use NetDev::tie_rel
 enum : int { SIGN_UNKNOWN = 0, SIGN_POSITIVE = 1, SIGN_NEGATIVE = 2 };
 
 // ------------------------------------------------------------------------------------------------
@@ -127,8 +127,9 @@ __device__ __forceinline__ int label_of(float lower, float upper, float offset) 
     if (upper < -offset) lab = SIGN_NEGATIVE;
     return lab;
 }
-__device__ __forceinline__ bool bound_near_tie(float lower, float upper, float offset) {
-    const float scale = fmaxf(fabsf(lower), fabsf(upper)) * kNearTieRel;
+// near-tie band of a bound: rel * (max(|lower|,|upper|) + sc), sc = sum_j |base_j A_j| + |b| of the last layer
+__device__ __forceinline__ bool bound_near_tie(float lower, float upper, float offset, float sc, float rel) {
+    const float scale = (fmaxf(fabsf(lower), fabsf(upper)) + sc) * rel;
     return fabsf(lower - offset) <= scale || fabsf(upper + offset) <= scale;
 }
 
@@ -170,7 +171,7 @@ k_classify_fixed(const __grid_constant__ NetDev net, const BoxSource src, long l
                     if (lower) lower[i] = lo;
                     if (upper) upper[i] = up;
                     if (label) label[i] = label_of(lo, up, offset);
-                    if (near_tie) near_tie[i] = bound_near_tie(lo, up, offset) ? 1 : 0;
+                    if (near_tie) near_tie[i] = bound_near_tie(lo, up, offset, ps[nn * 5], net.tie_rel) ? 1 : 0;
                 }
             }
         }
@@ -305,7 +306,7 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
                     float* d = eng.fin + (nn * E::G::TPW + eng.t) * 8;
                     d[0] = out[nn * 5]; d[1] = out[nn * 5 + 1]; d[2] = out[nn * 5 + 2];
                     d[3] = out[nn * 5 + 3]; d[4] = out[nn * 5 + 4];
-                    d[5] = ps[nn * 5 + 3]; d[6] = ps[nn * 5 + 4];
+                    d[5] = ps[nn * 5 + 3]; d[6] = ps[nn * 5 + 4]; d[7] = ps[nn * 5];
                 }
             }
             __syncwarp();
@@ -320,7 +321,7 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
                 const bool this_hit = (s0 != s1) || (v0 != v0) || (v1 != v1);   // sign(nan)=nan != anything
                 if (this_hit) hit_id = f + 1;
                 is_hit = is_hit || this_hit;
-                tie = tie || bound_near_tie(lo, up, 0.f) || fabsf(v0) <= kNearTieRel * d[5] ||
+                tie = tie || bound_near_tie(lo, up, 0.f, d[7], net.tie_rel) || fabsf(v0) <= kNearTieRel * d[5] ||
                       fabsf(v1) <= kNearTieRel * d[6];
             }
             __syncwarp();

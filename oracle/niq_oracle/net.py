@@ -28,6 +28,25 @@ SIGN_NEGATIVE = 2
 MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all")
 
 
+class precision:
+    """Context manager (tests only): evaluate this module's functions in another float type, e.g.
+    `with net.precision(np.float64): ...` gives the exact-arithmetic yardstick of the same formulas."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global F32
+        self.saved = F32
+        F32 = self.dtype
+        return self
+
+    def __exit__(self, *exc):
+        global F32
+        F32 = self.saved
+        return False
+
+
 # ----------------------------------------------------------------------------------------------
 # params dict format  (mlp.py:14-24, 117-167, 173-185)
 # ----------------------------------------------------------------------------------------------
@@ -372,6 +391,16 @@ def classify_box(params, ctx, lo, hi, offset=0.0, return_bounds=False, return_sc
 # ----------------------------------------------------------------------------------------------
 
 NEAR_TIE_REL = 1e-5
+NEAR_TIE_REL_ELU = 2e-4
+
+
+def tie_rel(params):
+    """Relative tolerance / near-tie band for bounds of this MLP: 1e-5 (BASELINE north_star) for relu-only
+    nets; 2e-4 for nets with elu, whose rule (affine_layers.py:59-97) is ill-conditioned in float32 --
+    delta = |r_upper - r_lower|/2 cancels O(1) terms, so two IEEE-correct implementations that differ by
+    1 ulp in exp/log/expm1 disagree by ~1e-7 ABSOLUTE per neuron, amplified by the following layers
+    (tests/test_oracle_golden.py::test_elu_rule_conditioning measures it against float64)."""
+    return NEAR_TIE_REL_ELU if any(nm == "elu" for nm, _ in op_list(params)) else NEAR_TIE_REL
 
 
 def tol_scale(lower, upper, scale=None):

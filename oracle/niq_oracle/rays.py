@@ -124,7 +124,7 @@ def _take_steps(funcs, params_tuple, opts, roots, dirs, t, step_size, n_substeps
             val_start = net.eval_points(params, pos_start)
             val_eps = net.eval_points(params, pos_eps)
             if tie is not None:
-                tie |= net.bound_near_tie(lo, up, 0.0, bsc)
+                tie |= net.bound_near_tie(lo, up, 0.0, bsc, rel=net.tie_rel(params))
                 tie |= _point_sign_near_tie(params, pos_start, val_start)
                 tie |= _point_sign_near_tie(params, pos_eps, val_eps)
             this_is_hit = _sign(val_start) != _sign(val_eps)

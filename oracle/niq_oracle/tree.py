@@ -103,7 +103,7 @@ def construct_uniform_unknown_levelset_tree(ctx, params, lower, upper, node_term
             bv, bl, bu = v3[ib], l3[ib], u3[ib]
             lab, lo_b, up_b, sc_b = net.classify_box(params, ctx, bl, bu, offset, return_scale=True)
             n_evals += int(bv.sum())
-            n_near_tie += int((net.bound_near_tie(lo_b, up_b, offset, sc_b) & bv).sum())
+            n_near_tie += int((net.bound_near_tie(lo_b, up_b, offset, sc_b, rel=net.tie_rel(params)) & bv).sum())
             split_dim = _argmax_first(bu - bl)
             for tag, sign in (("interior", net.SIGN_NEGATIVE), ("exterior", net.SIGN_POSITIVE)):
                 if tag in fin:
@@ -207,7 +207,7 @@ def find_any_intersection(ctx_tuple, params_tuple, lower, upper, eps, stats=None
         tB, loB, upB, scB = net.classify_box(pB, ctxB, lo, hi, return_scale=True)
         vA = net.eval_points(pA, pts.reshape(-1, 3)).reshape(nb, 7)
         vB = net.eval_points(pB, pts.reshape(-1, 3)).reshape(nb, 7)
-        n_tie += int(((net.bound_near_tie(loA, upA, 0.0, scA) | net.bound_near_tie(loB, upB, 0.0, scB)) & valid).sum())
+        n_tie += int(((net.bound_near_tie(loA, upA, 0.0, scA, rel=net.tie_rel(pA)) | net.bound_near_tie(loB, upB, 0.0, scB, rel=net.tie_rel(pB))) & valid).sum())
 
         near_A = is_small & ~_all_same_sign(vA)
         near_B = is_small & ~_all_same_sign(vB)
@@ -319,7 +319,7 @@ def closest_point(ctx, params, lower, upper, query_points, eps=0.001, batch_proc
         pts = (center[:, None, :] + ext[:, None, :] * _SAMPLE_OFFSETS[None, :, :]).astype(F32)
 
         lab, lo_b, up_b, sc_b = net.classify_box(params, ctx, lo, hi, return_scale=True)
-        n_tie += int((net.bound_near_tie(lo_b, up_b, 0.0, sc_b) & valid).sum())
+        n_tie += int((net.bound_near_tie(lo_b, up_b, 0.0, sc_b, rel=net.tie_rel(params)) & valid).sum())
         is_outside = (lab == net.SIGN_NEGATIVE) | (lab == net.SIGN_POSITIVE)
         vals = net.eval_points(params, pts.reshape(-1, 3)).reshape(-1, 7)
         spans = ~_all_same_sign(vals) & valid

@@ -245,8 +245,10 @@ CASES["mc_fox_d4_s2"] = (case_mc, ("fox", "affine_fixed", 4, 2))
 CASES["mc_bunny_d4_s3"] = (case_mc, ("bunny", "affine_fixed", 4, 3))
 CASES["isect_fixed"] = (case_intersection, ("affine_fixed", 0, [(0.3, (0.0, 0.1, 0.05)), (0.3, (1.2, 0.1, 0.05)), (0.3, (1.6, 0.1, 0.05)), (1.1, (0.9, -0.4, 0.3))]))
 CASES["isect_trunc64"] = (case_intersection, ("affine_truncate", 64, [(0.3, (1.2, 0.1, 0.05)), (0.3, (1.6, 0.1, 0.05))]))
-CASES["closest_fox_B32"] = (case_closest, ("fox", "affine_fixed", 6, 0.02, 32))
-CASES["closest_fox_Bbig"] = (case_closest, ("fox", "affine_fixed", 6, 0.02, 2 ** 20))
+# the stand-in runs vmap lanes in a Python loop, so the closest-point cases are kept to ~10k lanes; the two
+# window sizes give DIFFERENT results for query 2 (0.528 vs 0.430): the order dependence of SURVEY.md F6
+CASES["closest_fox_B4"] = (case_closest, ("fox", "affine_fixed", 3, 0.4, 4))
+CASES["closest_fox_B256"] = (case_closest, ("fox", "affine_fixed", 3, 0.4, 256))
 
 
 def run(name):
