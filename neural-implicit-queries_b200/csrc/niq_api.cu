@@ -269,11 +269,27 @@ struct niq_mlp {
     int wmax = 32;         // width class of the fixed-row engine
     int maxw_pad = 8;      // widest padded row (grow engine)
     int64_t macs = 0;
+    int total_floats = 0;  // packed weights of all layers
     int sum_act_out = 0;   // sum of out_dim over activation layers (affine_all growth)
     int max_act_out = 0;
 };
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+constexpr int kResidentPad = 512;   // floats after the resident weights: the pipelined loop over-reads one weight row
+
+// Decide where the weights of a launch live: resident in shared memory when everything fits beside the
+// activation buffers, otherwise streamed through the ring.  Returns the dynamic shared-memory size.
+template <class E>
+static size_t place_weights(niq_ctx* c, NetDev& net, int total_floats) {
+    const size_t res = E::smem_bytes(total_floats + kResidentPad);
+    if (res <= c->prop.sharedMemPerBlockOptin) {
+        net.resident = 1;
+        net.w_region_floats = total_floats + kResidentPad;
+        return res;
+    }
+    net.resident = 0;
+    return E::smem_bytes();
+}
 
 static bool invert3(const float* R, float* inv) {   // float32 Gauss-Jordan with partial pivoting
     float a[3][6];
@@ -406,11 +422,14 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
             C.k0 = k0; C.kc = std::min(kc_max, L.in_pad - k0);
             C.src = m->d_weights + L.w_off + (size_t)k0 * row;
             C.n_floats = (unsigned)(C.kc * row);
-            C.pad_ = 0;
+            C.smem_off = (int)(L.w_off + (size_t)k0 * row);
         }
         D.chunk_end = n_chunks;
     }
     nd.n_chunks = n_chunks;
+    nd.resident = 0;
+    nd.w_region_floats = (int)hw.size() + kResidentPad;
+    m->total_floats = (int)hw.size();
     *out = m;
     return NIQ_OK;
 }
@@ -447,35 +466,38 @@ static int grid_for(niq_ctx* c, long long n_pass) {
 }
 
 template <int WMAX>
-static int launch_classify_fixed_w(niq_ctx* c, const NetDev& net, const BoxSource& src, long long n, float offset,
+static int launch_classify_fixed_w(niq_ctx* c, NetDev net, int total_floats, const BoxSource& src, long long n, float offset,
                                    int* label, float* lower, float* upper, unsigned char* tie) {
     using E = Engine<WMAX, TileBox3>;
-    TRY(set_smem(k_classify_fixed<WMAX>, E::smem_bytes()));
+    const size_t smem = place_weights<E>(c, net, total_floats);
+    TRY(set_smem(k_classify_fixed<WMAX>, smem));
     const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
     LaunchTimer lt(c, 0);
-    k_classify_fixed<WMAX><<<grid_for(c, n_pass), kThreads, E::smem_bytes(), c->stream>>>(net, src, n, offset, label, lower, upper, tie);
+    k_classify_fixed<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, src, n, offset, label, lower, upper, tie);
     CU(cudaGetLastError());
     return NIQ_OK;
 }
 template <int WMAX>
-static int launch_eval_points_w(niq_ctx* c, const NetDev& net, const PointSource& src, long long n, float* f, float* scale) {
+static int launch_eval_points_w(niq_ctx* c, NetDev net, int total_floats, const PointSource& src, long long n, float* f, float* scale) {
     using E = Engine<WMAX, TilePts>;
-    TRY(set_smem(k_eval_points<WMAX>, E::smem_bytes()));
+    const size_t smem = place_weights<E>(c, net, total_floats);
+    TRY(set_smem(k_eval_points<WMAX>, smem));
     const long long per = kWarps * E::WARP_ROWS;
     LaunchTimer lt(c, 0);
-    k_eval_points<WMAX><<<grid_for(c, (n + per - 1) / per), kThreads, E::smem_bytes(), c->stream>>>(net, src, n, f, scale);
+    k_eval_points<WMAX><<<grid_for(c, (n + per - 1) / per), kThreads, smem, c->stream>>>(net, src, n, f, scale);
     CU(cudaGetLastError());
     return NIQ_OK;
 }
 template <int WMAX>
-static int launch_cast_rays_w(niq_ctx* c, const NetDev& net, const CastOpts& o, long long n, int interval,
+static int launch_cast_rays_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, long long n, int interval,
                               const float* roots, const float* dirs, float* t, int* hit, int* cnt,
                               unsigned char* tie, unsigned long long* queue) {
     using E = Engine<WMAX, TileRay>;
-    TRY(set_smem(k_cast_rays<WMAX>, E::smem_bytes()));
+    const size_t smem = place_weights<E>(c, net, total_floats);
+    TRY(set_smem(k_cast_rays<WMAX>, smem));
     const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
     LaunchTimer lt(c, 0);
-    k_cast_rays<WMAX><<<grid_for(c, n_pass), kThreads, E::smem_bytes(), c->stream>>>(net, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
+    k_cast_rays<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
     CU(cudaGetLastError());
     return NIQ_OK;
 }
@@ -483,19 +505,19 @@ static int launch_classify_fixed(niq_ctx* c, const niq_mlp* m, const BoxSource& 
                                  int* label, float* lower, float* upper, unsigned char* tie) {
     if (n <= 0) return NIQ_OK;
     switch (m->wmax) {
-        case 32: return launch_classify_fixed_w<32>(c, m->net, src, n, offset, label, lower, upper, tie);
-        case 64: return launch_classify_fixed_w<64>(c, m->net, src, n, offset, label, lower, upper, tie);
-        case 128: return launch_classify_fixed_w<128>(c, m->net, src, n, offset, label, lower, upper, tie);
-        default: return launch_classify_fixed_w<256>(c, m->net, src, n, offset, label, lower, upper, tie);
+        case 32: return launch_classify_fixed_w<32>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+        case 64: return launch_classify_fixed_w<64>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+        case 128: return launch_classify_fixed_w<128>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+        default: return launch_classify_fixed_w<256>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
     }
 }
 static int launch_eval_points(niq_ctx* c, const niq_mlp* m, const PointSource& src, long long n, float* f, float* scale) {
     if (n <= 0) return NIQ_OK;
     switch (m->wmax) {
-        case 32: return launch_eval_points_w<32>(c, m->net, src, n, f, scale);
-        case 64: return launch_eval_points_w<64>(c, m->net, src, n, f, scale);
-        case 128: return launch_eval_points_w<128>(c, m->net, src, n, f, scale);
-        default: return launch_eval_points_w<256>(c, m->net, src, n, f, scale);
+        case 32: return launch_eval_points_w<32>(c, m->net, m->total_floats, src, n, f, scale);
+        case 64: return launch_eval_points_w<64>(c, m->net, m->total_floats, src, n, f, scale);
+        case 128: return launch_eval_points_w<128>(c, m->net, m->total_floats, src, n, f, scale);
+        default: return launch_eval_points_w<256>(c, m->net, m->total_floats, src, n, f, scale);
     }
 }
 
@@ -717,7 +739,7 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
     if (is_fixed_mode(&cfgs[0])) {
         // concatenate the funcs' layer / chunk tables into one stream
         NetDev net{};
-        int wmax = 32;
+        int wmax = 32, total_floats = 0;
         for (int f = 0; f < n_funcs; ++f) {
             const NetDev& s = mlps[f]->net;
             if (net.n_layers + s.n_layers > kMaxLayers || net.n_chunks + s.n_chunks > kMaxChunks)
@@ -727,7 +749,11 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
                 L.chunk_begin += net.n_chunks; L.chunk_end += net.n_chunks;
                 net.layers[net.n_layers + l] = L;
             }
-            for (int k = 0; k < s.n_chunks; ++k) net.chunks[net.n_chunks + k] = s.chunks[k];
+            for (int k = 0; k < s.n_chunks; ++k) {
+                net.chunks[net.n_chunks + k] = s.chunks[k];
+                net.chunks[net.n_chunks + k].smem_off += total_floats;     // nets sit one after the other when resident
+            }
+            total_floats += mlps[f]->total_floats;
             net.n_layers += s.n_layers; net.n_chunks += s.n_chunks;
             net.tie_rel = std::max(net.tie_rel, s.tie_rel);
             wmax = std::max(wmax, mlps[f]->wmax);
@@ -738,10 +764,10 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
         CU(cudaMemsetAsync(queue.p, 0, 8, c->stream));
         const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
         switch (wmax) {
-            case 32: TRY(launch_cast_rays_w<32>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
-            case 64: TRY(launch_cast_rays_w<64>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
-            case 128: TRY(launch_cast_rays_w<128>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
-            default: TRY(launch_cast_rays_w<256>(c, net, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            case 32: TRY(launch_cast_rays_w<32>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            case 64: TRY(launch_cast_rays_w<64>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            case 128: TRY(launch_cast_rays_w<128>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            default: TRY(launch_cast_rays_w<256>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
         }
     } else {
         return fail(NIQ_EUNSUPPORTED, "cast_rays with affine_all / affine_truncate runs through the host-level stepping loop of the Python layer");

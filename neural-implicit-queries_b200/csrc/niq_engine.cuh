@@ -53,11 +53,14 @@ struct ChunkDev {
     const float* src;         // device, 16-byte aligned; rows [k0, k0+kc) of the layer's padded A, contiguous
     unsigned int n_floats;    // multiple of 4
     int k0, kc;
-    int pad_;
+    int smem_off;             // resident mode: float offset of this chunk inside the shared-memory weight region
 };
 
 struct NetDev {               // passed by value (__grid_constant__) to every engine kernel
     int n_layers, n_chunks, n_nets;
+    int resident;             // 1: ALL weights of the launch fit in shared memory and are loaded once (no ring,
+                              //    no CTA barrier in the layer loop: warps run independently); 0: streamed ring
+    int w_region_floats;      // resident: size of the weight region (incl. over-read padding)
     float tie_rel;            // near-tie band: 1e-5 (relu-only nets) or 2e-4 (nets with elu)
     LayerDev layers[kMaxLayers];
     ChunkDev chunks[kMaxChunks];
@@ -149,6 +152,19 @@ struct TilePts {    // [P x 8]
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float elu_f(float x) { return x > 0.f ? x : expm1f(x); }
 
+// n / d without the branch to the IEEE slow path: reciprocal seed + one Newton step on the reciprocal + one
+// residual correction of the quotient.  For normal, well-scaled operands (the rules below only divide
+// 0 < n <= d or O(1) differences) this is the correctly rounded quotient except in rare 1-ulp cases --
+// far inside every tolerance of this backend -- and it keeps the 16 neurons of a thread in
+// one basic block.  inf / nan operands propagate to nan like the IEEE quotient inf/inf.
+__device__ __forceinline__ float div_nr(float n, float d) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d));
+    r = fmaf(fmaf(-d, r, 1.f), r, r);
+    const float q = n * r;
+    return fmaf(fmaf(-d, q, n), r, q);
+}
+
 // relu linearisation on [l,u]  (reference src/affine_layers.py:34-56)
 __device__ __forceinline__ void relu_lin(float l, float u, float& alpha, float& beta, float& delta) {
     // alpha = (relu(u) - relu(l)) / (u - l), then the l >= 0 / u < 0 overrides.  Only the straddling case
@@ -156,7 +172,7 @@ __device__ __forceinline__ void relu_lin(float l, float u, float& alpha, float& 
     // the IEEE division on its fast path (0/x and x/0 take the slow subroutine) without changing any result:
     //   l >= 0 -> 1 ; u < 0 -> 0 ; u == 0 (l < 0) -> 0/(0-l) = 0 ; l == u == 0 is covered by l >= 0.
     const bool straddle = (l < 0.f) && (u > 0.f);
-    float a = (straddle ? u : 1.f) / (straddle ? (u - l) : 1.f);
+    float a = div_nr(straddle ? u : 1.f, straddle ? (u - l) : 1.f);
     if (!straddle) a = 0.f;                    // u <= 0 (and nan bounds: comparisons false -> nan_to_num -> 0)
     if (l >= 0.f) a = 1.f;
     if (a != a) a = 0.f;                       // inf/inf -> nan -> 0 (nan_to_num(nan=0))
@@ -206,8 +222,8 @@ struct Engine {
     static constexpr int WARP_FLOATS = WARP_ROWS * G::S;
     static constexpr int CTA_TILES = kWarps * SLOTS;
 
-    static constexpr size_t smem_bytes() {
-        return 64 + sizeof(float) * (size_t)(kStages * kChunkFloats + kWarps * WARP_FLOATS + kWarps * SLOTS * 8);
+    static constexpr size_t smem_bytes(int w_region_floats = kStages * kChunkFloats) {
+        return 64 + sizeof(float) * ((size_t)w_region_floats + kWarps * WARP_FLOATS + kWarps * SLOTS * 8);
     }
 
     // shared-memory carve-up
@@ -217,6 +233,7 @@ struct Engine {
     float* fin;            // this warp's [SLOTS][8] final scalars / scratch
     const NetDev& net;
     int warp, lane, t, cg;
+    bool resident;
     // weight pipeline state (identical in every thread)
     unsigned int seq_consumed, seq_issued;
 
@@ -227,7 +244,8 @@ struct Engine {
         cg = lane % G::CG;
         full = reinterpret_cast<uint64_t*>(smem_raw);
         stage = reinterpret_cast<float*>(smem_raw + 64);
-        float* acts = stage + kStages * kChunkFloats;
+        resident = net.resident != 0;
+        float* acts = stage + (resident ? net.w_region_floats : kStages * kChunkFloats);
         act = acts + warp * WARP_FLOATS;
         fin = acts + kWarps * WARP_FLOATS + warp * SLOTS * 8;
         seq_consumed = 0;
@@ -237,9 +255,29 @@ struct Engine {
             fence_barrier_init();
         }
         __syncthreads();
-        // prologue: fill the ring
-        if (threadIdx.x == 0) {
-            for (int s = 0; s < kStages - 1; ++s) issue_next();
+        if (resident) {
+            // the whole weight set is staged ONCE: one mbarrier, one bulk copy per chunk
+            if (threadIdx.x == 0) {
+                uint32_t total = 0;
+                for (int c = 0; c < net.n_chunks; ++c) total += net.chunks[c].n_floats * 4u;
+                mbar_expect_tx(&full[0], total);
+                for (int c = 0; c < net.n_chunks; ++c)
+                    tma_bulk_g2s(stage + net.chunks[c].smem_off, net.chunks[c].src, net.chunks[c].n_floats * 4u, &full[0]);
+            }
+            mbar_wait(&full[0], 0u);
+#if !(NIQ_VARIANT & 4)
+            // De-phase the two warps that share an SM sub-partition (warps w and w+4): every warp repeats the same
+            // period (FMA-bound main loop, then the latency-bound activation epilogue); started together they
+            // stay in lock-step, so the FMA pipe idles during both epilogues.  Half a layer of head start makes
+            // one warp's epilogue overlap the other's main loop, and with no CTA barrier it stays that way.
+            if (warp >= 4) {
+                const long long t0 = clock64();
+                const long long wait_cycles = 40ll * net.layers[net.n_layers > 1 ? 1 : 0].in_pad;
+                while (clock64() - t0 < wait_cycles) {}
+            }
+#endif
+        } else if (threadIdx.x == 0) {
+            for (int s = 0; s < kStages - 1; ++s) issue_next();   // prologue: fill the ring
         } else {
             seq_issued = kStages - 1;
         }
@@ -260,7 +298,8 @@ struct Engine {
     }
 
     // Wait for the next chunk of the stream, recycle the stage consumed before it, return its smem pointer.
-    __device__ __forceinline__ const float* acquire_chunk() {
+    __device__ __forceinline__ const float* acquire_chunk(int ch) {
+        if (resident) return stage + net.chunks[ch].smem_off;
         const unsigned s = seq_consumed % kStages;
         mbar_wait(&full[s], (seq_consumed / kStages) & 1u);
         __syncthreads();                     // everyone is done with chunk seq_consumed-1 -> its stage is free
@@ -275,6 +314,7 @@ struct Engine {
 
     // Every thread must call this before the kernel exits: no bulk copy may be in flight into a dead CTA.
     __device__ __forceinline__ void drain() {
+        if (resident) return;
         while (seq_consumed < seq_issued) {
             const unsigned s = seq_consumed % kStages;
             mbar_wait(&full[s], (seq_consumed / kStages) & 1u);
@@ -301,16 +341,28 @@ struct Engine {
             const ulonglong2 n0 = *reinterpret_cast<const ulonglong2*>(wnext + jj * wstride);
             const ulonglong2 n1 = *reinterpret_cast<const ulonglong2*>(wnext + jj * wstride + dcol);
             const f32x2 wv[4] = {w0.x, w0.y, w1.x, w1.y};
+#if !(NIQ_VARIANT & 1)
             f32x2 wa[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) wa[c] = abs2(wv[c]);
+#endif
 #pragma unroll
             for (int r = 0; r < ROWS; ++r) {
                 const float av = jj == 0 ? a[r].x : jj == 1 ? a[r].y : jj == 2 ? a[r].z : a[r].w;
                 const f32x2 ap = pack2(av, av);
                 if (Tile::is_err(r % RT)) {
+#if NIQ_VARIANT & 1
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {       // scalar FFMA with the |.| operand modifier: no LOP3
+                        float wx, wy, ax, ay;
+                        unpack2(wv[c], wx, wy);
+                        unpack2(acc[r][c], ax, ay);
+                        acc[r][c] = pack2(fmaf(av, fabsf(wx), ax), fmaf(av, fabsf(wy), ay));
+                    }
+#else
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[r][c] = ffma2(ap, wa[c], acc[r][c]);
+#endif
                 } else {
 #pragma unroll
                     for (int c = 0; c < 4; ++c) acc[r][c] = ffma2(ap, wv[c], acc[r][c]);
@@ -318,6 +370,59 @@ struct Engine {
             }
             w0 = n0;
             w1 = n1;
+        }
+    }
+
+    // bias + activation rule on the thread's NT x 8 neurons (reference src/affine_layers.py:34-97 and
+    // src/affine.py:164-182 for the group rows, src/mlp.py:283-293 for the point rows), stage by stage over the 8
+    // columns so that independent chains sit next to each other
+    template <int ACT>
+    __device__ __forceinline__ void epilogue(float (&acc)[ROWS][8], const float (&bias)[8]) const {
+#pragma unroll
+        for (int n = 0; n < NT; ++n) {
+            if (Tile::has_group) {
+                constexpr int ie = Tile::n_aff + 1;      // err row index inside the tile
+                float base[8], rad[8];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) base[c] = acc[n * RT][c] + bias[c];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    float r = 0.f;
+#pragma unroll
+                    for (int k = 1; k <= Tile::n_aff; ++k) r += fabsf(acc[n * RT + k][c]);
+                    rad[c] = r + acc[n * RT + ie][c];
+                }
+                if (ACT != ACT_NONE) {
+                    float alpha[8], beta[8], delta[8];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (ACT == ACT_RELU) relu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
+                        else elu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
+                    }
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        base[c] = alpha[c] * base[c] + beta[c];
+#pragma unroll
+                        for (int k = 1; k <= Tile::n_aff; ++k) acc[n * RT + k][c] = alpha[c] * acc[n * RT + k][c];
+                        acc[n * RT + ie][c] = alpha[c] * acc[n * RT + ie][c] + delta[c];
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 8; ++c) acc[n * RT][c] = base[c];
+            }
+#pragma unroll
+            for (int r = 0; r < RT; ++r) {
+                const bool is_pt = Tile::has_group ? (r > Tile::n_aff + 1) : true;
+                if (is_pt) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        float x = acc[n * RT + r][c] + bias[c];
+                        if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
+                        else if (ACT == ACT_ELU) x = elu_f(x);
+                        acc[n * RT + r][c] = x;
+                    }
+                }
+            }
         }
     }
 
@@ -335,7 +440,7 @@ struct Engine {
         const float* a_base = row_ptr(0, t, 0);
 
         for (int ch = L.chunk_begin; ch < L.chunk_end; ++ch) {
-            const float* w = acquire_chunk();
+            const float* w = acquire_chunk(ch);
             const ChunkDev& C = net.chunks[ch];
             if (active) {
                 const float* wrow = w + col0;
@@ -353,6 +458,7 @@ struct Engine {
                     load_act(aA, arow);
                     w0 = *reinterpret_cast<const ulonglong2*>(wrow);
                     w1 = *reinterpret_cast<const ulonglong2*>(wrow + dcol);
+#pragma unroll 2
                     for (int j = 0; j < C.kc; j += 8) {
                         load_act(aB, arow + j + 4);
                         fma_group(acc2, aA, w0, w1, wrow + (j + 1) * wstride, wstride, dcol);
@@ -387,41 +493,11 @@ struct Engine {
                 bias[0] = b0.x; bias[1] = b0.y; bias[2] = b0.z; bias[3] = b0.w;
                 bias[4] = b1.x; bias[5] = b1.y; bias[6] = b1.z; bias[7] = b1.w;
             }
-#pragma unroll
-            for (int n = 0; n < NT; ++n) {
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    if (Tile::has_group) {
-                        constexpr int ie = Tile::n_aff + 1;      // err row index inside the tile
-                        float base = acc[n * RT][c] + bias[c];
-                        float rad = 0.f;
-#pragma unroll
-                        for (int k = 1; k <= Tile::n_aff; ++k) rad += fabsf(acc[n * RT + k][c]);
-                        rad += acc[n * RT + ie][c];
-                        if (L.act != ACT_NONE) {
-                            float alpha, beta, delta;
-                            const float lo = base - rad, up = base + rad;
-                            if (L.act == ACT_RELU) relu_lin(lo, up, alpha, beta, delta);
-                            else elu_lin(lo, up, alpha, beta, delta);
-                            base = alpha * base + beta;
-#pragma unroll
-                            for (int k = 1; k <= Tile::n_aff; ++k) acc[n * RT + k][c] = alpha * acc[n * RT + k][c];
-                            acc[n * RT + ie][c] = alpha * acc[n * RT + ie][c] + delta;
-                        }
-                        acc[n * RT][c] = base;
-                    }
-#pragma unroll
-                    for (int r = 0; r < RT; ++r) {
-                        const bool is_pt = Tile::has_group ? (r > Tile::n_aff + 1) : true;
-                        if (is_pt) {
-                            float x = acc[n * RT + r][c] + bias[c];
-                            if (L.act == ACT_RELU) x = fmaxf(x, 0.f);
-                            else if (L.act == ACT_ELU) x = elu_f(x);
-                            acc[n * RT + r][c] = x;
-                        }
-                    }
-                }
-            }
+            // one straight-line instance per activation kind: the 16 neurons of the thread are independent, and
+            // without a runtime branch inside the unrolled loops the scheduler interleaves their chains
+            if (L.act == ACT_RELU) epilogue<ACT_RELU>(acc, bias);
+            else if (L.act == ACT_ELU) epilogue<ACT_ELU>(acc, bias);
+            else epilogue<ACT_NONE>(acc, bias);
         }
         __syncwarp();            // every lane has finished READING this layer's input rows
         if (active) {
@@ -446,7 +522,7 @@ struct Engine {
         for (int r = 0; r < ROWS; ++r) { out[r] = 0.f; pscale[r] = 0.f; }
         const float* a_base = row_ptr(0, t, 0);
         for (int ch = L.chunk_begin; ch < L.chunk_end; ++ch) {
-            const float* w = acquire_chunk();
+            const float* w = acquire_chunk(ch);
             const ChunkDev& C = net.chunks[ch];
             for (int j = cg; j < C.kc; j += G::CG) {
                 const float wj = w[j];

@@ -351,7 +351,9 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
         }
         // ---- does anyone in the CTA still have work? (queue not exhausted or a live ray) ----
         const bool more = owner && (ray >= 0 || (long long)(*((volatile unsigned long long*)queue)) < n);
-        cta_live = __syncthreads_or(more ? 1 : 0) != 0;
+        // streamed weights: every warp takes part in the ring's CTA barriers, so the CTA leaves together;
+        // resident weights: no CTA barrier anywhere, each warp retires on its own
+        cta_live = eng.resident ? (__any_sync(0xffffffffu, more) != 0) : (__syncthreads_or(more ? 1 : 0) != 0);
     }
     eng.drain();
 }

@@ -49,8 +49,10 @@ def run(lib_path, width, n_boxes, reps=5, act="relu"):
 
 
 if __name__ == "__main__":
-    libs = sys.argv[1:] or [os.path.join(ROOT, "neural-implicit-queries_b200", "libniq.so")]
-    for width in (256, 64, 32):
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    widths = [int(a.split("=")[1]) for a in sys.argv[1:] if a.startswith("--width=")] or [256, 64, 32]
+    libs = args or [os.path.join(ROOT, "neural-implicit-queries_b200", "libniq.so")]
+    for width in widths:
         n = 148 * 16 * (64 if width == 256 else 512)
         for lib in libs:
             tf, ms, peak, chk = run(lib, width, n)
