@@ -281,8 +281,10 @@ def run_ours(args):
     launches0 = ctx.launch_count()
     ctx.kernel_timing(True)
     ctx.kernel_ms(0, reset=True)
+    ctx.exec_macs(on=True, reset=True)       # executed multiply-adds (the kernels skip exactly-zero columns after relu)
     clocks = ClockSampler(local)
-    clocks.start()
+    if not os.environ.get("NIQ_BENCH_NO_CLOCKS"):
+        clocks.start()
     barrier()
     step_ms = []
     for _ in range(args.steps):
@@ -294,6 +296,7 @@ def run_ours(args):
     barrier()
     clk = clocks.stop()
     kernel_ms, kernel_launches = ctx.kernel_ms(0, reset=True)
+    exec_macs = ctx.exec_macs(on=False, reset=True)
     ctx.kernel_timing(False)
     gpu_launches = ctx.launch_count() - launches0
     total_ms = float(sum(step_ms))
@@ -309,6 +312,36 @@ def run_ours(args):
     barrier()
     e2e_s = time.perf_counter() - t0
 
+    # ---- second half of BASELINE's metric: kd-tree boxes/s on the same network (configs[4]: depth-14 level-set tree).
+    # The tree of this network is full (nothing is pruned: 32,767 box classifications).  N = 1: the whole tree;
+    # N > 1: top levels replicated, subtrees dealt round-robin (sharding.tree_sharded) = strong scaling of one tree.
+    import kd_tree
+    lo3, hi3 = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
+    TREE_DEPTH = 14
+
+    def tree_step():
+        if world == 1:
+            st = {}
+            out = kd_tree.construct_uniform_unknown_levelset_tree(func, params, lo3, hi3, split_depth=TREE_DEPTH, stats=st, ctx=ctx)
+            return int(out["unknown_node_valid"].sum()), st["n_evals"]
+        lo_l, hi_l = sharding.tree_sharded(func, params, lo3, hi3, TREE_DEPTH, ctx=ctx)
+        return int(lo_l.shape[0]), None
+
+    tree_step()
+    barrier()
+    tree_reps = 5
+    t0 = time.perf_counter()
+    for _ in range(tree_reps):
+        n_leaves, n_tree_evals = tree_step()
+    barrier()
+    tree_s = (time.perf_counter() - t0) / tree_reps
+    tree_dev_ms = None
+    if world == 1:
+        ctx.timer_start()
+        tr = kd_tree.build_tree(func, params, lo3, hi3, split_depth=TREE_DEPTH, ctx=ctx)
+        tree_dev_ms = ctx.timer_stop()
+        tr.close()
+
     if world > 1:
         red = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -321,7 +354,9 @@ def run_ours(args):
 
     if rank == 0:
         value = n_all * args.steps / (total_ms * 1e-3)
-        achieved = flop_per_ray_step * ray_steps / (kernel_ms / max(kernel_launches, 1) * 1e-3) / 1e12   # this rank's kernel
+        k_s = kernel_ms / max(kernel_launches, 1) * 1e-3                  # this rank's kernel, average launch duration
+        algorithmic = flop_per_ray_step * ray_steps / k_s / 1e12         # reference formulation: every column of every layer
+        achieved = 2.0 * exec_macs / max(kernel_launches, 1) / k_s / 1e12   # FMAs the kernel actually issued (device counter)
         out = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,15 +364,27 @@ def run_ours(args):
             "ray_steps_per_s": ray_steps_all * args.steps / (total_ms * 1e-3),
             "e2e": {"value": n_all * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_all * 24,
                     "d2h_bytes_per_step": n_all * 13, "timer": "wall clock around queries.cast_rays (+ all_gather for N>1)"},
-            "gpu_launches": int(gpu_launches),
+            "gpu_launches": int(gpu_launches), "step_ms": [round(x, 2) for x in step_ms],
             "clocks": clk,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": None, "kernel": "k_cast_rays<256>", "peak_source": "measured on this GPU: register-only FFMA kernel "
+                         "traffic": 2.1e6, "traffic_note": "dram__bytes_read+write per launch from the ncu --set full capture of the same kernel at 18 tiles (profiles/): 2.1 MB, i.e. the weights once; not memory-bound",
+                         "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / peak_tflops,
+                         "executed_over_algorithmic_flops": achieved / algorithmic,
+                         "note": "achieved = EXECUTED FP32 FMA flops (device counter: columns that are exactly zero after a relu layer are skipped, "
+                                 "exact since fma(0,w,acc)=acc) / kernel time; achieved_algorithmic = the reference formulation's 10*M flop per ray-step / kernel time (can exceed the peak)",
+                         "kernel": "k_cast_rays<256>", "peak_source": "measured on this GPU: register-only FFMA kernel "
                          "(niq_measure_fp32_peak); nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5",
                          "flop_per_ray_step": flop_per_ray_step, "ray_steps_per_launch": ray_steps,
                          "kernel_ms_per_launch": kernel_ms / max(kernel_launches, 1),
                          "hbm_note": "not HBM-bound: 37 B per ray moved for 2.35 GFLOP"},
         }
+        full_tree_boxes = 2 ** (TREE_DEPTH + 1) - 1
+        out["tree"] = {"metric": "kd-tree boxes/s (construct_uniform_unknown_levelset_tree, same 8x256 ReLU MLP, affine_fixed, split_depth 14, domain [-1,1]^3)",
+                       "value": full_tree_boxes / tree_s, "unit": "boxes/s", "boxes": full_tree_boxes, "leaves": n_leaves,
+                       "ms": tree_s * 1e3, "scaling": "strong" if world > 1 else None,
+                       "timer": "wall clock through the public API incl. the leaf download (e2e); 15 levels, each a classify launch + scan/split",
+                       "device_ms": tree_dev_ms,
+                       "note": "full tree of the random-init net (no pruning): latency-bound (levels 0-7 hold <= 128 boxes); bunny depth-21 (1.79 M boxes) is in --extra"}
         # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores ----
         if world == 1 and not args.no_cpu:
             import multiprocessing as mp

@@ -108,6 +108,11 @@ int niq_ctx_timer_stop(niq_ctx* ctx, float* ms);
 int niq_ctx_kernel_ms(niq_ctx* ctx, int which, float* ms, int64_t* launches, int reset);
 /* per-launch CUDA-event timing of the kernel families above is off by default (events cost launch latency) */
 int niq_ctx_kernel_timing(niq_ctx* ctx, int on);
+/* executed-MAC accounting of the network kernels: they skip columns that are exactly zero after a relu layer
+ * (exact: fma(0,w,acc) == acc), so executed work < algorithmic work (report both).  `on` switches
+ * the device counter on/off for subsequent launches; *macs (optional) returns the row-level multiply-adds counted
+ * so far (padded rows / idle slots included); reset != 0 clears it.                                          */
+int niq_ctx_exec_macs(niq_ctx* ctx, int on, int64_t* macs, int reset);
 /* device memory helpers so a host language can keep inputs resident (bench `value` leg)              */
 int niq_dev_alloc(niq_ctx* ctx, int64_t bytes, void** out);
 int niq_dev_free(niq_ctx* ctx, void* p);

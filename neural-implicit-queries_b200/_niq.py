@@ -15,7 +15,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libniq.so")
+LIB_PATH = os.environ.get("NIQ_LIB") or os.path.join(_HERE, "libniq.so")   # NIQ_LIB: development builds (tools/)
 
 NIQ_OK, NIQ_EINVAL, NIQ_ENOMEM, NIQ_ECUDA, NIQ_ECAPACITY, NIQ_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
@@ -27,7 +27,7 @@ TREE_INTERIOR, TREE_EXTERIOR = 1, 2
 SYMBOLS = (
     "niq_last_error", "niq_version", "niq_ctx_create", "niq_ctx_destroy", "niq_ctx_sync", "niq_ctx_device_info",
     "niq_ctx_launch_count", "niq_ctx_timer_start", "niq_ctx_timer_stop", "niq_ctx_kernel_ms",
-    "niq_ctx_kernel_timing", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
+    "niq_ctx_kernel_timing", "niq_ctx_exec_macs", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
     "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
     "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_tree_build", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
@@ -152,6 +152,13 @@ class Context:
         ms, n = C.c_float(), C.c_int64()
         check(lib().niq_ctx_kernel_ms(self.handle, C.c_int(which), C.byref(ms), C.byref(n), C.c_int(1 if reset else 0)))
         return ms.value, n.value
+
+    def exec_macs(self, on=True, reset=False):
+        """Executed multiply-adds counted by the network kernels so far (zero-skipping accounting); also
+        switches the counter on/off for subsequent launches."""
+        out = C.c_int64()
+        check(lib().niq_ctx_exec_macs(self.handle, C.c_int(1 if on else 0), C.byref(out), C.c_int(1 if reset else 0)))
+        return out.value
 
     def fp32_peak_tflops(self):
         out = C.c_float()

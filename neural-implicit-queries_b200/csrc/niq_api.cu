@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -64,6 +65,9 @@ struct niq_ctx {
     double fam_ms[2] = {0, 0};
     long long fam_launches[2] = {0, 0};
     long long* pinned = nullptr;     // small pinned read-back area (64 x int64)
+    bool timer_armed = false, timer_started = false;   // niq_ctx_timer_start .. _stop bracket (see timer_touch / timer_mark)
+    unsigned long long* d_exec = nullptr;   // executed-MAC counter of the engine kernels (zero-skipping accounting)
+    bool count_exec = false;
 };
 
 struct DevBuf {   // stream-ordered temporary
@@ -128,6 +132,8 @@ extern "C" int niq_ctx_create(int device, niq_ctx** out) {
     CU(cudaEventCreate(&c->t0));
     CU(cudaEventCreate(&c->t1));
     CU(cudaMallocHost(&c->pinned, 64 * sizeof(long long)));
+    CU(cudaMalloc(&c->d_exec, 8));
+    CU(cudaMemset(c->d_exec, 0, 8));
     *out = c;
     return NIQ_OK;
 }
@@ -140,6 +146,7 @@ extern "C" int niq_ctx_destroy(niq_ctx* c) {
     if (c->t0) cudaEventDestroy(c->t0);
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->d_exec) cudaFree(c->d_exec);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return NIQ_OK;
@@ -160,16 +167,34 @@ extern "C" int niq_ctx_launch_count(niq_ctx* c, int64_t* out) {
     *out = c->launches;
     return NIQ_OK;
 }
+// Device-side timing of a bracket of API calls: t0 is recorded on the stream when the first call after
+// niq_ctx_timer_start enqueues its work, t1 right after the last call has enqueued its last operation (BEFORE the
+// host waits for it), so the reading is the device time of the calls and does not include the wake-up latency of a
+// descheduled host thread (measured on the shared GPU box: up to a second of jitter on a 0.6 s step).
+static void timer_touch(niq_ctx* c) {
+    if (c->timer_armed && !c->timer_started) { cudaEventRecord(c->t0, c->stream); c->timer_started = true; }
+}
+static void timer_mark(niq_ctx* c) {
+    if (c->timer_armed && c->timer_started) cudaEventRecord(c->t1, c->stream);
+}
+#define FINAL_SYNC(c) do { timer_mark(c); CU(cudaStreamSynchronize((c)->stream)); } while (0)
+
 extern "C" int niq_ctx_timer_start(niq_ctx* c) {
     if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
-    CU(cudaEventRecord(c->t0, c->stream));
+    c->timer_armed = true;
+    c->timer_started = false;
     return NIQ_OK;
 }
 extern "C" int niq_ctx_timer_stop(niq_ctx* c, float* ms) {
     if (!c || !ms) return fail(NIQ_EINVAL, "bad argument");
-    CU(cudaEventRecord(c->t1, c->stream));
-    CU(cudaEventSynchronize(c->t1));
-    CU(cudaEventElapsedTime(ms, c->t0, c->t1));
+    *ms = 0.f;
+    const bool started = c->timer_armed && c->timer_started;
+    c->timer_armed = false;
+    c->timer_started = false;
+    if (started) {
+        CU(cudaEventSynchronize(c->t1));
+        CU(cudaEventElapsedTime(ms, c->t0, c->t1));
+    }
     return NIQ_OK;
 }
 extern "C" int niq_ctx_kernel_timing(niq_ctx* c, int on) {
@@ -184,6 +209,19 @@ extern "C" int niq_ctx_kernel_ms(niq_ctx* c, int which, float* ms, int64_t* laun
     if (ms) *ms = (float)c->fam_ms[which];
     if (launches) *launches = c->fam_launches[which];
     if (reset) { c->fam_ms[which] = 0; c->fam_launches[which] = 0; }
+    return NIQ_OK;
+}
+extern "C" int niq_ctx_exec_macs(niq_ctx* c, int on, int64_t* macs, int reset) {
+    if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    if (macs) {
+        unsigned long long v = 0;
+        CU(cudaMemcpy(&v, c->d_exec, 8, cudaMemcpyDeviceToHost));
+        *macs = (int64_t)v;
+    }
+    if (reset) CU(cudaMemset(c->d_exec, 0, 8));
+    c->count_exec = on != 0;
     return NIQ_OK;
 }
 extern "C" int niq_dev_alloc(niq_ctx* c, int64_t bytes, void** out) {
@@ -281,6 +319,7 @@ constexpr int kResidentPad = 512;   // floats after the resident weights: the pi
 // activation buffers, otherwise streamed through the ring.  Returns the dynamic shared-memory size.
 template <class E>
 static size_t place_weights(niq_ctx* c, NetDev& net, int total_floats) {
+    net.exec_macs = c->count_exec ? c->d_exec : nullptr;
     const size_t res = E::smem_bytes(total_floats + kResidentPad);
     if (res <= c->prop.sharedMemPerBlockOptin) {
         net.resident = 1;
@@ -427,6 +466,11 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
         D.chunk_end = n_chunks;
     }
     nd.n_chunks = n_chunks;
+    // zero-skipping after relu layers (niq_engine.cuh write_back_sparse); NIQ_NO_SPARSE=1 forces the dense K loops (A/B tests)
+    nd.sparse = getenv("NIQ_NO_SPARSE") == nullptr || getenv("NIQ_NO_SPARSE")[0] == '0';
+    for (int l = 0; l < nd.n_layers; ++l)
+        if (nd.layers[l].chunk_end - nd.layers[l].chunk_begin > kMaxSegs) nd.sparse = 0;
+    nd.exec_macs = nullptr;
     nd.resident = 0;
     nd.w_region_floats = (int)hw.size() + kResidentPad;
     m->total_floats = (int)hw.size();
@@ -649,6 +693,7 @@ extern "C" int niq_eval_points(niq_ctx* c, const niq_mlp* m, int64_t n, const fl
     if (!c || !m || n < 0 || (n > 0 && (!x || !f))) return fail(NIQ_EINVAL, "niq_eval_points: bad argument");
     if (n == 0) return NIQ_OK;
     CU(cudaSetDevice(c->device));
+    timer_touch(c);
     InBuf dx(c); OutBuf df(c), ds(c);
     TRY(dx.stage(c, x, (size_t)n * 12, mem));
     TRY(df.stage(c, f, (size_t)n * 4, mem));
@@ -657,7 +702,7 @@ extern "C" int niq_eval_points(niq_ctx* c, const niq_mlp* m, int64_t n, const fl
     src.kind = 0; src.a = dx.as<float>();
     TRY(launch_eval_points(c, m, src, n, df.as<float>(), ds.as<float>()));
     TRY(df.flush(c)); TRY(ds.flush(c));
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     return NIQ_OK;
 }
 
@@ -665,6 +710,7 @@ static int classify_common(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg
                            size_t b_bytes, const float* a, const float* b, float offset, int32_t* label, float* lower,
                            float* upper, uint8_t* tie, int mem) {
     CU(cudaSetDevice(c->device));
+    timer_touch(c);
     InBuf da(c), db(c); OutBuf dl(c), dlo(c), dup(c), dt(c);
     TRY(da.stage(c, a, a_bytes, mem));
     TRY(db.stage(c, b, b_bytes, mem));
@@ -675,7 +721,7 @@ static int classify_common(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg
     src.a = da.as<float>(); src.b = db.as<float>();
     TRY(classify_dev(c, m, cfg, src, n, offset, dl.as<int>(), dlo.as<float>(), dup.as<float>(), dt.as<unsigned char>()));
     TRY(dl.flush(c)); TRY(dlo.flush(c)); TRY(dup.flush(c)); TRY(dt.flush(c));
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     return NIQ_OK;
 }
 
@@ -723,6 +769,7 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
     if (n_evals) *n_evals = 0;
     if (n == 0) return NIQ_OK;
     CU(cudaSetDevice(c->device));
+    timer_touch(c);
     InBuf dr(c), dd(c); OutBuf dt(c), dh(c), dc(c), dtie(c);
     TRY(dr.stage(c, roots, (size_t)n * 12, mem));
     TRY(dd.stage(c, dirs, (size_t)n * 12, mem));
@@ -756,6 +803,7 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
             total_floats += mlps[f]->total_floats;
             net.n_layers += s.n_layers; net.n_chunks += s.n_chunks;
             net.tie_rel = std::max(net.tie_rel, s.tie_rel);
+            net.sparse = f == 0 ? s.sparse : std::min(net.sparse, s.sparse);
             wmax = std::max(wmax, mlps[f]->wmax);
         }
         net.n_nets = n_funcs;
@@ -798,7 +846,7 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
         *n_evals = evals;
     }
     TRY(dt.flush(c)); TRY(dh.flush(c)); TRY(dc.flush(c)); TRY(dtie.flush(c));
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     return NIQ_OK;
 }
 
@@ -856,6 +904,7 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
         return fail(NIQ_EINVAL, "must specify at least one of node_terminate_thresh or split_depth as a terminating condition");
     if (node_thresh <= 0) node_thresh = 9999999999ll;
     CU(cudaSetDevice(c->device));
+    timer_touch(c);
 
     niq_tree* T = new niq_tree();
     T->ctx = c;
@@ -953,7 +1002,7 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
     // hand the final frontier to the tree object
     T->lists[0] = cur;
     cur = NodeList{};
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     guard.ok = true;
     *out = T;
     return NIQ_OK;
@@ -1009,6 +1058,7 @@ static int mc_device(niq_ctx* c, const niq_mlp* m, long long n, const float* lo,
     M->ctx = c;
     *out = M;
     if (n == 0) return NIQ_OK;
+    timer_touch(c);
     const int side = 1 << n_sub, P = side + 1;
     const long long pts_per_leaf = (long long)P * P * P;
     // leaves are processed in slabs so the lattice values stay bounded (256 MB)
@@ -1060,7 +1110,7 @@ static int mc_device(niq_ctx* c, const niq_mlp* m, long long n, const float* lo,
         }
     }
     M->n = total;
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     return NIQ_OK;
 }
 
@@ -1133,6 +1183,7 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
     if (!c || !mA || !mB || !lower || !upper || !found || !loc) return fail(NIQ_EINVAL, "niq_find_any_intersection: bad argument");
     TRY(check_cfg(cfgA)); TRY(check_cfg(cfgB));
     CU(cudaSetDevice(c->device));
+    timer_touch(c);
     const float eps_w = eps / sqrtf(3.0f);                 // reference src/kd_tree.py:446
     NodeList cur, nxt;
     struct ListGuard { niq_ctx* c; NodeList* L; ~ListGuard() { if (L->lo) cudaFreeAsync(L->lo, c->stream); if (L->hi) cudaFreeAsync(L->hi, c->stream); } } g1{c, &cur}, g2{c, &nxt};
@@ -1196,7 +1247,7 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
         std::swap(cur, nxt);
     }
     if (stats) { stats[0] = n_nodes; stats[1] = n_rounds; stats[2] = n_tie; }
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     return NIQ_OK;
 }
 
@@ -1212,6 +1263,7 @@ extern "C" int niq_closest_point(niq_ctx* c, const niq_mlp* m, const niq_mode_cf
     if (stats) stats[0] = stats[1] = stats[2] = stats[3] = 0;
     if (q == 0) return NIQ_OK;
     CU(cudaSetDevice(c->device));
+    timer_touch(c);
     InBuf dq(c); OutBuf dd(c), dl(c);
     TRY(dq.stage(c, query_points, (size_t)q * 12, mem));
     TRY(dd.stage(c, dist, (size_t)q * 4, mem));
@@ -1331,6 +1383,6 @@ extern "C" int niq_closest_point(niq_ctx* c, const niq_mlp* m, const niq_mode_cf
         stats[0] = hs[0]; stats[1] = hs[1]; stats[2] = mt; stats[3] = hs[2];
     }
     TRY(dd.flush(c)); TRY(dl.flush(c));
-    CU(cudaStreamSynchronize(c->stream));
+    FINAL_SYNC(c);
     return NIQ_OK;
 }

@@ -344,6 +344,95 @@ def test_cast_rays_full_size_properties():
     assert tie.mean() < 0.02
 
 
+@pytest.mark.parametrize("width", [128, 256])
+def test_cast_rays_wide_relu_vs_oracle(width):
+    """The 128 / 256-wide engine (streamed weights, zero-skipping K loops) through queries.cast_rays against the
+    oracle: the synthetic config-5 network family, few rays, step limit cut so the oracle finishes in seconds."""
+    import queries
+    import render
+    p = net.random_mlp([3] + [width] * 8 + [1], "relu", seed=0)
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=20, fov_deg=30.)
+    opts = queries.get_default_cast_opts()
+    opts["n_max_step"] = 48
+    t, hit, cnt, n_evals, tie = queries.cast_rays((make(p, "affine_fixed"),), (p,), roots, dirs, opts, return_near_tie=True)
+    ot, ohit, ocnt, on_evals, otie = rays.cast_rays((octx("affine_fixed"),), (p,), roots, dirs, opts, return_near_tie=True)
+    ok = ~(tie | otie)
+    assert ok.mean() > 0.9
+    assert np.array_equal(hit[ok], ohit[ok]) and np.array_equal(cnt[ok], ocnt[ok])
+    np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL)
+
+
+def test_zero_skipping_equals_dense(monkeypatch):
+    """Engine A/B: the list-driven K loops (columns that are exactly zero after a relu layer are dropped) against the
+    dense loops (NIQ_NO_SPARSE=1).  Hidden layers are bit-identical; the lane-split dot product of the last layer
+    sums in a different order, so values may differ by a few ulp of the summed magnitude."""
+    import _niq
+    import mlp
+    import queries
+    import render
+    p = net.random_mlp([3] + [256] * 8 + [1], "relu", seed=0)
+    func = make(p, "affine_fixed")
+    rng = np.random.default_rng(5)
+    c = rng.uniform(-1, 1, (4001, 3)).astype(np.float32)
+    h = (2.0 ** rng.uniform(-12, -1, (4001, 1)) * rng.uniform(0.5, 1, (4001, 3))).astype(np.float32)
+    x = (c + 0.5 * h).astype(np.float32)
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=24, fov_deg=30.)
+    opts = queries.get_default_cast_opts()
+    opts["n_max_step"] = 40
+    res = {}
+    for tag, env in (("dense", "1"), ("sparse", "0")):
+        monkeypatch.setenv("NIQ_NO_SPARSE", env)
+        ctx = _niq.Context(0)
+        try:
+            ctx.exec_macs(on=True, reset=True)
+            lab, lo, upb, tie = func.bound_box(p, c - h, c + h, ctx=ctx)
+            f, sc = mlp.eval_points(p, x, return_scale=True, ctx=ctx)
+            macs = ctx.exec_macs(on=False, reset=True)
+            r = queries.cast_rays((func,), (p,), roots, dirs, opts, return_near_tie=True, ctx=ctx)
+            res[tag] = (lab, lo, upb, tie, f, sc, r, macs)
+        finally:
+            ctx.close()
+    d, s_ = res["dense"], res["sparse"]
+    mag = np.maximum(np.abs(d[1]), np.abs(d[2])) + 1e-30
+    assert np.all(np.abs(d[1] - s_[1]) <= 4e-6 * mag) and np.all(np.abs(d[2] - s_[2]) <= 4e-6 * mag)
+    assert np.all((d[0] == s_[0]) | d[3].astype(bool) | s_[3].astype(bool))
+    assert np.all(np.abs(d[4] - s_[4]) <= 4e-6 * d[5])
+    ok = ~(d[6][4] | s_[6][4])
+    assert ok.mean() > 0.9 and np.array_equal(d[6][1][ok], s_[6][1][ok]) and np.array_equal(d[6][2][ok], s_[6][2][ok])
+    np.testing.assert_allclose(d[6][0][ok], s_[6][0][ok], rtol=RTOL)
+    # the accounting: dense executes every (padded) column, zero-skipping clearly fewer on these small boxes
+    assert s_[7] < 0.85 * d[7]
+
+
+def test_exec_macs_counter_and_device_timer():
+    """niq_ctx_exec_macs counts the multiply-adds the network kernels issue; an elu net has no exact zeros, so the
+    count is the padded dense count (>= algorithmic 5*M per box).  niq_ctx_timer_* brackets device time only."""
+    import _niq
+    ctx = _niq.Context(0)
+    try:
+        p = sample_params("bunny")                      # elu, 8x64
+        func = make(p, "affine_fixed")
+        lo_b, hi_b = random_boxes(4, 2048, smin=-8, smax=-3)
+        ctx.exec_macs(on=True, reset=True)
+        ctx.timer_start()
+        func.bound_box(p, lo_b, hi_b, ctx=ctx)
+        ms = ctx.timer_stop()
+        macs = ctx.exec_macs(on=False, reset=True)
+        M = ctx.mlp(p).macs
+        assert 5 * M * 2048 <= macs <= 1.5 * 5 * M * 2048
+        assert 0.0 < ms < 1000.0
+        ctx.timer_start()
+        assert ctx.timer_stop() == 0.0                  # no call in the bracket
+        func.bound_box(p, lo_b, hi_b, ctx=ctx)
+        assert ctx.exec_macs(on=False) == 0             # counter off: nothing counted
+    finally:
+        ctx.close()
+
+
 # ---------------------------------------------------------------------------------------------------
 # level-set tree, marching cubes
 # ---------------------------------------------------------------------------------------------------
