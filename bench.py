@@ -252,7 +252,9 @@ def run_ours(args):
     h_d = torch.zeros(n, dtype=torch.int32, device=dev)
     c_d = torch.zeros(n, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, n, 3), dtype=torch.int32, device=dev) if world > 1 else None
+    cap = tiles_per_rank * TILE * TILE            # shards differ in size (partial border tiles): the gather is padded to cap
+    gathered = torch.empty((world, cap, 3), dtype=torch.int32, device=dev) if world > 1 else None
+    pack_h = torch.zeros((cap, 3), dtype=torch.int32).pin_memory() if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,8 +269,8 @@ def run_ours(args):
     def e2e_step():
         out = queries.cast_rays((func,), (params,), r_h.numpy(), d_h.numpy(), opts, ctx=ctx)
         if world > 1:        # the one collective of the path: gather (t, hit, count) = 12 B/ray over NVLink
-            pack = torch.from_numpy(np.stack((out[0].view(np.int32), out[1], out[2]), axis=1)).to(dev)
-            dist.all_gather_into_tensor(gathered.view(-1, 3), pack)
+            pack_h[:n] = torch.from_numpy(np.stack((out[0].view(np.int32), out[1], out[2]), axis=1))
+            dist.all_gather_into_tensor(gathered.view(-1, 3), pack_h.to(dev, non_blocking=True))
             torch.cuda.synchronize()
         return out
 
@@ -446,6 +448,9 @@ def extra_metrics(ctx):
 
 
 def main():
+    if os.environ.get("NIQ_BENCH_WATCHDOG"):          # development: dump every thread's Python stack if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["NIQ_BENCH_WATCHDOG"]), exit=True)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -169,6 +169,12 @@ enum { NIQ_TREE_INTERIOR = 1, NIQ_TREE_EXTERIOR = 2 };  /* flags: also collect N
 int niq_tree_build(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, const float lower[3],
                    const float upper[3], int32_t split_depth, int64_t node_terminate_thresh, float offset,
                    int32_t flags, int32_t batch_process_size, niq_tree** out);
+/* The same tree grown from n_roots root boxes lower/upper (n_roots,3) at once (ours: the unit of the multi-GPU
+ * partition -- a rank refines all frontier boxes it was dealt in ONE level-synchronous build; n_roots = 1 is
+ * niq_tree_build).                                                                                     */
+int niq_tree_build_roots(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, int64_t n_roots, const float* lower,
+                         const float* upper, int32_t split_depth, int64_t node_terminate_thresh, float offset,
+                         int32_t flags, int32_t batch_process_size, niq_tree** out);
 /* which: 0 unknown leaves, 1 interior (NEGATIVE) nodes, 2 exterior (POSITIVE) nodes                    */
 int niq_tree_count(const niq_tree* tree, int which, int64_t* n);
 int niq_tree_copy(const niq_tree* tree, int which, float* lower, float* upper, int64_t capacity, int mem);

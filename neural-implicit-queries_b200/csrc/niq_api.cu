@@ -129,6 +129,13 @@ extern "C" int niq_ctx_create(int device, niq_ctx** out) {
     if (c->prop.major < 9)
         return fail(NIQ_ECUDA, "device compute capability %d.%d: kernels are built for sm_100a only", c->prop.major, c->prop.minor);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    {   // stream-ordered temporaries (DevBuf) stay in the pool across synchronisations instead of going back to the OS
+        cudaMemPool_t pool = nullptr;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     CU(cudaEventCreate(&c->t0));
     CU(cudaEventCreate(&c->t1));
     CU(cudaMallocHost(&c->pinned, 64 * sizeof(long long)));
@@ -890,9 +897,10 @@ extern "C" int niq_tree_destroy(niq_tree* t) {
     return NIQ_OK;
 }
 
-extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, const float lower[3], const float upper[3],
-                              int32_t split_depth, int64_t node_thresh, float offset, int32_t flags, int32_t bps, niq_tree** out) {
-    if (!c || !m || !lower || !upper || !out) return fail(NIQ_EINVAL, "niq_tree_build: bad argument");
+extern "C" int niq_tree_build_roots(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, int64_t n_roots, const float* lower,
+                                    const float* upper, int32_t split_depth, int64_t node_thresh, float offset, int32_t flags,
+                                    int32_t bps, niq_tree** out) {
+    if (!c || !m || !lower || !upper || !out || n_roots < 1) return fail(NIQ_EINVAL, "niq_tree_build: bad argument");
     TRY(check_cfg(cfg));
     if (bps <= 0) return fail(NIQ_EINVAL, "batch_process_size must be positive");
     for (int p = 7; p < 31; ++p) {        // reference src/kd_tree.py:105-109
@@ -912,11 +920,15 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
 
     NodeList cur, nxt;
     struct ListGuard { niq_ctx* c; NodeList* L; ~ListGuard() { if (L->lo) cudaFreeAsync(L->lo, c->stream); if (L->hi) cudaFreeAsync(L->hi, c->stream); } } g1{c, &cur}, g2{c, &nxt};
-    TRY(list_reserve(c, cur, 1));
-    CU(cudaMemcpyAsync(cur.lo, lower, 12, cudaMemcpyHostToDevice, c->stream));
-    CU(cudaMemcpyAsync(cur.hi, upper, 12, cudaMemcpyHostToDevice, c->stream));
-    cur.n = 1;
+    TRY(list_reserve(c, cur, n_roots));
+    CU(cudaMemcpyAsync(cur.lo, lower, (size_t)n_roots * 12, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(cur.hi, upper, (size_t)n_roots * 12, cudaMemcpyHostToDevice, c->stream));
+    cur.n = n_roots;
     long long bucket = 1;                                       // padded array size the reference would hold
+    if (n_roots > 1) TRY(next_bucket(n_roots, &bucket));
+    DevBuf d_tie(c);
+    TRY(d_tie.alloc(8));
+    CU(cudaMemsetAsync(d_tie.p, 0, 8, c->stream));
     const long long n_splits = split_depth < 0 ? 99999999ll : (long long)split_depth + 1;
 
     for (long long i_split = 0; i_split < n_splits; ++i_split) {
@@ -941,7 +953,8 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
             {
                 LaunchTimer lt(c, 1);
                 k_tree_flags<<<g, 256, 0, c->stream>>>(label.as<int>(), N, f_unk.as<int>(), want_neg ? f_neg.as<int>() : nullptr,
-                                                      want_pos ? f_pos.as<int>() : nullptr);
+                                                      want_pos ? f_pos.as<int>() : nullptr, tie.as<unsigned char>(),
+                                                      d_tie.as<unsigned long long>());
                 CU(cudaGetLastError());
             }
             TRY(scan_exclusive(c, f_unk.as<int>(), N, s_unk.as<int>()));
@@ -958,14 +971,6 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
             if (want_pos) tot[2] = reinterpret_cast<int*>(c->pinned)[2];
             counts[0] = tot[0]; counts[1] = tot[1]; counts[2] = tot[2];
             T->levels.insert(T->levels.end(), {N, counts[0], counts[1], counts[2]});
-            {   // near-tie boxes of this level (diagnostic counter)
-                std::vector<unsigned char> ht((size_t)N);
-                CU(cudaMemcpyAsync(ht.data(), tie.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
-                CU(cudaStreamSynchronize(c->stream));
-                long long nt = 0;
-                for (unsigned char b : ht) nt += b;
-                T->stats[1] += nt;
-            }
             if (want_neg && counts[1] > 0) {
                 NodeList& L = T->lists[1];
                 TRY(list_reserve(c, L, L.n + counts[1]));
@@ -989,8 +994,7 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
                 k_tree_scatter<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, N, f_unk.as<int>(), s_unk.as<int>(), this_b, quit_next ? 0 : 1, nxt.lo, nxt.hi);
                 CU(cudaGetLastError());
             }
-            nxt.n = n_out;
-            CU(cudaStreamSynchronize(c->stream));   // temporaries of this level are released after their last use
+            nxt.n = n_out;                          // temporaries are stream-ordered (DevBuf): no host sync needed here
         } else {
             T->levels.insert(T->levels.end(), {0, 0, 0, 0});
             nxt.n = 0;
@@ -1002,12 +1006,21 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
     // hand the final frontier to the tree object
     T->lists[0] = cur;
     cur = NodeList{};
+    {   // near-tie boxes over all levels (device counter fed by k_tree_flags)
+        unsigned long long nt = 0;
+        TRY(read_back(c, d_tie.p, 8, &nt));
+        T->stats[1] = (long long)nt;
+    }
     FINAL_SYNC(c);
     guard.ok = true;
     *out = T;
     return NIQ_OK;
 }
 
+extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, const float lower[3], const float upper[3],
+                              int32_t split_depth, int64_t node_thresh, float offset, int32_t flags, int32_t bps, niq_tree** out) {
+    return niq_tree_build_roots(c, m, cfg, 1, lower, upper, split_depth, node_thresh, offset, flags, bps, out);
+}
 extern "C" int niq_tree_count(const niq_tree* t, int which, int64_t* n) {
     if (!t || !n || which < 0 || which > 2) return fail(NIQ_EINVAL, "bad argument");
     *n = t->lists[which].n;

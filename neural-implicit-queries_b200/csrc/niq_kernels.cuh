@@ -440,13 +440,19 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_apply(const int* __restri
 
 // flags from labels for one tree level: which[0]=unknown, [1]=negative (interior), [2]=positive (exterior)
 __global__ void k_tree_flags(const int* __restrict__ label, long long n, int* __restrict__ f_unk,
-                             int* __restrict__ f_neg, int* __restrict__ f_pos) {
+                             int* __restrict__ f_neg, int* __restrict__ f_pos, const unsigned char* __restrict__ tie,
+                             unsigned long long* __restrict__ n_tie) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int lab = label[i];
-    f_unk[i] = lab == SIGN_UNKNOWN;
-    if (f_neg) f_neg[i] = lab == SIGN_NEGATIVE;
-    if (f_pos) f_pos[i] = lab == SIGN_POSITIVE;
+    bool is_tie = false;
+    if (i < n) {
+        const int lab = label[i];
+        f_unk[i] = lab == SIGN_UNKNOWN;
+        if (f_neg) f_neg[i] = lab == SIGN_NEGATIVE;
+        if (f_pos) f_pos[i] = lab == SIGN_POSITIVE;
+        is_tie = tie != nullptr && tie[i] != 0;
+    }
+    const unsigned b = __ballot_sync(0xffffffffu, is_tie);      // near-tie boxes of the level (diagnostic counter)
+    if (b != 0u && (threadIdx.x & 31) == 0 && n_tie) atomicAdd(n_tie, (unsigned long long)__popc(b));
 }
 
 __device__ __forceinline__ int argmax3_first(float a, float b, float c) {

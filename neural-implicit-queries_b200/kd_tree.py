@@ -69,15 +69,22 @@ class _Tree:
 
 def build_tree(func, params, lower, upper, node_terminate_thresh=None, split_depth=None, with_interior_nodes=False,
                with_exterior_nodes=False, offset=0., batch_process_size=2048, ctx=None):
-    """The device-resident tree (ours): what construct_uniform_unknown_levelset_tree wraps."""
+    """The device-resident tree (ours): what construct_uniform_unknown_levelset_tree wraps.  lower / upper may be
+    (3,) -- the reference's single root box -- or (n,3): n root boxes refined in one level-synchronous build (the unit
+    of the multi-GPU subtree partition, sharding.tree_sharded)."""
     ctx = ctx or _niq.default_context()
-    lower, upper = _vec3(lower, "lower"), _vec3(upper, "upper")
+    lower = np.ascontiguousarray(lower, np.float32)
+    upper = np.ascontiguousarray(upper, np.float32)
+    if lower.ndim == 1:
+        lower, upper = _vec3(lower, "lower")[None], _vec3(upper, "upper")[None]
+    if lower.ndim != 2 or lower.shape[1] != 3 or lower.shape != upper.shape or lower.shape[0] < 1:
+        raise ValueError("lower / upper must have shape (3,) or (n,3)")
     flags = (_niq.TREE_INTERIOR if with_interior_nodes else 0) | (_niq.TREE_EXTERIOR if with_exterior_nodes else 0)
     cfg = _niq.mode_cfg(func.ctx)
     m = ctx.mlp(params)
     h = C.c_void_p()
-    _niq.check(_niq.lib().niq_tree_build(
-        ctx.handle, m.handle, C.byref(cfg), _niq.ptr(lower), _niq.ptr(upper),
+    _niq.check(_niq.lib().niq_tree_build_roots(
+        ctx.handle, m.handle, C.byref(cfg), C.c_int64(lower.shape[0]), _niq.ptr(lower), _niq.ptr(upper),
         C.c_int32(-1 if split_depth is None else int(split_depth)),
         C.c_int64(0 if node_terminate_thresh is None else int(node_terminate_thresh)), C.c_float(offset),
         C.c_int32(flags), C.c_int32(int(batch_process_size)), C.byref(h)))
@@ -104,8 +111,8 @@ def construct_uniform_unknown_levelset_tree(func, params, lower, upper, node_ter
             raise ValueError(f"batch_process_size must be a factor of our bucket sizes, is not a factor of {b} (try a power of 2)")
     if node_terminate_thresh is None and split_depth is None:
         raise ValueError("must specify at least one of node_terminate_thresh or split_depth as a terminating condition")
-    tree = build_tree(func, params, lower, upper, node_terminate_thresh, split_depth, with_interior_nodes,
-                      with_exterior_nodes, offset, batch_process_size, ctx)
+    tree = build_tree(func, params, _vec3(lower, "lower"), _vec3(upper, "upper"), node_terminate_thresh, split_depth,
+                      with_interior_nodes, with_exterior_nodes, offset, batch_process_size, ctx)
     try:
         lo, hi = tree.nodes(0)
         valid, plo, phi = _padded(lo, hi, get_next_bucket_size(lo.shape[0]))

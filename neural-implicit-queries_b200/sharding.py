@@ -84,6 +84,7 @@ def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_
     Leaf ORDER differs from the single-device call (canonicalise before comparing).  -> (lower, upper) (L,3)."""
     import torch
     import torch.distributed as dist
+    injected = build_fn is not None
     if build_fn is None:
         import kd_tree
         build_fn = kd_tree.construct_uniform_unknown_levelset_tree
@@ -95,13 +96,23 @@ def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_
     v = top['unknown_node_valid']
     flo, fhi = top['unknown_node_lower'][v], top['unknown_node_upper'][v]
     mine = deal_boxes(flo.shape[0], rank, world)
-    los, his = [], []
-    for i in mine:
-        sub = build_fn(func, params, flo[i], fhi[i], split_depth=split_depth - top_depth, **kw)
-        sv = sub['unknown_node_valid']
-        los.append(sub['unknown_node_lower'][sv]); his.append(sub['unknown_node_upper'][sv])
-    lo = np.concatenate(los) if los else np.zeros((0, 3), np.float32)
-    hi = np.concatenate(his) if his else np.zeros((0, 3), np.float32)
+    if injected or len(mine) == 0:
+        los, his = [], []
+        for i in mine:
+            sub = build_fn(func, params, flo[i], fhi[i], split_depth=split_depth - top_depth, **kw)
+            sv = sub['unknown_node_valid']
+            los.append(sub['unknown_node_lower'][sv]); his.append(sub['unknown_node_upper'][sv])
+        lo = np.concatenate(los) if los else np.zeros((0, 3), np.float32)
+        hi = np.concatenate(his) if his else np.zeros((0, 3), np.float32)
+    else:
+        # all of this rank's frontier boxes are refined in ONE level-synchronous build (niq_tree_build_roots)
+        import kd_tree
+        tkw = {k: v for k, v in kw.items() if k in ("offset", "batch_process_size", "ctx")}
+        tree = kd_tree.build_tree(func, params, flo[mine], fhi[mine], split_depth=split_depth - top_depth, **tkw)
+        try:
+            lo, hi = tree.nodes(0)
+        finally:
+            tree.close()
     if world == 1:
         return lo, hi
     backend = dist.get_backend(group)
