@@ -444,6 +444,47 @@ def extra_metrics(ctx):
                                                "near_tie": st["n_near_tie"], "ms": dt * 1e3}
     dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 7, n_subcell_depth=3), reps=2)
     ex["cfg2_bunny_hmc_depth7_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "leaves_per_s": 4096 / dt}
+    dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 9, n_subcell_depth=3), reps=1)
+    ex["cfg2_bunny_hmc_depth9_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "triangles_per_s": tri.shape[0] / dt}
+
+    # config 3: hammer x bunny under seeded rigid transforms, affine_truncate (n_keep 64, 'absolute'), eps 1e-3
+    import mlp
+    pA = mlps["hammer"]
+    pB = mlp.prepend_op(mlps["bunny"], mlp.spatial_transformation())
+    kw = dict(affine_n_truncate=64, affine_truncate_policy="absolute")
+    fA = implicit_mlp_utils.generate_implicit_from_params(pA, "affine_truncate", **kw)
+    fB = implicit_mlp_utils.generate_implicit_from_params(pB, "affine_truncate", **kw)
+    rng = np.random.default_rng(0)
+    n_q, n_found, n_nodes, n_rounds, t_tot, t_max = 24, 0, 0, 0, 0.0, 0.0
+    for i in range(n_q + 1):
+        th = rng.uniform(0, 2 * np.pi)
+        pB["0000.spatial_transformation.R"] = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+        pB["0000.spatial_transformation.t"] = rng.uniform(-1.5, 1.5, 3).astype(np.float32)
+        st = {}
+        t0 = time.perf_counter()
+        found = kd_tree.find_any_intersection((fA, fB), (pA, pB), lo, hi, 1e-3, stats=st, ctx=ctx)[0]
+        d = time.perf_counter() - t0
+        if i == 0:
+            continue                      # warm-up
+        n_found += bool(found); n_nodes += st["n_nodes"]; n_rounds += st["n_rounds"]; t_tot += d; t_max = max(t_max, d)
+    ex["cfg3_hammer_x_bunny_intersection_truncate64"] = {"queries": n_q, "found": n_found, "queries_per_s": n_q / t_tot, "nodes_per_s": n_nodes / t_tot,
+                                                        "nodes": n_nodes, "rounds": n_rounds, "mean_ms": 1e3 * t_tot / n_q, "max_ms": 1e3 * t_max}
+
+    # config 4: birdcage_occ closest_point, affine_fixed, eps 1e-3.  The reference's default global LIFO window
+    # (batch_process_size 2048) couples the queries and is sequential by construction; the window >= stack
+    # regime is the same algorithm run level-synchronously per query (shardable).  Both on stated sub-samples of the 1 M queries.
+    p = mlps["birdcage_occ"]
+    f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
+    q_all = np.random.default_rng(0).uniform(-1, 1, (1000000, 3)).astype(np.float32)
+    for tag, nq, B in (("window2048", 256, 2048), ("window_ge_stack", 4096, 2 ** 26)):
+        st = {}
+        kd_tree.closest_point(f, p, lo, hi, q_all[:64], eps=1e-3, batch_process_size=B, ctx=ctx)
+        t0 = time.perf_counter()
+        dist_q, _ = kd_tree.closest_point(f, p, lo, hi, q_all[:nq], eps=1e-3, batch_process_size=B, stats=st, ctx=ctx)
+        d = time.perf_counter() - t0
+        ex[f"cfg4_birdcage_closest_point_{tag}"] = {"queries": nq, "batch_process_size": B, "queries_per_s": nq / d, "node_visits_per_s": st["n_visits"] / d,
+                                                   "visits_per_query": st["n_visits"] / nq, "rounds": st["n_rounds"], "max_stack": st["max_stack"], "ms": d * 1e3,
+                                                   "finite": int(np.isfinite(dist_q).sum())}
     return ex
 
 
