@@ -508,11 +508,11 @@ struct Engine {
         unsigned m[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-            bool nz = false;
-            if (active) {
+            // nonzero in any row: OR of the bit patterns without their sign bits (-0 counts as zero, nan as nonzero)
+            unsigned bits = 0u;
 #pragma unroll
-                for (int r = 0; r < ROWS; ++r) nz = nz || (acc[r][c] != 0.f);
-            }
+            for (int r = 0; r < ROWS; ++r) bits |= __float_as_uint(acc[r][c]);
+            const bool nz = active && (bits << 1) != 0u;
             unsigned b = __ballot_sync(0xffffffffu, nz);
 #pragma unroll
             for (int s = G::CG; s < 32; s <<= 1) b |= b >> s;          // OR over the tiles (t) that share this column
@@ -583,18 +583,20 @@ struct Engine {
                 }
             }
         }
-        // zero columns that pad every segment to a multiple of 4 (+ the list's over-read tail)
-        for (int i = 0; i < nch; ++i) {
-            const int s0 = seg[4 * i] + seg[4 * i + 3], pad = seg[4 * i + 1] - seg[4 * i + 3];
-            if (pad > 0) {
-                for (int idx = lane; idx < WARP_ROWS * 4; idx += 32) {
-                    const int q = idx & 3;
-                    if (q < pad) act[(idx >> 2) * G::S + s0 + q] = 0.f;
+        // zero columns that pad every segment to a multiple of 4 (+ the list's over-read tail): lane = (chunk, pad slot)
+        {
+            const int i = lane >> 2, q = lane & 3;
+            if (i < nch) {
+                const int4 sg = *reinterpret_cast<const int4*>(seg + 4 * i);      // start, n4, cb0, cnt
+                if (q < sg.y - sg.w) {
+                    const int pos = sg.x + sg.w + q;
+#pragma unroll 5
+                    for (int r = 0; r < WARP_ROWS; ++r) act[r * G::S + pos] = 0.f;
+                    lst[pos] = 0u;
                 }
-                if (lane < pad) lst[s0 + lane] = 0u;
             }
+            if (lane < 8) lst[seg[4 * nch] + lane] = 0u;
         }
-        if (lane < 8) lst[seg[4 * nch] + lane] = 0u;
     }
 
     // ---- one hidden layer: acc[rows][8] = act[rows][:K] @ W[:K][my 8 columns] -----------------------
