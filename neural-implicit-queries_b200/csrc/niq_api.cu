@@ -56,6 +56,8 @@ struct TimedLaunch { cudaEvent_t a, b; int family; };
 struct niq_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;          // side stream: the second shape of find_any_intersection runs beside the first
+    cudaEvent_t fork = nullptr, join = nullptr;
     cudaDeviceProp prop{};
     long long launches = 0;
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -136,6 +138,9 @@ extern "C" int niq_ctx_create(int device, niq_ctx** out) {
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     }
+    CU(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->fork, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->join, cudaEventDisableTiming));
     CU(cudaEventCreate(&c->t0));
     CU(cudaEventCreate(&c->t1));
     CU(cudaMallocHost(&c->pinned, 64 * sizeof(long long)));
@@ -154,6 +159,9 @@ extern "C" int niq_ctx_destroy(niq_ctx* c) {
     if (c->t1) cudaEventDestroy(c->t1);
     if (c->pinned) cudaFreeHost(c->pinned);
     if (c->d_exec) cudaFree(c->d_exec);
+    if (c->fork) cudaEventDestroy(c->fork);
+    if (c->join) cudaEventDestroy(c->join);
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
     return NIQ_OK;
@@ -587,7 +595,7 @@ static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg
     g.kcap = round_up(std::max(g.kcap, 4), 4);   // keeps the aff matrix 16-byte aligned behind mags/rank
     g.W = round_up(m->maxw_pad, 8);
     g.label = label; g.lower = lower; g.upper = upper; g.near_tie = tie;
-    const size_t floats = (size_t)13 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W + (size_t)(g.truncate ? g.n_keep : 0) * g.W + 16;
+    const size_t floats = (size_t)22 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W * (g.truncate ? 2 : 1) + 16;
     const size_t bytes = floats * sizeof(float);
     if (bytes > c->prop.sharedMemPerBlockOptin)
         return fail(NIQ_EUNSUPPORTED, "affine state of %zu bytes exceeds shared memory (%zu): network too wide/deep for this mode", bytes, (size_t)c->prop.sharedMemPerBlockOptin);
@@ -1207,48 +1215,61 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
     long long n_nodes = 0, n_rounds = 0, n_tie = 0;
     *found = 0;
     loc[0] = loc[1] = loc[2] = -777.f;
+    DevBuf meta(c);                       // [0] first found index (u64), [1] near-tie boxes (u64), [2] survivors of the round (int)
+    TRY(meta.alloc(32));
     while (cur.n > 0) {
         const long long N = cur.n;
         n_nodes += N; n_rounds += 1;
-        DevBuf labA(c), labB(c), vA(c), vB(c), needs(c), scan(c), locs(c), first(c), tieA(c), tieB(c);
+        DevBuf labA(c), labB(c), vA(c), vB(c), needs(c), scan(c), locs(c), tieA(c), tieB(c);
         TRY(labA.alloc(N * 4)); TRY(labB.alloc(N * 4)); TRY(vA.alloc(N * 28)); TRY(vB.alloc(N * 28));
-        TRY(needs.alloc(N * 4)); TRY(scan.alloc((N + 1) * 4)); TRY(locs.alloc(N * 12)); TRY(first.alloc(8));
+        TRY(needs.alloc(N * 4)); TRY(scan.alloc((N + 1) * 4)); TRY(locs.alloc(N * 12));
         TRY(tieA.alloc(N)); TRY(tieB.alloc(N));
+        {
+            const unsigned long long init[4] = {~0ull, 0ull, 0ull, 0ull};
+            memcpy(c->pinned + 8, init, 32);
+            CU(cudaMemcpyAsync(meta.p, c->pinned + 8, 32, cudaMemcpyHostToDevice, c->stream));
+        }
         BoxSource bs{};
         bs.kind = 1; bs.v = 3; bs.a = cur.lo; bs.b = cur.hi;
-        TRY(classify_dev(c, mA, cfgA, bs, N, 0.f, labA.as<int>(), nullptr, nullptr, tieA.as<unsigned char>()));
-        TRY(classify_dev(c, mB, cfgB, bs, N, 0.f, labB.as<int>(), nullptr, nullptr, tieB.as<unsigned char>()));
         PointSource ps{};
         ps.kind = 2; ps.a = cur.lo; ps.b = cur.hi; ps.sample_scale = eps_w;
+        // shape B on the side stream, beside shape A (the frontier is small: each launch alone leaves most SMs idle)
+        CU(cudaEventRecord(c->fork, c->stream));
+        CU(cudaStreamWaitEvent(c->stream2, c->fork, 0));
+        int rB = NIQ_OK;
+        {
+            const bool timing = c->timing;
+            c->timing = false;
+            std::swap(c->stream, c->stream2);
+            rB = classify_dev(c, mB, cfgB, bs, N, 0.f, labB.as<int>(), nullptr, nullptr, tieB.as<unsigned char>());
+            if (rB == NIQ_OK) rB = launch_eval_points(c, mB, ps, 7 * N, vB.as<float>(), nullptr);
+            std::swap(c->stream, c->stream2);
+            c->timing = timing;
+        }
+        CU(cudaEventRecord(c->join, c->stream2));
+        TRY(rB);
+        TRY(classify_dev(c, mA, cfgA, bs, N, 0.f, labA.as<int>(), nullptr, nullptr, tieA.as<unsigned char>()));
         TRY(launch_eval_points(c, mA, ps, 7 * N, vA.as<float>(), nullptr));
-        TRY(launch_eval_points(c, mB, ps, 7 * N, vB.as<float>(), nullptr));
-        CU(cudaMemsetAsync(first.p, 0xFF, 8, c->stream));
+        CU(cudaStreamWaitEvent(c->stream, c->join, 0));
         const int g = (int)((N + 255) / 256);
         {
             LaunchTimer lt(c, 1);
             k_isect_logic<<<g, 256, 0, c->stream>>>(cur.lo, cur.hi, N, labA.as<int>(), labB.as<int>(), vA.as<float>(), vB.as<float>(),
-                                                   eps_w, needs.as<int>(), locs.as<float>(), first.as<unsigned long long>());
+                                                   eps_w, needs.as<int>(), locs.as<float>(), meta.as<unsigned long long>(),
+                                                   tieA.as<unsigned char>(), tieB.as<unsigned char>(), meta.as<unsigned long long>() + 1);
             CU(cudaGetLastError());
         }
-        unsigned long long first_idx = ~0ull;
-        TRY(read_back(c, first.p, 8, &first_idx));
-        {
-            std::vector<unsigned char> ht((size_t)N);
-            CU(cudaMemcpyAsync(ht.data(), tieA.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            for (unsigned char b : ht) n_tie += b;
-            CU(cudaMemcpyAsync(ht.data(), tieB.p, (size_t)N, cudaMemcpyDeviceToHost, c->stream));
-            CU(cudaStreamSynchronize(c->stream));
-            for (unsigned char b : ht) n_tie += b;
-        }
-        if (first_idx != ~0ull) {
-            TRY(read_back(c, locs.as<float>() + 3 * first_idx, 12, loc));
+        TRY(scan_exclusive(c, needs.as<int>(), N, scan.as<int>()));
+        CU(cudaMemcpyAsync(meta.as<unsigned long long>() + 2, scan.as<int>() + N, 4, cudaMemcpyDeviceToDevice, c->stream));
+        unsigned long long hm[4];
+        TRY(read_back(c, meta.p, 32, hm));                 // the round's only host synchronisation
+        n_tie += (long long)hm[1];
+        if (hm[0] != ~0ull) {
+            TRY(read_back(c, locs.as<float>() + 3 * hm[0], 12, loc));
             *found = 1;
             break;
         }
-        TRY(scan_exclusive(c, needs.as<int>(), N, scan.as<int>()));
-        int n_new = 0;
-        TRY(read_back(c, scan.as<int>() + N, 4, &n_new));
+        const int n_new = (int)(hm[2] & 0xffffffffull);
         TRY(list_reserve(c, nxt, std::max<long long>(2ll * n_new, 1)));
         if (n_new > 0) {
             LaunchTimer lt(c, 1);
@@ -1256,7 +1277,6 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
             CU(cudaGetLastError());
         }
         nxt.n = 2ll * n_new;
-        CU(cudaStreamSynchronize(c->stream));
         std::swap(cur, nxt);
     }
     if (stats) { stats[0] = n_nodes; stats[1] = n_rounds; stats[2] = n_tie; }

@@ -5,8 +5,11 @@
 // base, err live in shared memory (up to 132 KB for the 8x64 nets in affine_all).  A dense layer is the
 // row-wise product S@A, done in place: the 4 rows of a register tile are owned by lanes of ONE warp, so
 // __syncwarp() orders the read-all / write-back; weights are read through L1 (they are shared by every CTA).
-// Radius reduction, (alpha,beta,delta), row scaling, diag(delta) append and the top-n_keep selection are
-// block-wide phases separated by __syncthreads().
+// The two vector rows (base, err) are K-split over thread groups.  Radius reduction, (alpha,beta,delta), row
+// scaling (one warp per row: conflict-free, yields the row's L1 norm for free), diag(delta) append and the stable
+// top-n_keep selection (two threads per row for the O(k^2) rank, kept rows moved to a second buffer that then swaps
+// with the first) are block-wide phases separated by __syncthreads().  Queries call it on small frontiers
+// (<= a few hundred boxes), so the design goal is the latency of ONE box.
 #pragma once
 #include "niq_kernels.cuh"
 
@@ -25,19 +28,27 @@ struct GrowArgs {
 
 __device__ __forceinline__ int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
+// warp-level sum of one value per lane
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
 __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant__ NetDev net, const GrowArgs g) {
     extern __shared__ __align__(16) float sm[];
     const int W = g.W;
     float* base = sm;                 // [W]
-    float* err = base + W;            // [W]
+    float* base2 = base + W;          // [W]
+    float* err = base2 + W;           // [W]
     float* err2 = err + W;            // [W]
     float* alpha = err2 + W;          // [W]
     float* delta = alpha + W;         // [W]
-    float* red = delta + W;           // [8][W] partial radius sums
-    float* mags = red + 8 * W;        // [kcap]
+    float* red = delta + W;           // [16][W] partial sums (two vectors x 8 parts)
+    float* mags = red + 16 * W;       // [kcap]
     int* rank = reinterpret_cast<int*>(mags + g.kcap);   // [kcap]
     float* aff = reinterpret_cast<float*>(rank + g.kcap); // [kcap][W]
-    float* tmp = aff + (size_t)g.kcap * W;               // [n_keep][W] (truncate only)
+    float* tmp = aff + (size_t)g.kcap * W;               // [kcap][W] (truncate only): the truncated state is built here, then the two swap
     __shared__ float s_fin[3];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -72,6 +83,8 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
             __syncthreads();
         }
 
+        float* b_cur = base;
+        float* b_nxt = base2;
         float* e_cur = err;
         float* e_nxt = err2;
         for (int l = 0; l < net.n_layers; ++l) {
@@ -79,20 +92,29 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
             const float* A = net.chunks[L.chunk_begin].src;
             if (!L.last_of_net) {
                 const int K = L.in_pad, N = L.out_pad;
-                // -- err row: e_nxt = e_cur @ |A| --
-                for (int c = tid; c < N; c += blockDim.x) {
-                    float s = 0.f;
-                    for (int j = 0; j < K; ++j) s = fmaf(e_cur[j], fabsf(__ldg(A + (size_t)j * N + c)), s);
-                    e_nxt[c] = s;
+                const int Np2 = next_pow2(N);
+                const int parts = 256 / Np2 >= 8 ? 8 : (256 / Np2 > 0 ? 256 / Np2 : 1);
+                // -- the two vector rows, K split over `parts` thread groups: base@A and err@|A| (partials in red) --
+                {
+                    const int c = tid % Np2, p = tid / Np2;
+                    if (c < N && p < parts) {
+                        float sb = 0.f, se = 0.f;
+                        for (int j = p; j < K; j += parts) {
+                            const float w = __ldg(A + (size_t)j * N + c);
+                            sb = fmaf(b_cur[j], w, sb);
+                            se = fmaf(e_cur[j], fabsf(w), se);
+                        }
+                        red[p * W + c] = sb;
+                        red[(8 + p) * W + c] = se;
+                    }
                 }
-                // -- base and aff rows, in place; row R = 0 is base, R >= 1 is aff[R-1] --
+                // -- aff rows, in place; a register tile = 4 rows x 4 columns, the 4 rows owned by lanes of ONE warp --
                 const int cgw = N >> 2;                       // column groups of 4
                 const int cgp = next_pow2(cgw) < 32 ? next_pow2(cgw) : 32;
                 const int rg_per_warp = 32 / cgp;
                 const int my_rg = lane / cgp, my_cg = lane % cgp;
-                const int n_rows = k + 1;
                 const int rows_per_iter = 8 * rg_per_warp * 4;
-                for (int r0 = 0; r0 < n_rows; r0 += rows_per_iter) {
+                for (int r0 = 0; r0 < k; r0 += rows_per_iter) {
                     const int rbase = r0 + (warp * rg_per_warp + my_rg) * 4;
                     for (int cg0 = 0; cg0 < cgw; cg0 += cgp) {      // cgw > 32 never happens (N <= 128)
                         const int cg = cg0 + my_cg;
@@ -104,10 +126,7 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                             for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
                         const float* rp[4];
 #pragma unroll
-                        for (int r = 0; r < 4; ++r) {
-                            const int R = rbase + r;
-                            rp[r] = R == 0 ? base : (R < n_rows ? aff + (size_t)(R - 1) * W : base);
-                        }
+                        for (int r = 0; r < 4; ++r) rp[r] = aff + (size_t)(rbase + r < k ? rbase + r : 0) * W;
                         if (act_thread) {
                             for (int j = 0; j < K; j += 4) {
                                 float4 a4[4];
@@ -130,30 +149,29 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                         __syncwarp();
                         if (act_thread) {
 #pragma unroll
-                            for (int r = 0; r < 4; ++r) {
-                                const int R = rbase + r;
-                                if (R < n_rows) {
-                                    float* dst = R == 0 ? base : aff + (size_t)(R - 1) * W;
-                                    float4 o = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
-                                    if (R == 0) {
-                                        const float4 b = __ldg(reinterpret_cast<const float4*>(L.bias + 4 * cg));
-                                        o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                                    }
-                                    *reinterpret_cast<float4*>(dst + 4 * cg) = o;
-                                }
-                            }
+                            for (int r = 0; r < 4; ++r)
+                                if (rbase + r < k)
+                                    *reinterpret_cast<float4*>(aff + (size_t)(rbase + r) * W + 4 * cg) =
+                                        make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
                         }
                         __syncwarp();
                     }
                 }
-                { float* t2 = e_cur; e_cur = e_nxt; e_nxt = t2; }
+                __syncthreads();
+                // -- finish the vector rows --
+                if (tid < N) {
+                    float sb = 0.f, se = 0.f;
+                    for (int p = 0; p < parts; ++p) { sb += red[p * W + tid]; se += red[(8 + p) * W + tid]; }
+                    b_nxt[tid] = sb + __ldg(L.bias + tid);
+                    e_nxt[tid] = se;
+                }
+                { float* t2 = e_cur; e_cur = e_nxt; e_nxt = t2; t2 = b_cur; b_cur = b_nxt; b_nxt = t2; }
                 __syncthreads();
 
                 if (L.act != ACT_NONE) {
-                    // -- radius per neuron: rad[c] = sum_r |aff[r][c]| + err[c] (partials over 8 row strides) --
-                    const int parts = 256 / next_pow2(N) >= 8 ? 8 : (256 / next_pow2(N) > 0 ? 256 / next_pow2(N) : 1);
+                    // -- radius per neuron: rad[c] = sum_r |aff[r][c]| + err[c] (partials over row strides) --
                     {
-                        const int c = tid % next_pow2(N), p = tid / next_pow2(N);
+                        const int c = tid % Np2, p = tid / Np2;
                         if (c < N && p < parts) {
                             float s = 0.f;
                             for (int r = p; r < k; r += parts) s += fabsf(aff[(size_t)r * W + c]);
@@ -166,85 +184,114 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                         float rad = 0.f;
                         for (int p = 0; p < parts; ++p) rad += red[p * W + c];
                         rad += e_cur[c];
-                        const float b0 = base[c];
+                        const float b0 = b_cur[c];
                         float al, be, de;
                         if (L.act == ACT_RELU) relu_lin(b0 - rad, b0 + rad, al, be, de);
                         else elu_lin(b0 - rad, b0 + rad, al, be, de);
-                        base[c] = al * b0 + be;
+                        b_cur[c] = al * b0 + be;
                         e_cur[c] = al * e_cur[c];
                         alpha[c] = al;
                         delta[c] = de;
                     }
                     __syncthreads();
-                    // -- scale rows by alpha, append diag(delta) (out_dim new rows) --
-                    for (int idx = tid; idx < k * N; idx += blockDim.x) {
-                        const int r = idx / N, c = idx - r * N;
-                        aff[(size_t)r * W + c] = alpha[c] * aff[(size_t)r * W + c];
+                    // -- scale rows by alpha (one warp per row: also yields the row's L1 norm), append diag(delta) --
+                    const bool trunc = g.truncate && k + L.out_dim > g.n_keep;
+                    for (int r = warp; r < k; r += 8) {
+                        float* row = aff + (size_t)r * W;
+                        for (int c = lane; c < N; c += 32) row[c] = alpha[c] * row[c];
+                        if (trunc) {
+                            // L1 norm in the summation order of the oracle's np.sum over a contiguous float32 row (n <= 128:
+                            // 8 strided accumulators, pairwise combine, sequential remainder), so that near-equal rows rank
+                            // the same way on both sides (reference src/affine.py:143-151 sorts by this norm)
+                            __syncwarp();
+                            const int w = L.out_dim, w8 = w & ~7;
+                            float s = 0.f;
+                            if (lane < 8)
+                                for (int c = lane; c < w8; c += 8) s += fabsf(row[c]);
+                            s += __shfl_xor_sync(0xffffffffu, s, 1);
+                            s += __shfl_xor_sync(0xffffffffu, s, 2);
+                            s += __shfl_xor_sync(0xffffffffu, s, 4);
+                            if (lane == 0) {
+                                for (int c = w8; c < w; ++c) s += fabsf(row[c]);
+                                mags[r] = s;
+                            }
+                        }
                     }
                     for (int idx = tid; idx < L.out_dim * N; idx += blockDim.x) {
                         const int r = idx / N, c = idx - r * N;
                         aff[(size_t)(k + r) * W + c] = (r == c) ? delta[c] : 0.f;
                     }
+                    if (trunc && tid < L.out_dim) mags[k + tid] = fabsf(delta[tid]);   // L1 norm of a diag row
                     k += L.out_dim;
                     __syncthreads();
 
-                    if (g.truncate && k > g.n_keep) {
+                    if (trunc) {
                         // -- keep the n_keep rows of largest L1 norm, stable (reference src/affine.py:127-162) --
-                        for (int r = tid; r < k; r += blockDim.x) {
-                            float s = 0.f;
-                            for (int c = 0; c < N; ++c) s += fabsf(aff[(size_t)r * W + c]);
-                            mags[r] = s;
+                        // rank[r] = #rows that sort before r; two threads per row, each scans half of the rows
+                        for (int r = tid; r < k; r += blockDim.x) rank[r] = 0;
+                        __syncthreads();
+                        for (int r0 = 0; r0 < k; r0 += 128) {
+                            const int r = r0 + (tid & 127), half = tid >> 7;
+                            if (r < k) {
+                                const float m = mags[r];
+                                int rk = 0;
+                                const int q0 = half ? (k + 1) / 2 : 0, q1 = half ? k : (k + 1) / 2;
+                                for (int q = q0; q < q1; ++q) { const float mq = mags[q]; rk += (mq > m) || (mq == m && q < r); }
+                                atomicAdd(&rank[r], rk);
+                            }
                         }
                         __syncthreads();
-                        for (int r = tid; r < k; r += blockDim.x) {
-                            const float m = mags[r];
-                            int rk = 0;
-                            for (int q = 0; q < k; ++q) rk += (mags[q] > m) || (mags[q] == m && q < r);
-                            rank[r] = rk;
+                        // dropped rows fold into err (partials over row strides); kept rows move to tmp at their rank
+                        {
+                            const int c = tid % Np2, p = tid / Np2;
+                            if (c < N && p < parts) {
+                                float s = 0.f;
+                                for (int r = p; r < k; r += parts)
+                                    if (rank[r] >= g.n_keep) s += fabsf(aff[(size_t)r * W + c]);
+                                red[p * W + c] = s;
+                            }
+                        }
+                        for (int r = warp; r < k; r += 8) {
+                            const int rk = rank[r];
+                            if (rk < g.n_keep)
+                                for (int c = lane; c < N; c += 32) tmp[(size_t)rk * W + c] = aff[(size_t)r * W + c];
                         }
                         __syncthreads();
                         if (tid < N) {
                             float s = 0.f;
-                            for (int r = 0; r < k; ++r)
-                                if (rank[r] >= g.n_keep) s += fabsf(aff[(size_t)r * W + tid]);
+                            for (int p = 0; p < parts; ++p) s += red[p * W + tid];
                             e_cur[tid] = e_cur[tid] + s;
                         }
-                        for (int idx = tid; idx < k * N; idx += blockDim.x) {
-                            const int r = idx / N, c = idx - r * N;
-                            if (rank[r] < g.n_keep) tmp[(size_t)rank[r] * W + c] = aff[(size_t)r * W + c];
-                        }
-                        __syncthreads();
-                        for (int idx = tid; idx < g.n_keep * N; idx += blockDim.x) {
-                            const int r = idx / N, c = idx - r * N;
-                            aff[(size_t)r * W + c] = tmp[(size_t)r * W + c];
-                        }
+                        { float* t2 = aff; aff = tmp; tmp = t2; }
                         k = g.n_keep;
                         __syncthreads();
                     }
                 }
             } else {
-                // ---- final dot layer: scalar base, k scalar coefficients, scalar err ----
+                // ---- final dot layer: scalar base, k scalar coefficients, scalar err (one warp per row) ----
                 const int K = L.in_pad;
                 float part = 0.f;
-                for (int r = tid; r < k; r += blockDim.x) {
+                for (int r = warp; r < k; r += 8) {
                     float s = 0.f;
-                    for (int j = 0; j < K; ++j) s = fmaf(aff[(size_t)r * W + j], __ldg(A + j), s);
+                    for (int j = lane; j < K; j += 32) s = fmaf(aff[(size_t)r * W + j], __ldg(A + j), s);
+                    s = warp_sum(s);
                     part += fabsf(s);
                 }
-                // block reduce |coefficients|
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
                 if (lane == 0) red[warp] = part;
-                if (tid == 32) {
-                    float s = 0.f, sa = 0.f;
-                    for (int j = 0; j < K; ++j) { s = fmaf(base[j], __ldg(A + j), s); sa = fmaf(fabsf(base[j]), fabsf(__ldg(A + j)), sa); }
-                    s_fin[0] = s + __ldg(L.bias);
-                    s_fin[2] = sa + fabsf(__ldg(L.bias));
-                }
-                if (tid == 64) {
-                    float s = 0.f;
-                    for (int j = 0; j < K; ++j) s = fmaf(e_cur[j], fabsf(__ldg(A + j)), s);
-                    s_fin[1] = s;
+                if (warp == 0) {
+                    float s = 0.f, sa = 0.f, se = 0.f;
+                    for (int j = lane; j < K; j += 32) {
+                        const float w = __ldg(A + j);
+                        s = fmaf(b_cur[j], w, s);
+                        sa = fmaf(fabsf(b_cur[j]), fabsf(w), sa);
+                        se = fmaf(e_cur[j], fabsf(w), se);
+                    }
+                    s = warp_sum(s); sa = warp_sum(sa); se = warp_sum(se);
+                    if (lane == 0) {
+                        s_fin[0] = s + __ldg(L.bias);
+                        s_fin[2] = sa + fabsf(__ldg(L.bias));
+                        s_fin[1] = se;
+                    }
                 }
                 __syncthreads();
                 if (tid == 0) {

@@ -542,8 +542,14 @@ __global__ void k_isect_logic(const float* __restrict__ lo, const float* __restr
                               const int* __restrict__ labA, const int* __restrict__ labB,
                               const float* __restrict__ valsA, const float* __restrict__ valsB, float eps_w,
                               int* __restrict__ needs, float* __restrict__ loc_out,
-                              unsigned long long* __restrict__ first_found) {
+                              unsigned long long* __restrict__ first_found, const unsigned char* __restrict__ tieA,
+                              const unsigned char* __restrict__ tieB, unsigned long long* __restrict__ n_tie) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    {   // near-tie boxes of the round (diagnostic counter): warp-aggregated
+        const int nt = i < n ? (int)(tieA[i] != 0) + (int)(tieB[i] != 0) : 0;
+        const unsigned b1 = __ballot_sync(0xffffffffu, nt >= 1), b2 = __ballot_sync(0xffffffffu, nt >= 2);
+        if ((threadIdx.x & 31) == 0 && (b1 | b2)) atomicAdd(n_tie, (unsigned long long)(__popc(b1) + __popc(b2)));
+    }
     if (i >= n) return;
     const float* l = lo + 3 * i;
     const float* h = hi + 3 * i;

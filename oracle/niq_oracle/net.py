@@ -195,6 +195,27 @@ class AffineContext:
             raise ValueError("oracle: affine_append is outside the hot-path scope")
 
 
+_RANK_TIE_RECORDER = None
+
+
+def truncate_rank_near_tie(params, ctx, center, vecs, rel=1e-5, chunk=1024):
+    """(N,) bool: some truncation of the box's propagation decided keep/drop between rows whose L1 norms agree to
+    `rel` (relative).  Such boxes are excluded from strict parity like bound near-ties (counted, reported)."""
+    global _RANK_TIE_RECORDER
+    center = np.ascontiguousarray(center, F32)
+    vecs = np.ascontiguousarray(vecs, F32)
+    out = np.zeros(center.shape[0], bool)
+    for s0 in range(0, center.shape[0], chunk):
+        _RANK_TIE_RECORDER = {"rel": F32(rel), "flags": []}
+        try:
+            affine_forward(params, ctx, center[s0:s0 + chunk], vecs[s0:s0 + chunk])
+            for f in _RANK_TIE_RECORDER["flags"]:
+                out[s0:s0 + chunk] |= f
+        finally:
+            _RANK_TIE_RECORDER = None
+    return out
+
+
 def _radius(aff, err):
     """affine.py:85-91 -- sum_r |aff_r| + err, batched: aff (N,k,w), err (N,w)."""
     return (np.abs(aff).sum(axis=1, dtype=F32) + err).astype(F32)
@@ -212,6 +233,13 @@ def _truncate(ctx, base, aff, err):
         raise RuntimeError("oracle: only the 'absolute' truncate policy is supported")
     mags = np.abs(aff).sum(axis=-1, dtype=F32)                       # (N,k)
     order = np.argsort(-mags, axis=-1, kind="stable")                # (N,k)
+    if _RANK_TIE_RECORDER is not None:
+        # diagnostic (ours): the keep/drop decision is a near-tie when the last kept and the first dropped row have
+        # L1 norms within `rel` of each other -- float32 summation-order noise can then flip it
+        srt = np.take_along_axis(mags, order, axis=-1)
+        a, b = srt[:, n_keep - 1], srt[:, n_keep]
+        # (rows that are exactly zero tie exactly on both sides: the stable sort settles them identically)
+        _RANK_TIE_RECORDER["flags"].append((a > 0) & ((a - b) <= _RANK_TIE_RECORDER["rel"] * a))
     aff = np.take_along_axis(aff, order[:, :, None], axis=1)
     keep, drop = aff[:, :n_keep, :], aff[:, n_keep:, :]
     err = (err + np.abs(drop).sum(axis=1, dtype=F32)).astype(F32)

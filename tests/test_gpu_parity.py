@@ -131,11 +131,19 @@ def test_classify_vs_oracle_random(name, mode, n):
     olab, olo, oup, sc = net.classify_box(p, octx(mode, 16), lo_b, hi_b, return_scale=True)
     lab, lo, up, tie = func.bound_box(p, lo_b, hi_b)
     rel = net.tie_rel(p)
-    check_bounds(lo, up, olo, oup, sc, rel)
-    n_tie = check_labels(lab, olab, olo, oup, sc, rel=rel)
+    ok = np.ones(n, bool)
+    if mode == "affine_truncate":
+        # keep/drop decisions between rows of (nearly) equal L1 norm flip with float32 summation order and change the
+        # affine form, not just its last bits: those boxes are near-ties of the truncation, counted and set aside
+        c, v = net.box_to_general(lo_b, hi_b)
+        rank_tie = net.truncate_rank_near_tie(p, octx(mode, 16), c, v, rel=rel)
+        assert rank_tie.mean() < (0.1 if rel > 1e-5 else 0.01), f"{rank_tie.sum()} truncation near-ties"   # elu nets: 2e-4 band
+        ok = ~rank_tie
+    check_bounds(lo[ok], up[ok], olo[ok], oup[ok], sc[ok], rel)
+    n_tie = check_labels(lab[ok], olab[ok], olo[ok], oup[ok], sc[ok], rel=rel)
     assert n_tie < 0.01 * n
     # the device's own near-tie flag covers every label disagreement
-    assert np.all(tie | (lab == olab))
+    assert np.all((tie | (lab == olab))[ok])
     assert tie.mean() < 0.01
 
 
