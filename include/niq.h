@@ -63,12 +63,13 @@ typedef enum niq_mode {
     NIQ_MODE_INTERVAL = 0,
     NIQ_MODE_AFFINE_FIXED = 1,
     NIQ_MODE_AFFINE_TRUNCATE = 2,
-    NIQ_MODE_AFFINE_ALL = 3
+    NIQ_MODE_AFFINE_ALL = 3,
+    NIQ_MODE_AFFINE_APPEND = 4   /* src/affine.py:183-191: per activation keep the n_append largest deltas as new terms */
 } niq_mode;
 
 typedef struct niq_mode_cfg {
     int32_t mode;            /* niq_mode */
-    int32_t truncate_count;  /* affine_truncate: rows kept (src/affine.py:133), ignored otherwise */
+    int32_t truncate_count;  /* affine_truncate: rows kept (src/affine.py:133); affine_append: n_append; else ignored */
     int32_t truncate_policy; /* 0 = 'absolute' (only policy supported; 'relative' -> NIQ_EUNSUPPORTED) */
 } niq_mode_cfg;
 

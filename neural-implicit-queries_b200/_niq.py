@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("NIQ_LIB") or os.path.join(_HERE, "libniq.so")   # NIQ
 NIQ_OK, NIQ_EINVAL, NIQ_ENOMEM, NIQ_ECUDA, NIQ_ECAPACITY, NIQ_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
 OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL = 0, 1, 2, 3, 4
-MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3}
+MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4}
 TREE_INTERIOR, TREE_EXTERIOR = 1, 2
 
 # every symbol include/niq.h declares (tests check the library exports all of them)
@@ -283,6 +283,8 @@ def mode_cfg(ctx):
     cfg = ModeCfg()
     cfg.mode = MODE_IDS[ctx.mode]
     cfg.truncate_count = int(ctx.truncate_count) if ctx.mode == "affine_truncate" else 0
+    if ctx.mode == "affine_append":
+        cfg.truncate_count = int(ctx.n_append)
     if ctx.mode == "affine_truncate" and ctx.truncate_policy != "absolute":
         if ctx.truncate_policy == "relative":
             cfg.truncate_policy = 1      # the library answers NIQ_EUNSUPPORTED with the reason

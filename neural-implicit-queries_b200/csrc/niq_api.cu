@@ -325,6 +325,7 @@ struct niq_mlp {
     int total_floats = 0;  // packed weights of all layers
     int sum_act_out = 0;   // sum of out_dim over activation layers (affine_all growth)
     int max_act_out = 0;
+    int min_act_out = 1 << 30, n_act_layers = 0;
 };
 
 static int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -448,7 +449,10 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
         m->layers.push_back(L);
         m->macs += (int64_t)L.in_dim * L.out_dim;
         m->maxw_pad = std::max(m->maxw_pad, std::max(L.in_pad, L.dot ? 1 : L.out_pad));
-        if (L.act != ACT_NONE) { m->sum_act_out += L.out_dim; m->max_act_out = std::max(m->max_act_out, L.out_dim); }
+        if (L.act != ACT_NONE) {
+            m->sum_act_out += L.out_dim; m->max_act_out = std::max(m->max_act_out, L.out_dim);
+            m->min_act_out = std::min(m->min_act_out, L.out_dim); m->n_act_layers += 1;
+        }
     }
     CU(cudaMalloc(&m->d_weights, hw.size() * sizeof(float)));
     CU(cudaMalloc(&m->d_bias, hb.size() * sizeof(float)));
@@ -589,9 +593,13 @@ static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg
     g.src = src; g.n = n; g.offset = offset;
     g.truncate = cfg->mode == NIQ_MODE_AFFINE_TRUNCATE;
     g.n_keep = g.truncate ? cfg->truncate_count : 0;
+    g.n_append = cfg->mode == NIQ_MODE_AFFINE_APPEND ? cfg->truncate_count : 0;
     const int v = src.kind == 0 ? src.v : 3;
     if (g.truncate && g.n_keep < 0) return fail(NIQ_EINVAL, "affine_truncate: truncate_count must be >= 0");
-    g.kcap = g.truncate ? std::max(v, std::min(g.n_keep, v + m->sum_act_out)) + m->max_act_out : v + m->sum_act_out;
+    if (cfg->mode == NIQ_MODE_AFFINE_APPEND && (g.n_append < 1 || g.n_append > m->min_act_out))
+        return fail(NIQ_EINVAL, "affine_append: n_append must be in 1..%d (the narrowest activation layer; jax.lax.top_k needs k <= width)", m->min_act_out);
+    g.kcap = g.truncate ? std::max(v, std::min(g.n_keep, v + m->sum_act_out)) + m->max_act_out
+             : g.n_append > 0 ? v + g.n_append * m->n_act_layers : v + m->sum_act_out;
     g.kcap = round_up(std::max(g.kcap, 4), 4);   // keeps the aff matrix 16-byte aligned behind mags/rank
     g.W = round_up(m->maxw_pad, 8);
     g.label = label; g.lower = lower; g.upper = upper; g.near_tie = tie;
@@ -612,7 +620,7 @@ static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg
 
 static int check_cfg(const niq_mode_cfg* cfg) {
     if (!cfg) return fail(NIQ_EINVAL, "mode cfg is NULL");
-    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_AFFINE_ALL) return fail(NIQ_EINVAL, "invalid mode");
+    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_AFFINE_APPEND) return fail(NIQ_EINVAL, "invalid mode");
     if (cfg->mode == NIQ_MODE_AFFINE_TRUNCATE && cfg->truncate_policy != 0)
         return fail(NIQ_EUNSUPPORTED, "truncate policy 'relative' is not supported (reference src/affine.py:146 broadcasts (k,)/(w,))");
     return NIQ_OK;

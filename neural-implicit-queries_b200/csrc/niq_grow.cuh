@@ -19,8 +19,9 @@ struct GrowArgs {
     BoxSource src;
     long long n;
     float offset;
-    int truncate;          // 1: affine_truncate, 0: affine_all
+    int truncate;          // 1: affine_truncate, 0: affine_all / affine_append
     int n_keep;
+    int n_append;          // > 0: affine_append (reference src/affine.py:183-191)
     int kcap;              // row capacity of the aff matrix
     int W;                 // padded row width (max out_pad / in_pad over layers, multiple of 8)
     int* label; float* lower; float* upper; unsigned char* near_tie;
@@ -50,6 +51,7 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
     float* aff = reinterpret_cast<float*>(rank + g.kcap); // [kcap][W]
     float* tmp = aff + (size_t)g.kcap * W;               // [kcap][W] (truncate only): the truncated state is built here, then the two swap
     __shared__ float s_fin[3];
+    __shared__ float s_rest;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -194,6 +196,49 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                         delta[c] = de;
                     }
                     __syncthreads();
+                    if (g.n_append > 0) {
+                        // ---- affine_append (reference src/affine.py:183-191): scale the rows; the n_append largest
+                        // deltas (jax.lax.top_k: descending, lower index first among equals) become single-entry rows;
+                        // err += sum(delta) - sum(kept), ONE scalar on every neuron, as the reference writes it ----
+                        const int na = g.n_append, w = L.out_dim;
+                        int* drank = reinterpret_cast<int*>(red);          // [w] ranks of the deltas (red's partials are consumed)
+                        for (int r = warp; r < k; r += 8) {
+                            float* row = aff + (size_t)r * W;
+                            for (int c = lane; c < N; c += 32) row[c] = alpha[c] * row[c];
+                        }
+                        if (tid < w) {
+                            const float d = delta[tid];
+                            int rk = 0;
+                            for (int q = 0; q < w; ++q) { const float dq = delta[q]; rk += (dq > d) || (dq == d && q < tid); }
+                            drank[tid] = rk;
+                            if (rk < na) mags[rk] = d;
+                        }
+                        for (int idx = tid; idx < na * N; idx += blockDim.x) aff[(size_t)k * W + (idx / N) * W + (idx % N)] = 0.f;
+                        __syncthreads();
+                        if (tid < w && drank[tid] < na) aff[(size_t)(k + drank[tid]) * W + tid] = delta[tid];
+                        if (warp == 0) {
+                            // np.sum order of the oracle (8 strided accumulators, pairwise, sequential remainder) for sum(delta);
+                            // the kept values are summed in rank order
+                            const int w8 = w & ~7;
+                            float s = 0.f;
+                            if (lane < 8)
+                                for (int c = lane; c < w8; c += 8) s += delta[c];
+                            s += __shfl_xor_sync(0xffffffffu, s, 1);
+                            s += __shfl_xor_sync(0xffffffffu, s, 2);
+                            s += __shfl_xor_sync(0xffffffffu, s, 4);
+                            if (lane == 0) {
+                                for (int c = w8; c < w; ++c) s += delta[c];
+                                float kp = 0.f;
+                                for (int r = 0; r < na; ++r) kp += mags[r];
+                                s_rest = s - kp;
+                            }
+                        }
+                        __syncthreads();
+                        if (tid < w) e_cur[tid] = e_cur[tid] + s_rest;
+                        k += na;
+                        __syncthreads();
+                        continue;
+                    }
                     // -- scale rows by alpha (one warp per row: also yields the row's L1 norm), append diag(delta) --
                     const bool trunc = g.truncate && k + L.out_dim > g.n_keep;
                     for (int r = warp; r < k; r += 8) {

@@ -1,4 +1,4 @@
-"""Mirrors /root/reference/src/implicit_mlp_utils.py:12-64 for the modes of the hot path."""
+"""Mirrors /root/reference/src/implicit_mlp_utils.py:12-64 for the affine-family modes (the hot path + affine_append)."""
 import _niq
 import affine
 import mlp
@@ -23,10 +23,12 @@ def generate_implicit_from_params(params, mode, **kwargs):
                                    truncate_policy=kwargs["affine_truncate_policy"])
     elif mode == "affine_all":
         ctx = affine.AffineContext("affine_all")
-    elif mode in ("sdf", "affine_append", "slope_interval"):
+    elif mode == "affine_append":
+        ctx = affine.AffineContext("affine_append", n_append=kwargs["affine_n_append"])
+    elif mode in ("sdf", "slope_interval"):
         raise _niq.NiqError(_niq.NIQ_EUNSUPPORTED,
                             f"mode '{mode}' exists in the reference but is outside this backend's hot path "
-                            "(interval, affine_fixed, affine_truncate, affine_all)")
+                            "(interval, affine_fixed, affine_truncate, affine_all, affine_append)")
     else:
         raise RuntimeError("unrecognized mode")
     return affine.AffineImplicitFunction(mlp.func_from_spec(mode="affine"), ctx)

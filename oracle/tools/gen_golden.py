@@ -46,6 +46,8 @@ def _load(m, name, mode, **kw):
 def _mode_kwargs(mode, n_trunc):
     if mode == "affine_truncate":
         return dict(affine_n_truncate=n_trunc, affine_truncate_policy="absolute")
+    if mode == "affine_append":
+        return dict(affine_n_append=n_trunc)
     return {}
 
 
@@ -231,6 +233,9 @@ for _n in SAMPLES:
     for _mode in ("interval", "affine_fixed", "affine_truncate", "affine_all"):
         CASES[f"classify_{_n}_{_mode}"] = (case_classify, (_n, _mode))
 CASES["classify_hammer_affine_truncate64"] = (case_classify, ("hammer", "affine_truncate", 64))
+for _n in SAMPLES:                                   # the affine_append bounder (n_append = 4)
+    CASES[f"classify_{_n}_affine_append"] = (case_classify, (_n, "affine_append", 4))
+CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))
 CASES["rays_fox_interval_r6"] = (case_cast_rays, (("fox",), "interval", 6))
 CASES["rays_fox_all_r6"] = (case_cast_rays, (("fox",), "affine_all", 6))

@@ -23,10 +23,14 @@ HI = np.full(3, 1, np.float32)
 def make(params, mode, n_trunc=8):
     import implicit_mlp_utils
     kw = dict(affine_n_truncate=int(n_trunc), affine_truncate_policy="absolute") if mode == "affine_truncate" else {}
+    if mode == "affine_append":
+        kw = dict(affine_n_append=int(n_trunc))
     return implicit_mlp_utils.generate_implicit_from_params(params, mode, **kw)
 
 
 def octx(mode, n_trunc=8):
+    if mode == "affine_append":
+        return net.AffineContext(mode, n_append=int(n_trunc))
     return net.AffineContext(mode, truncate_count=int(n_trunc))
 
 
@@ -110,6 +114,55 @@ def test_classify_golden(name, mode):
     check_labels(lab, g["xf_label"], g["xf_lower"], g["xf_upper"], sc, rel=rel)
     f = func(p2, g["xf_points"])
     assert np.all(np.abs(f - g["xf_values"]) <= RTOL * rays.point_scale(op2, g["xf_points"]))
+
+
+APPEND_N = 4
+
+
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_append_golden_and_oracle(name):
+    """the affine_append bounder (src/affine.py:183-191) against the golden vectors of the unmodified
+    reference and against the oracle on random boxes.  Tolerance net.mode_rel (10x the hot-path band: the reference's
+    `err + (sum(delta) - sum(kept))` cancels catastrophically; the oracle itself only matches the reference run to
+    2e-5 / 4e-4 relative, tests/test_oracle_golden.py).  Soundness is checked exactly like the other modes."""
+    import mlp
+    p = sample_params(name)
+    ctx = octx("affine_append", APPEND_N)
+    rel = net.mode_rel(p, ctx)
+    func = make(p, "affine_append", APPEND_N)
+    g = golden(f"classify_{name}_affine_append")
+    _, _, _, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, g["box_lower"], g["box_upper"])
+    check_bounds(lo, up, g["lower"], g["upper"], sc, rel)
+    check_labels(lab, g["label"], g["lower"], g["upper"], sc, rel=rel)
+    _, _, _, sc = net.classify_general_box(p, ctx, g["seg_center"], g["seg_vecs"], return_scale=True)
+    lab, lo, up, tie = func.bound_general_box(p, g["seg_center"], g["seg_vecs"])
+    check_bounds(lo, up, g["seg_lower"], g["seg_upper"], sc, rel)
+    check_labels(lab, g["seg_label"], g["seg_lower"], g["seg_upper"], sc, rel=rel)
+    # random boxes: held to the float64 value of the same formulas, and statistically no further from it than the
+    # float32 oracle is (the yardstick of an ill-conditioned formula, like the elu case of test_classify_synthetic_widths)
+    lo_b, hi_b = random_boxes(13, 1200)
+    olab, olo, oup, sc = net.classify_box(p, ctx, lo_b, hi_b, return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, lo_b, hi_b)
+    check_bounds(lo, up, olo, oup, sc, rel)
+    with net.precision(np.float64):
+        _, lo6, up6, sc6 = net.classify_box(p, ctx, lo_b, hi_b, return_scale=True)
+    s6 = net.tol_scale(lo6, up6, sc6)
+    e_gpu = np.maximum(np.abs(lo - lo6), np.abs(up - up6)) / s6
+    e_o32 = np.maximum(np.abs(olo - lo6), np.abs(oup - up6)) / s6
+    for q in (50, 90, 99, 100):
+        assert np.percentile(e_gpu, q) <= 6 * np.percentile(e_o32, q) + 1e-5, f"P{q}: gpu {np.percentile(e_gpu, q):.2e} oracle {np.percentile(e_o32, q):.2e}"
+    assert check_labels(lab, olab, olo, oup, sc, rel=rel) < 0.1 * 1200
+    # soundness
+    rng = np.random.default_rng(2)
+    u = rng.uniform(0, 1, (1200, 8, 3)).astype(np.float32)
+    x = lo_b[:, None, :] + u * (hi_b - lo_b)[:, None, :]
+    f = mlp.eval_points(p, x)
+    slack = 1e-5 * np.maximum(np.abs(lo), np.abs(up))[:, None] + 1e-6
+    assert np.all(f >= lo[:, None] - slack) and np.all(f <= up[:, None] + slack)
+    # argument checking: jax.lax.top_k needs k <= width
+    with pytest.raises(ValueError):
+        make(p, "affine_append", 1000).classify_box(p, LO, HI)
 
 
 def test_classify_truncate64_golden():
@@ -450,6 +503,7 @@ TREE_CASES = {
     "tree_fox_fixed_d12": ("fox", "affine_fixed"),
     "tree_bunny_all_d9": ("bunny", "affine_all"),
     "tree_fox_trunc_d9": ("fox", "affine_truncate"),
+    "tree_fox_append_d9": ("fox", "affine_append"),
     "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
     "tree_fox_fixed_b128": ("fox", "affine_fixed"),
 }

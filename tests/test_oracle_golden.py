@@ -12,17 +12,19 @@ from niq_oracle import net, rays, tree
 
 RTOL = 1e-5
 SAMPLES = ("fox", "bunny", "hammer", "birdcage_occ")
-MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all")
+MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all", "affine_append")
 
 
 def ctx_for(mode, n_trunc):
+    if mode == "affine_append":            # the golden files store the count under the same key
+        return net.AffineContext(mode, n_append=int(n_trunc))
     return net.AffineContext(mode, truncate_count=int(n_trunc))
 
 
-def assert_bounds_close(lo, up, glo, gup, sc):
+def assert_bounds_close(lo, up, glo, gup, sc, rtol=RTOL):
     scale = net.tol_scale(glo, gup, sc)
-    assert np.all(np.abs(lo.astype(np.float64) - glo) <= RTOL * scale + 1e-30)
-    assert np.all(np.abs(up.astype(np.float64) - gup) <= RTOL * scale + 1e-30)
+    assert np.all(np.abs(lo.astype(np.float64) - glo) <= rtol * scale + 1e-30)
+    assert np.all(np.abs(up.astype(np.float64) - gup) <= rtol * scale + 1e-30)
 
 
 def assert_labels(lab, glab, lo, up, sc, offset=0.0):
@@ -45,21 +47,42 @@ def test_classify(name, mode):
     g = golden(f"classify_{name}_{mode}")
     p = sample_params(name)
     ctx = ctx_for(mode, g["n_trunc"])
+    rtol = net.mode_rel(p, ctx) if mode == "affine_append" else RTOL      # see net.mode_rel: ill-conditioned reference formula
     lab, lo, up, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
-    assert_bounds_close(lo, up, g["lower"], g["upper"], sc)
+    assert_bounds_close(lo, up, g["lower"], g["upper"], sc, rtol)
     assert_labels(lab, g["label"], lo, up, sc)
     assert_labels(net.labels_from_bounds(lo, up, 0.05), g["label_offset005"], lo, up, sc, 0.05)
     # ray segments (v = 1)
     lab, lo, up, sc = net.classify_general_box(p, ctx, g["seg_center"], g["seg_vecs"], return_scale=True)
-    assert_bounds_close(lo, up, g["seg_lower"], g["seg_upper"], sc)
+    assert_bounds_close(lo, up, g["seg_lower"], g["seg_upper"], sc, rtol)
     assert_labels(lab, g["seg_label"], lo, up, sc)
     # rigid transform prepended
     p2 = net.prepend_op(p, net.spatial_transformation(g["xf_R"], g["xf_t"]))
     lab, lo, up, sc = net.classify_box(p2, ctx, g["box_lower"][9:18], g["box_upper"][9:18], return_scale=True)
-    assert_bounds_close(lo, up, g["xf_lower"], g["xf_upper"], sc)
+    assert_bounds_close(lo, up, g["xf_lower"], g["xf_upper"], sc, rtol)
     assert_labels(lab, g["xf_label"], lo, up, sc)
     f = net.eval_points(p2, g["xf_points"])
     assert np.all(np.abs(f - g["xf_values"]) <= RTOL * rays.point_scale(p2, g["xf_points"]))
+
+
+def test_append_is_ill_conditioned_in_float32():
+    """Evidence for net.mode_rel: float32 vs float64 evaluation of the oracle's own formulas.  affine_append loses
+    1.5-2.5 more digits than affine_fixed (the reference's `sum(delta) - sum(kept)` cancellation, src/affine.py:191)."""
+    rng = np.random.default_rng(13)
+    n = 600
+    c = rng.uniform(-1, 1, (n, 3)).astype(np.float32)
+    h = (2.0 ** rng.uniform(-9, 0, (n, 1)) * rng.uniform(0.5, 1.0, (n, 3))).astype(np.float32)
+    for name in ("fox", "birdcage_occ"):
+        p = sample_params(name)
+        worst = {}
+        for mode, kw in (("affine_append", dict(n_append=4)), ("affine_fixed", {})):
+            ctx = net.AffineContext(mode, **kw)
+            _, lo, up, _ = net.classify_box(p, ctx, c - h, c + h, return_scale=True)
+            with net.precision(np.float64):
+                _, lo6, up6, sc6 = net.classify_box(p, ctx, c - h, c + h, return_scale=True)
+            s = net.tol_scale(lo6, up6, sc6)
+            worst[mode] = float(np.max(np.maximum(np.abs(lo - lo6), np.abs(up - up6)) / s))
+        assert worst["affine_fixed"] < 1e-5 < 10 * worst["affine_fixed"] < worst["affine_append"] < net.mode_rel(p, net.AffineContext("affine_append", n_append=4))
 
 
 def test_classify_truncate64():
@@ -107,6 +130,7 @@ TREE_CASES = {
     "tree_fox_fixed_d12": ("fox", "affine_fixed"),
     "tree_bunny_all_d9": ("bunny", "affine_all"),
     "tree_fox_trunc_d9": ("fox", "affine_truncate"),
+    "tree_fox_append_d9": ("fox", "affine_append"),
     "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
     "tree_fox_fixed_b128": ("fox", "affine_fixed"),
 }
