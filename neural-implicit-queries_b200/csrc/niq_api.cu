@@ -1370,13 +1370,62 @@ extern "C" int niq_closest_point(niq_ctx* c, const niq_mlp* m, const niq_mode_cf
     }
     const float eps_w = eps / sqrtf(3.0f);                 // reference :689
     unsigned long long round = 0;
+    // Windowed regime with a window of <= 2048 entries (the reference's default): one round = classify + 7-sample
+    // evaluation + ONE fused single-CTA kernel, captured once into a CUDA graph and replayed (the launch-bound inner
+    // loop of the query); buffers of the graph live for the whole call.
+    const bool small_window = Bw <= 2 * kCpSmallThreads;
+    DevBuf g_label(c), g_tie(c), g_vals(c);
+    cudaGraphExec_t cp_exec = nullptr;
+    struct GraphGuard { cudaGraphExec_t* e; ~GraphGuard() { if (*e) cudaGraphExecDestroy(*e); } } gg{&cp_exec};
+    const float* graph_stack = nullptr;
+    if (small_window) { TRY(g_label.alloc(Bw * 4)); TRY(g_tie.alloc(Bw)); TRY(g_vals.alloc(Bw * 28)); }
     while (true) {
         // ub <= B: the window covers the whole stack (per-query level-synchronous regime) -> poll every round so
         // the launch size tracks the stack; ub > B: steady windows of exactly B entries -> poll every kPoll rounds.
         const bool level_regime = ub <= Bw;
-        const int rounds = level_regime ? 1 : kPoll;
+        const bool fused = !level_regime && small_window;
+        const int rounds = level_regime ? 1 : (fused ? 4 * kPoll : kPoll);
         const long long W = std::min<long long>(Bw, std::max<long long>(ub, 1));
         TRY(reserve(ub + (rounds + 2) * W + 16, ub));
+        if (fused) {
+            if (cp_exec == nullptr || graph_stack != s_lo) {
+                if (cp_exec) { cudaGraphExecDestroy(cp_exec); cp_exec = nullptr; }
+                const bool timing = c->timing;
+                c->timing = false;
+                const long long launches0 = c->launches;
+                CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+                BoxSource bs{};
+                bs.kind = 2; bs.v = 3; bs.a = s_lo; bs.b = s_hi; bs.top = d_top.as<long long>(); bs.window = W;
+                int rc = classify_dev(c, m, cfg, bs, W, 0.f, g_label.as<int>(), nullptr, nullptr, g_tie.as<unsigned char>());
+                PointSource ps{};
+                ps.kind = 2; ps.a = s_lo; ps.b = s_hi; ps.sample_scale = -1.f; ps.top = d_top.as<long long>(); ps.window = W;
+                if (rc == NIQ_OK) rc = launch_eval_points(c, m, ps, 7 * W, g_vals.as<float>(), nullptr);
+                CpRound r{};
+                r.stack_lo = s_lo; r.stack_hi = s_hi; r.stack_qid = s_id; r.top = d_top.as<long long>(); r.window = W;
+                r.query = dq.as<float>(); r.min_dist = dd.as<float>(); r.min_loc = dl.as<float>(); r.winner = d_winner.as<unsigned long long>();
+                r.n_query = q; r.label = g_label.as<int>(); r.tie = g_tie.as<unsigned char>(); r.vals = g_vals.as<float>(); r.eps_w = eps_w;
+                r.stats = d_stats.as<long long>();
+                k_cp_round_small<<<1, kCpSmallThreads, 0, c->stream>>>(r, s_lo, s_hi, s_id, d_maxtop.as<long long>());
+                cudaGraph_t graph = nullptr;
+                const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+                c->timing = timing;
+                c->launches = launches0;
+                if (rc != NIQ_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                if (ce != cudaSuccess) return fail(NIQ_ECUDA, "closest_point: graph capture failed: %s", cudaGetErrorString(ce));
+                const cudaError_t ie = cudaGraphInstantiate(&cp_exec, graph, 0);
+                cudaGraphDestroy(graph);
+                if (ie != cudaSuccess) { cp_exec = nullptr; return fail(NIQ_ECUDA, "closest_point: graph instantiation failed: %s", cudaGetErrorString(ie)); }
+                graph_stack = s_lo;
+            }
+            // the fused kernel keeps the round number on the device (winner tags must keep growing across regimes)
+            CU(cudaMemcpyAsync(d_stats.as<long long>() + 3, &round, 8, cudaMemcpyHostToDevice, c->stream));
+            for (int it = 0; it < rounds; ++it) CU(cudaGraphLaunch(cp_exec, c->stream));
+            c->launches += 3ll * rounds;
+            round += (unsigned long long)rounds;
+            TRY(read_back(c, d_top.p, 8, &ub));
+            if (ub <= 0) break;
+            continue;
+        }
         DevBuf label(c), tie(c), vals(c), this_d(c), cen(c), needs(c), scan(c), t_lo(c), t_hi(c), t_id(c);
         TRY(label.alloc(W * 4)); TRY(tie.alloc(W)); TRY(vals.alloc(W * 28)); TRY(this_d.alloc(W * 4)); TRY(cen.alloc(W * 12));
         TRY(needs.alloc(W * 4)); TRY(scan.alloc((W + 1) * 4)); TRY(t_lo.alloc(W * 12)); TRY(t_hi.alloc(W * 12)); TRY(t_id.alloc(W * 8));

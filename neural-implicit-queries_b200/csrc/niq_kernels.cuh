@@ -706,6 +706,125 @@ __global__ void k_cp_advance(CpRound r, const int* scan, long long* max_top) {
     if (top > 0 && r.stats) r.stats[0] += 1;             // rounds that did work
 }
 
+// The whole round in ONE CTA for windows of <= 2048 entries (the reference's default batch_process_size): the phases of
+// k_cp_eval / _min / _winner / _loc / scan / _push / _advance separated by __syncthreads instead of kernel boundaries.
+// Thread t owns window entries 2t and 2t+1 (consecutive, so the block scan yields the reference's child order); their
+// stack rows are read into registers before anything is written, which replaces the copy of the window.  The round
+// number lives on the device (stats[3]) so that the launch can be replayed from a CUDA graph.
+constexpr int kCpSmallThreads = 1024;
+__global__ void __launch_bounds__(kCpSmallThreads) k_cp_round_small(CpRound r, float* stack_lo, float* stack_hi,
+                                                                     long long* stack_qid, long long* max_top) {
+    __shared__ int warp_sums[kCpSmallThreads / 32];
+    __shared__ int s_total;
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long top = *r.top;
+    const long long pop = top - r.window > 0 ? top - r.window : 0;
+    const unsigned long long round = (unsigned long long)r.stats[3];
+    const float INF = __int_as_float(0x7f800000);
+    float l[2][3], h[2][3], dist[2], cen[2][3];
+    long long qid[2];
+    bool valid[2], need[2];
+    int n_valid = 0, n_tie = 0;
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        const long long i = 2ll * tid + e;
+        valid[e] = i < r.window && i < top;                   // reference :685 (arange(B) < stack_top)
+        need[e] = false; dist[e] = INF; qid[e] = 0;
+        for (int d = 0; d < 3; ++d) { l[e][d] = h[e][d] = cen[e][d] = 0.f; }
+        if (i < r.window) {
+            const long long sidx = pop + i;
+            for (int d = 0; d < 3; ++d) { l[e][d] = r.stack_lo[3 * sidx + d]; h[e][d] = r.stack_hi[3 * sidx + d]; }
+            long long q = r.stack_qid[sidx];
+            if (!valid[e] || q < 0 || q >= r.n_query) q = 0;  // stale entries: keep gathers in range
+            qid[e] = q;
+            const float* qp = r.query + 3 * q;
+            const float ex = h[e][0] - l[e][0], ey = h[e][1] - l[e][1], ez = h[e][2] - l[e][2];
+            const float width = fmaxf(fmaxf(ex, ey), ez);
+            for (int d = 0; d < 3; ++d) cen[e][d] = 0.5f * (l[e][d] + h[e][d]);
+            const float off = sqrtf((ex * ex + ey * ey) + ez * ez);
+            const float qx = qp[0] - cen[e][0], qy = qp[1] - cen[e][1], qz = qp[2] - cen[e][2];
+            const float dc = sqrtf((qx * qx + qy * qy) + qz * qz);
+            const bool small = width < r.eps_w;
+            const int lab = r.label[i];
+            const bool outside = lab == SIGN_NEGATIVE || lab == SIGN_POSITIVE;
+            const bool spans = !all_same_sign7(r.vals + 7 * i) && valid[e];
+            const float snap = r.min_dist[q];                 // snapshot before this round's scatter-min (:684)
+            dist[e] = spans ? dc + off : INF;
+            need[e] = valid[e] && !outside && !small && dc < snap;
+            if (valid[e]) { n_valid += 1; n_tie += (r.tie && r.tie[i]) ? 1 : 0; }
+        }
+    }
+    __syncthreads();                                          // every snapshot is taken before any scatter-min
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        if (valid[e]) atomicMin(reinterpret_cast<int*>(r.min_dist + qid[e]), __float_as_int(dist[e]));   // dist >= 0
+    __threadfence();
+    __syncthreads();
+    const unsigned long long tag0 = (round << 32);
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        if (valid[e] && dist[e] == *reinterpret_cast<volatile float*>(r.min_dist + qid[e]))
+            atomicMax(&r.winner[qid[e]], tag0 | (unsigned long long)(2ll * tid + e + 1));
+    __threadfence();
+    __syncthreads();
+#pragma unroll
+    for (int e = 0; e < 2; ++e)
+        if (valid[e] && dist[e] == *reinterpret_cast<volatile float*>(r.min_dist + qid[e]) &&
+            *reinterpret_cast<volatile unsigned long long*>(&r.winner[qid[e]]) == (tag0 | (unsigned long long)(2ll * tid + e + 1)))
+            for (int d = 0; d < 3; ++d) r.min_loc[3 * qid[e] + d] = cen[e][d];
+    // exclusive scan of the survivors, in window order
+    const int mine = (need[0] ? 1 : 0) + (need[1] ? 1 : 0);
+    int x = mine;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, off); if (lane >= off) x += y; }
+    if (lane == 31) warp_sums[w] = x;
+    __syncthreads();
+    if (w == 0) {
+        int sv = warp_sums[lane];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int y = __shfl_up_sync(0xffffffffu, sv, off); if (lane >= off) sv += y; }
+        warp_sums[lane] = sv;
+        if (lane == 31) s_total = sv;
+    }
+    __syncthreads();
+    int rank = (w > 0 ? warp_sums[w - 1] : 0) + x - mine;
+    // children of the survivors go back on the stack at pop + 2*rank, interleaved [A, B] (reference :732-754)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+        if (need[e]) {
+            const long long oa = pop + 2ll * rank, ob = oa + 1;
+            const int sd = argmax3_first(h[e][0] - l[e][0], h[e][1] - l[e][1], h[e][2] - l[e][2]);
+            for (int d = 0; d < 3; ++d) {
+                const float mid = 0.5f * (l[e][d] + h[e][d]);
+                stack_lo[3 * oa + d] = l[e][d];
+                stack_hi[3 * oa + d] = d == sd ? mid : h[e][d];
+                stack_lo[3 * ob + d] = d == sd ? mid : l[e][d];
+                stack_hi[3 * ob + d] = h[e][d];
+            }
+            stack_qid[oa] = qid[e];
+            stack_qid[ob] = qid[e];
+            rank += 1;
+        }
+    }
+    // statistics (warp-aggregated) and the new stack top
+    {
+        int nv = n_valid, nt = n_tie;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) { nv += __shfl_xor_sync(0xffffffffu, nv, off); nt += __shfl_xor_sync(0xffffffffu, nt, off); }
+        if (lane == 0 && r.stats) {
+            if (nv) atomicAdd((unsigned long long*)&r.stats[1], (unsigned long long)nv);
+            if (nt) atomicAdd((unsigned long long*)&r.stats[2], (unsigned long long)nt);
+        }
+    }
+    if (tid == 0) {
+        const long long nt2 = pop + 2ll * s_total;
+        *r.top = nt2;
+        if (nt2 > *max_top) *max_top = nt2;
+        if (top > 0) r.stats[0] += 1;                         // rounds that did work
+        r.stats[3] += 1;                                      // round number (winner tags)
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // marching cubes over leaves (reference src/extract_cell.py:314-421, src/kd_tree.py:338-355)
 // ------------------------------------------------------------------------------------------------
