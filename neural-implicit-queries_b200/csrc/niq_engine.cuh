@@ -188,8 +188,12 @@ __device__ __forceinline__ void relu_lin(float l, float u, float& alpha, float& 
 
 // elu linearisation on [l,u]  (reference src/affine_layers.py:59-97)
 __device__ __forceinline__ void elu_lin(float l, float u, float& alpha, float& beta, float& delta) {
-    const float lF = elu_f(l), uF = elu_f(u);
-    const float lS = fminf(expf(l), 1.f), uS = fminf(expf(u), 1.f);
+    // One expm1 per endpoint serves both elu(x) = x > 0 ? x : expm1(x) and the slope min(exp(x), 1): for x < 0
+    // exp(x) = expm1(x) + 1 (within 1 ulp of 1, i.e. <= 1.2e-7 ABSOLUTE of a bound that only clips alpha), for x >= 0
+    // the min is 1.  Saves the two expf of the reference formulation; everything else is as written there.
+    const float ml = expm1f(fminf(l, 0.f)), mu = expm1f(fminf(u, 0.f));
+    const float lF = l > 0.f ? l : ml, uF = u > 0.f ? u : mu;
+    const float lS = ml + 1.f, uS = mu + 1.f;
     float a = (uF - lF) / (u - l);
     if (l >= 0.f) a = 1.f;
     if (a != a) a = 0.f;
