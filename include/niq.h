@@ -64,13 +64,15 @@ typedef enum niq_mode {
     NIQ_MODE_AFFINE_FIXED = 1,
     NIQ_MODE_AFFINE_TRUNCATE = 2,
     NIQ_MODE_AFFINE_ALL = 3,
-    NIQ_MODE_AFFINE_APPEND = 4   /* src/affine.py:183-191: per activation keep the n_append largest deltas as new terms */
+    NIQ_MODE_AFFINE_APPEND = 4,  /* src/affine.py:183-191: per activation keep the n_append largest deltas as new terms */
+    NIQ_MODE_SDF = 5             /* src/sdf.py:17-50 WeakSDFImplicitFunction: f(centre) against lipschitz * box radius */
 } niq_mode;
 
 typedef struct niq_mode_cfg {
     int32_t mode;            /* niq_mode */
     int32_t truncate_count;  /* affine_truncate: rows kept (src/affine.py:133); affine_append: n_append; else ignored */
     int32_t truncate_policy; /* 0 = 'absolute' (only policy supported; 'relative' -> NIQ_EUNSUPPORTED) */
+    float sdf_lipschitz;     /* NIQ_MODE_SDF: the Lipschitz bound of src/sdf.py:19 (kwarg sdf_lipschitz); else ignored */
 } niq_mode_cfg;
 
 /* opts of src/queries.py:23-36 that cast_rays reads */

@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("NIQ_LIB") or os.path.join(_HERE, "libniq.so")   # NIQ
 NIQ_OK, NIQ_EINVAL, NIQ_ENOMEM, NIQ_ECUDA, NIQ_ECAPACITY, NIQ_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
 OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL = 0, 1, 2, 3, 4
-MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4}
+MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4, "sdf": 5}
 TREE_INTERIOR, TREE_EXTERIOR = 1, 2
 
 # every symbol include/niq.h declares (tests check the library exports all of them)
@@ -42,7 +42,8 @@ class OpDesc(C.Structure):
 
 
 class ModeCfg(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("truncate_count", C.c_int32), ("truncate_policy", C.c_int32)]
+    _fields_ = [("mode", C.c_int32), ("truncate_count", C.c_int32), ("truncate_policy", C.c_int32),
+                ("sdf_lipschitz", C.c_float)]
 
 
 class CastOpts(C.Structure):
@@ -285,6 +286,8 @@ def mode_cfg(ctx):
     cfg.truncate_count = int(ctx.truncate_count) if ctx.mode == "affine_truncate" else 0
     if ctx.mode == "affine_append":
         cfg.truncate_count = int(ctx.n_append)
+    if ctx.mode == "sdf":
+        cfg.sdf_lipschitz = float(ctx.lipschitz_bound)
     if ctx.mode == "affine_truncate" and ctx.truncate_policy != "absolute":
         if ctx.truncate_policy == "relative":
             cfg.truncate_policy = 1      # the library answers NIQ_EUNSUPPORTED with the reason

@@ -620,7 +620,8 @@ static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg
 
 static int check_cfg(const niq_mode_cfg* cfg) {
     if (!cfg) return fail(NIQ_EINVAL, "mode cfg is NULL");
-    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_AFFINE_APPEND) return fail(NIQ_EINVAL, "invalid mode");
+    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_SDF) return fail(NIQ_EINVAL, "invalid mode");
+    if (cfg->mode == NIQ_MODE_SDF && !(cfg->sdf_lipschitz >= 0.f)) return fail(NIQ_EINVAL, "sdf mode: lipschitz bound must be >= 0");
     if (cfg->mode == NIQ_MODE_AFFINE_TRUNCATE && cfg->truncate_policy != 0)
         return fail(NIQ_EUNSUPPORTED, "truncate policy 'relative' is not supported (reference src/affine.py:146 broadcasts (k,)/(w,))");
     return NIQ_OK;
@@ -635,6 +636,20 @@ static int classify_dev(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, B
         return launch_classify_fixed(c, m, src, n, offset, label, lower, upper, tie);
     }
     src.interval = 0;
+    if (cfg->mode == NIQ_MODE_SDF) {
+        // reference src/sdf.py:31-50: one point evaluation at the box centre, then the Lipschitz test
+        if (n <= 0) return NIQ_OK;
+        DevBuf vals(c), scl(c);
+        TRY(vals.alloc((size_t)n * 4)); TRY(scl.alloc((size_t)n * 4));
+        PointSource ps{};
+        ps.kind = 3; ps.box_kind = src.kind; ps.a = src.a; ps.b = src.b; ps.top = src.top; ps.window = src.window;
+        TRY(launch_eval_points(c, m, ps, n, vals.as<float>(), scl.as<float>()));
+        LaunchTimer lt(c, 1);
+        k_sdf_labels<<<(int)((n + 255) / 256), 256, 0, c->stream>>>(src, n, vals.as<float>(), scl.as<float>(), cfg->sdf_lipschitz, offset,
+                                                                     m->net.tie_rel, label, lower, upper, tie);
+        CU(cudaGetLastError());
+        return NIQ_OK;
+    }
     return launch_classify_grow(c, m, cfg, src, n, offset, label, lower, upper, tie);
 }
 

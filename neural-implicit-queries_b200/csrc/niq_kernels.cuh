@@ -24,7 +24,9 @@ struct BoxSource {
 };
 
 struct PointSource {
-    int kind;                 // 0: xyz (n,3); 1: MC lattice of leaves; 2: 7 samples per node (center +- s*e_i)
+    int kind;                 // 0: xyz (n,3); 1: MC lattice of leaves; 2: 7 samples per node (center +- s*e_i);
+                              // 3: box centres (a = centres when box_kind == 0, else lo/hi in a/b, optionally windowed)
+    int box_kind;             // kind 3: the BoxSource kind the centres come from
     const float* a;           // xyz | leaf lo | node lo
     const float* b;           //     | leaf hi | node hi
     int pts_per_side;         // kind 1: P = 2^n + 1
@@ -104,6 +106,15 @@ __device__ __forceinline__ float4 load_point(const PointSource& src, long long i
             }
         }
         return make_float4(xyz[0], xyz[1], xyz[2], 0.f);
+    } else if (src.kind == 3) {
+        if (src.box_kind == 0) {
+            const float* p = src.a + 3 * i;
+            return make_float4(p[0], p[1], p[2], 0.f);
+        }
+        const long long j = i + window_base(src.top, src.window);
+        const float* lo = src.a + 3 * j;
+        const float* hi = src.b + 3 * j;
+        return make_float4(0.5f * (lo[0] + hi[0]), 0.5f * (lo[1] + hi[1]), 0.5f * (lo[2] + hi[2]), 0.f);   // src/implicit_function.py:34
     } else {
         // reference src/kd_tree.py:461-464 (intersection) / :702-704 (closest point)
         const long long node = i / 7 + window_base(src.top, src.window);
@@ -178,6 +189,50 @@ k_classify_fixed(const __grid_constant__ NetDev net, const BoxSource src, long l
         __syncwarp();
     }
     eng.drain();
+}
+
+// ------------------------------------------------------------------------------------------------
+// sdf mode (reference src/sdf.py:31-50): label of a general box from f(centre) and lipschitz * radius, where
+// radius = sqrt(sum_v ||vec_v||^2).  vals / scale come from k_eval_points on the centres (PointSource kind 3).
+// lower / upper = f -+ lipschitz * radius (ours: the reference returns only the label).
+// ------------------------------------------------------------------------------------------------
+__global__ void k_sdf_labels(const BoxSource src, long long n, const float* __restrict__ vals,
+                             const float* __restrict__ scale, float lipschitz, float offset, float tie_rel,
+                             int* __restrict__ label, float* __restrict__ lower, float* __restrict__ upper,
+                             unsigned char* __restrict__ near_tie) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s2 = 0.f;
+    if (src.kind == 0) {
+        for (int k = 0; k < src.v; ++k) {
+            const float* p = src.b + (i * src.v + k) * 3;
+            const float nv = sqrtf((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);     // jnp.linalg.norm(box_vecs, axis=-1)
+            s2 = s2 + nv * nv;
+        }
+    } else {
+        const long long j = i + window_base(src.top, src.window);
+        const float* lo = src.a + 3 * j;
+        const float* hi = src.b + 3 * j;
+        for (int d = 0; d < 3; ++d) {
+            const float hv = hi[d] - 0.5f * (lo[d] + hi[d]);                        // diag(upper - centre)
+            const float nv = sqrtf((hv * hv + 0.f) + 0.f);
+            s2 = s2 + nv * nv;
+        }
+    }
+    const float rad = sqrtf(s2);
+    const float val = vals[i];
+    const float reach = rad * lipschitz;
+    const bool can_change = fabsf(val) - reach < 0.f;
+    int lab = SIGN_UNKNOWN;
+    if (!can_change && val > offset) lab = SIGN_POSITIVE;
+    if (!can_change && val < -offset) lab = SIGN_NEGATIVE;
+    if (label) label[i] = lab;
+    if (lower) lower[i] = val - reach;
+    if (upper) upper[i] = val + reach;
+    if (near_tie) {
+        const float band = tie_rel * (scale ? scale[i] : fabsf(val)) + tie_rel * reach;
+        near_tie[i] = (fabsf(fabsf(val) - reach) <= band || fabsf(val - offset) <= band || fabsf(val + offset) <= band) ? 1 : 0;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -25,10 +25,13 @@ def generate_implicit_from_params(params, mode, **kwargs):
         ctx = affine.AffineContext("affine_all")
     elif mode == "affine_append":
         ctx = affine.AffineContext("affine_append", n_append=kwargs["affine_n_append"])
-    elif mode in ("sdf", "slope_interval"):
+    elif mode == "sdf":
+        import sdf
+        return sdf.WeakSDFImplicitFunction(mlp.func_from_spec(mode="default"), lipschitz_bound=kwargs.get("sdf_lipschitz", 1.))
+    elif mode == "slope_interval":
         raise _niq.NiqError(_niq.NIQ_EUNSUPPORTED,
                             f"mode '{mode}' exists in the reference but is outside this backend's hot path "
-                            "(interval, affine_fixed, affine_truncate, affine_all, affine_append)")
+                            "(interval, affine_fixed, affine_truncate, affine_all, affine_append, sdf)")
     else:
         raise RuntimeError("unrecognized mode")
     return affine.AffineImplicitFunction(mlp.func_from_spec(mode="affine"), ctx)

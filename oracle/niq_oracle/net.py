@@ -186,9 +186,10 @@ class AffineContext:
     truncate_count: int = -777
     truncate_policy: str = "absolute"
     n_append: int = 0
+    sdf_lipschitz: float = 1.0          # mode "sdf" (ours: the reference keeps it on sdf.WeakSDFImplicitFunction)
 
     def __post_init__(self):
-        if self.mode not in ("interval", "affine_fixed", "affine_truncate", "affine_append", "affine_all"):
+        if self.mode not in ("interval", "affine_fixed", "affine_truncate", "affine_append", "affine_all", "sdf"):
             raise ValueError("invalid mode")
         if self.mode == "affine_truncate" and self.truncate_count is None:
             raise ValueError("must specify truncate count")
@@ -382,10 +383,28 @@ def affine_forward(params, ctx, center, vecs):
     return base, aff, err, scale
 
 
+def sdf_center_value_and_reach(params, ctx, center, vecs):
+    """sdf.py:31-43 (WeakSDFImplicitFunction.classify_general_box), batched: f(centre) and lipschitz * radius with
+    radius = sqrt(sum_v ||vec_v||^2)."""
+    center = np.ascontiguousarray(center, F32)
+    vecs = np.ascontiguousarray(vecs, F32)
+    nv = np.sqrt((vecs * vecs).sum(axis=-1, dtype=F32)).astype(F32)          # jnp.linalg.norm(box_vecs, axis=-1)
+    rad = np.sqrt((nv * nv).sum(axis=-1, dtype=F32)).astype(F32)
+    val = eval_points(params, center)
+    return val, (rad * F32(ctx.sdf_lipschitz)).astype(F32)
+
+
 def bound_general_box(params, ctx, center, vecs, chunk=None, return_scale=False):
     """-> (lower, upper[, scale]) float32 (N,): affine.py:119-125 applied to the propagated output."""
     center = np.ascontiguousarray(center, F32)
     vecs = np.ascontiguousarray(vecs, F32)
+    if ctx.mode == "sdf":
+        val, reach = sdf_center_value_and_reach(params, ctx, center, vecs)
+        lower, upper = (val - reach).astype(F32), (val + reach).astype(F32)
+        if return_scale:
+            from . import rays
+            return lower, upper, (rays.point_scale(params, center) + reach).astype(F32)
+        return lower, upper
     n = center.shape[0]
     if chunk is None:
         chunk = 65536 if ctx.mode in ("interval", "affine_fixed") else 1024
@@ -415,7 +434,15 @@ def labels_from_bounds(lower, upper, offset=0.0):
 def classify_general_box(params, ctx, center, vecs, offset=0.0, return_bounds=False, return_scale=False):
     """affine.py:34-55, batched over N boxes."""
     lower, upper, scale = bound_general_box(params, ctx, center, vecs, return_scale=True)
-    lab = labels_from_bounds(lower, upper, offset)
+    if ctx.mode == "sdf":
+        # sdf.py:42-48: the offset is tested on f(centre) itself, not on the bounds
+        val, reach = sdf_center_value_and_reach(params, ctx, center, vecs)
+        can_change = (np.abs(val) - reach) < 0
+        lab = np.full(val.shape, SIGN_UNKNOWN, np.int32)
+        lab = np.where(~can_change & (val > F32(offset)), SIGN_POSITIVE, lab)
+        lab = np.where(~can_change & (val < -F32(offset)), SIGN_NEGATIVE, lab).astype(np.int32)
+    else:
+        lab = labels_from_bounds(lower, upper, offset)
     if return_scale:
         return lab, lower, upper, scale
     return (lab, lower, upper) if return_bounds else lab

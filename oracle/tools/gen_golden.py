@@ -48,6 +48,8 @@ def _mode_kwargs(mode, n_trunc):
         return dict(affine_n_truncate=n_trunc, affine_truncate_policy="absolute")
     if mode == "affine_append":
         return dict(affine_n_append=n_trunc)
+    if mode == "sdf":
+        return dict(sdf_lipschitz=n_trunc)
     return {}
 
 
@@ -136,6 +138,25 @@ def case_classify(name, mode, n_trunc=8):
                xf_upper=np.array(tub, np.float32), xf_points=pts,
                xf_values=np.array([float(func(p2, jnp.array(x))) for x in pts], np.float32))
     return out
+
+
+def case_classify_sdf(name, lipschitz):
+    """sdf.WeakSDFImplicitFunction (src/sdf.py): labels of axis-aligned boxes (two offsets) and v=1 / v=2 general boxes."""
+    m = _ref_modules()
+    jnp = m["jnp"]
+    func, params = _load(m, name, "sdf", sdf_lipschitz=lipschitz)
+    import zlib
+    lo, hi = _boxes(seed=zlib.crc32(f"{name}-sdf".encode()) % 1000)
+    lab = [int(func.classify_box(params, jnp.array(lo[i]), jnp.array(hi[i]))) for i in range(lo.shape[0])]
+    lab_off = [int(func.classify_box(params, jnp.array(lo[i]), jnp.array(hi[i]), offset=0.05)) for i in range(lo.shape[0])]
+    rng = np.random.default_rng(7)
+    cen = rng.uniform(-1, 1, (16, 3)).astype(np.float32)
+    vec = (rng.standard_normal((16, 2, 3)) * (2.0 ** -rng.integers(2, 9, (16, 1, 1)))).astype(np.float32)
+    glab = [int(func.classify_general_box(params, jnp.array(cen[i]), jnp.array(vec[i]))) for i in range(16)]
+    glab1 = [int(func.classify_general_box(params, jnp.array(cen[i]), jnp.array(vec[i, :1]))) for i in range(16)]
+    return dict(box_lower=lo, box_upper=hi, lipschitz=np.float32(lipschitz), label=np.array(lab, np.int32),
+                label_offset005=np.array(lab_off, np.int32), gen_center=cen, gen_vecs=vec, gen_label=np.array(glab, np.int32),
+                gen_label_v1=np.array(glab1, np.int32))
 
 
 def case_points(name):
@@ -235,6 +256,9 @@ for _n in SAMPLES:
 CASES["classify_hammer_affine_truncate64"] = (case_classify, ("hammer", "affine_truncate", 64))
 for _n in SAMPLES:                                   # the affine_append bounder (n_append = 4)
     CASES[f"classify_{_n}_affine_append"] = (case_classify, (_n, "affine_append", 4))
+for _n, _L in (("fox", 1.0), ("bunny", 2.0), ("hammer", 1.5), ("birdcage_occ", 4.0)):   # the sdf bounder
+    CASES[f"classify_{_n}_sdf"] = (case_classify_sdf, (_n, _L))
+CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))
 CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))
 CASES["rays_fox_interval_r6"] = (case_cast_rays, (("fox",), "interval", 6))

@@ -25,10 +25,14 @@ def make(params, mode, n_trunc=8):
     kw = dict(affine_n_truncate=int(n_trunc), affine_truncate_policy="absolute") if mode == "affine_truncate" else {}
     if mode == "affine_append":
         kw = dict(affine_n_append=int(n_trunc))
+    if mode == "sdf":
+        kw = dict(sdf_lipschitz=float(n_trunc))
     return implicit_mlp_utils.generate_implicit_from_params(params, mode, **kw)
 
 
 def octx(mode, n_trunc=8):
+    if mode == "sdf":
+        return net.AffineContext(mode, sdf_lipschitz=float(n_trunc))
     if mode == "affine_append":
         return net.AffineContext(mode, n_append=int(n_trunc))
     return net.AffineContext(mode, truncate_count=int(n_trunc))
@@ -163,6 +167,43 @@ def test_classify_append_golden_and_oracle(name):
     # argument checking: jax.lax.top_k needs k <= width
     with pytest.raises(ValueError):
         make(p, "affine_append", 1000).classify_box(p, LO, HI)
+
+
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_sdf_golden_and_oracle(name):
+    """the sdf bounder (src/sdf.py:31-50: f(centre) against lipschitz * radius) against the labels of
+    the unmodified reference and against the oracle on random boxes; (lower, upper) = f -+ L*radius within 1e-5."""
+    p = sample_params(name)
+    g = golden(f"classify_{name}_sdf")
+    L = float(g["lipschitz"])
+    ctx = octx("sdf", L)
+    func = make(p, "sdf", L)
+
+    def check(lab, tie, glab, center, vecs, offset):
+        val, reach = net.sdf_center_value_and_reach(p, ctx, center, vecs)
+        band = RTOL * (rays.point_scale(p, center) + reach)
+        otie = (np.abs(np.abs(val) - reach) <= band) | (np.abs(val - offset) <= band) | (np.abs(val + offset) <= band)
+        assert np.all((lab == glab) | otie)
+        assert np.all((lab == glab) | tie)                 # the device flag covers every disagreement too
+
+    c, v = net.box_to_general(g["box_lower"], g["box_upper"])
+    lab, lo, up, tie = func.bound_box(p, g["box_lower"], g["box_upper"])
+    check(lab, tie, g["label"], c, v, 0.0)
+    lab5, _, _, tie5 = func.bound_box(p, g["box_lower"], g["box_upper"], offset=0.05)
+    check(lab5, tie5, g["label_offset005"], c, v, 0.05)
+    labg, _, _, tieg = func.bound_general_box(p, g["gen_center"], g["gen_vecs"])
+    check(labg, tieg, g["gen_label"], g["gen_center"], g["gen_vecs"], 0.0)
+    lab1, _, _, tie1 = func.bound_general_box(p, g["gen_center"], g["gen_vecs"][:, :1])
+    check(lab1, tie1, g["gen_label_v1"], g["gen_center"], g["gen_vecs"][:, :1], 0.0)
+    assert np.array_equal(func.classify_box(p, g["box_lower"], g["box_upper"]), lab)
+    # random boxes vs the oracle (labels + our bounds)
+    lo_b, hi_b = random_boxes(17, 5000)
+    c, v = net.box_to_general(lo_b, hi_b)
+    olab, olo, oup, sc = net.classify_box(p, ctx, lo_b, hi_b, return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, lo_b, hi_b)
+    check(lab, tie, olab, c, v, 0.0)
+    assert np.all(np.abs(lo - olo) <= RTOL * sc) and np.all(np.abs(up - oup) <= RTOL * sc)
+    assert tie.mean() < 0.01
 
 
 def test_classify_truncate64_golden():
@@ -504,6 +545,7 @@ TREE_CASES = {
     "tree_bunny_all_d9": ("bunny", "affine_all"),
     "tree_fox_trunc_d9": ("fox", "affine_truncate"),
     "tree_fox_append_d9": ("fox", "affine_append"),
+    "tree_fox_sdf_d12": ("fox", "sdf"),
     "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
     "tree_fox_fixed_b128": ("fox", "affine_fixed"),
 }

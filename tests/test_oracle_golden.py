@@ -16,6 +16,8 @@ MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all", "affine_ap
 
 
 def ctx_for(mode, n_trunc):
+    if mode == "sdf":                      # tree fixtures store the Lipschitz bound under the same key
+        return net.AffineContext(mode, sdf_lipschitz=float(n_trunc))
     if mode == "affine_append":            # the golden files store the count under the same key
         return net.AffineContext(mode, n_append=int(n_trunc))
     return net.AffineContext(mode, truncate_count=int(n_trunc))
@@ -85,6 +87,29 @@ def test_append_is_ill_conditioned_in_float32():
         assert worst["affine_fixed"] < 1e-5 < 10 * worst["affine_fixed"] < worst["affine_append"] < net.mode_rel(p, net.AffineContext("affine_append", n_append=4))
 
 
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_sdf(name):
+    """sdf.WeakSDFImplicitFunction (src/sdf.py:31-50).  Labels are exact unless |f(centre)| is within
+    the point-value band of lipschitz*radius or of the offset."""
+    g = golden(f"classify_{name}_sdf")
+    p = sample_params(name)
+    ctx = net.AffineContext("sdf", sdf_lipschitz=float(g["lipschitz"]))
+
+    def check(lab, glab, center, vecs, offset):
+        val, reach = net.sdf_center_value_and_reach(p, ctx, center, vecs)
+        band = RTOL * (rays.point_scale(p, center) + reach)
+        tie = (np.abs(np.abs(val) - reach) <= band) | (np.abs(val - offset) <= band) | (np.abs(val + offset) <= band)
+        assert np.all((lab == glab) | tie)
+        assert tie.mean() < 0.1
+
+    c, v = net.box_to_general(g["box_lower"], g["box_upper"])
+    check(net.classify_box(p, ctx, g["box_lower"], g["box_upper"]), g["label"], c, v, 0.0)
+    check(net.classify_box(p, ctx, g["box_lower"], g["box_upper"], offset=0.05), g["label_offset005"], c, v, 0.05)
+    check(net.classify_general_box(p, ctx, g["gen_center"], g["gen_vecs"]), g["gen_label"], g["gen_center"], g["gen_vecs"], 0.0)
+    check(net.classify_general_box(p, ctx, g["gen_center"], g["gen_vecs"][:, :1]), g["gen_label_v1"], g["gen_center"], g["gen_vecs"][:, :1], 0.0)
+    assert name == "hammer" or len(np.unique(g["label"])) >= 2      # (hammer's values dwarf L*radius: all POSITIVE)
+
+
 def test_classify_truncate64():
     g = golden("classify_hammer_affine_truncate64")
     ctx = ctx_for("affine_truncate", g["n_trunc"])
@@ -131,6 +156,7 @@ TREE_CASES = {
     "tree_bunny_all_d9": ("bunny", "affine_all"),
     "tree_fox_trunc_d9": ("fox", "affine_truncate"),
     "tree_fox_append_d9": ("fox", "affine_append"),
+    "tree_fox_sdf_d12": ("fox", "sdf"),
     "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
     "tree_fox_fixed_b128": ("fox", "affine_fixed"),
 }
