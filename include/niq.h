@@ -65,7 +65,8 @@ typedef enum niq_mode {
     NIQ_MODE_AFFINE_TRUNCATE = 2,
     NIQ_MODE_AFFINE_ALL = 3,
     NIQ_MODE_AFFINE_APPEND = 4,  /* src/affine.py:183-191: per activation keep the n_append largest deltas as new terms */
-    NIQ_MODE_SDF = 5             /* src/sdf.py:17-50 WeakSDFImplicitFunction: f(centre) against lipschitz * box radius */
+    NIQ_MODE_SDF = 5,            /* src/sdf.py:17-50 WeakSDFImplicitFunction: f(centre) against lipschitz * box radius */
+    NIQ_MODE_SLOPE_INTERVAL = 6  /* src/slope_interval.py + src/slope_interval_layers.py: primal + slope centre / width */
 } niq_mode;
 
 typedef struct niq_mode_cfg {

@@ -20,7 +20,8 @@ LIB_PATH = os.environ.get("NIQ_LIB") or os.path.join(_HERE, "libniq.so")   # NIQ
 NIQ_OK, NIQ_EINVAL, NIQ_ENOMEM, NIQ_ECUDA, NIQ_ECAPACITY, NIQ_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
 OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL = 0, 1, 2, 3, 4
-MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4, "sdf": 5}
+MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4, "sdf": 5,
+            "slope_interval": 6}
 TREE_INTERIOR, TREE_EXTERIOR = 1, 2
 
 # every symbol include/niq.h declares (tests check the library exports all of them)

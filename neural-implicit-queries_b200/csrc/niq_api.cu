@@ -541,6 +541,28 @@ static int launch_classify_fixed_w(niq_ctx* c, NetDev net, int total_floats, con
     return NIQ_OK;
 }
 template <int WMAX>
+static int launch_classify_slope_w(niq_ctx* c, NetDev net, int total_floats, const BoxSource& src, long long n, float offset,
+                                   int* label, float* lower, float* upper, unsigned char* tie) {
+    using E = Engine<WMAX, TileSlope3>;
+    const size_t smem = place_weights<E>(c, net, total_floats);
+    TRY(set_smem(k_classify_slope<WMAX>, smem));
+    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
+    LaunchTimer lt(c, 0);
+    k_classify_slope<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, src, n, offset, label, lower, upper, tie);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+static int launch_classify_slope(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
+                                 int* label, float* lower, float* upper, unsigned char* tie) {
+    if (n <= 0) return NIQ_OK;
+    switch (m->wmax) {
+        case 32: return launch_classify_slope_w<32>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+        case 64: return launch_classify_slope_w<64>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+        case 128: return launch_classify_slope_w<128>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+        default: return launch_classify_slope_w<256>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
+    }
+}
+template <int WMAX>
 static int launch_eval_points_w(niq_ctx* c, NetDev net, int total_floats, const PointSource& src, long long n, float* f, float* scale) {
     using E = Engine<WMAX, TilePts>;
     const size_t smem = place_weights<E>(c, net, total_floats);
@@ -620,7 +642,7 @@ static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg
 
 static int check_cfg(const niq_mode_cfg* cfg) {
     if (!cfg) return fail(NIQ_EINVAL, "mode cfg is NULL");
-    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_SDF) return fail(NIQ_EINVAL, "invalid mode");
+    if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_SLOPE_INTERVAL) return fail(NIQ_EINVAL, "invalid mode");
     if (cfg->mode == NIQ_MODE_SDF && !(cfg->sdf_lipschitz >= 0.f)) return fail(NIQ_EINVAL, "sdf mode: lipschitz bound must be >= 0");
     if (cfg->mode == NIQ_MODE_AFFINE_TRUNCATE && cfg->truncate_policy != 0)
         return fail(NIQ_EUNSUPPORTED, "truncate policy 'relative' is not supported (reference src/affine.py:146 broadcasts (k,)/(w,))");
@@ -636,6 +658,7 @@ static int classify_dev(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, B
         return launch_classify_fixed(c, m, src, n, offset, label, lower, upper, tie);
     }
     src.interval = 0;
+    if (cfg->mode == NIQ_MODE_SLOPE_INTERVAL) return launch_classify_slope(c, m, src, n, offset, label, lower, upper, tie);
     if (cfg->mode == NIQ_MODE_SDF) {
         // reference src/sdf.py:31-50: one point evaluation at the box centre, then the Lipschitz test
         if (n <= 0) return NIQ_OK;
@@ -769,7 +792,8 @@ extern "C" int niq_classify_general_boxes(niq_ctx* c, const niq_mlp* m, const ni
     if (!c || !m || n < 0 || (n > 0 && (!center || !vecs))) return fail(NIQ_EINVAL, "niq_classify_general_boxes: bad argument");
     TRY(check_cfg(cfg));
     if (v < 1) return fail(NIQ_EINVAL, "v must be >= 1");
-    if (is_fixed_mode(cfg) && v > 3) return fail(NIQ_EUNSUPPORTED, "interval / affine_fixed support v <= 3 box vectors (got %d)", v);
+    if ((is_fixed_mode(cfg) || cfg->mode == NIQ_MODE_SLOPE_INTERVAL) && v > 3)
+        return fail(NIQ_EUNSUPPORTED, "interval / affine_fixed / slope_interval support v <= 3 box vectors (got %d)", v);
     if (n == 0) return NIQ_OK;
     BoxSource src{};
     src.kind = 0; src.v = v;

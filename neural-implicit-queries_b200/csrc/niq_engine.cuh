@@ -129,25 +129,43 @@ __device__ __forceinline__ f32x2 abs2(f32x2 v) { return v & 0x7fffffff7ffffffful
 // Tile descriptors: which rows a thread carries and how the activation couples them.
 //   row kinds: B = base, A = affine coefficient, E = interval error (multiplies |A|), P = point
 // ------------------------------------------------------------------------------------------------
+//   rule: 0 = affine group [base, aff.., err] (+ optional point rows), 1 = point rows only,
+//         2 = slope interval [primal, slope centre x3, slope width x3] (reference src/slope_interval_layers.py)
 struct TileBox3 {   // [B, A, A, A, E] : one general box with 3 symbols (affine_fixed, v<=3; interval uses E only)
-    static constexpr int RT = 5, NT = 2;
+    static constexpr int RT = 5, NT = 2, rule = 0;
     __host__ __device__ static constexpr bool is_err(int r) { return r == 4; }
     __host__ __device__ static constexpr bool has_bias(int r) { return r == 0; }
+    __host__ __device__ static constexpr bool is_pt(int) { return false; }
+    __host__ __device__ static constexpr bool want_scale(int r) { return r == 0; }
     static constexpr int n_aff = 3, n_pts = 0;
     static constexpr bool has_group = true;
 };
 struct TileRay {    // [B, A, E, P, P] : one ray step = segment bound (v=1) + f(start), f(start+eps)
-    static constexpr int RT = 5, NT = 2;
+    static constexpr int RT = 5, NT = 2, rule = 0;
     __host__ __device__ static constexpr bool is_err(int r) { return r == 2; }
     __host__ __device__ static constexpr bool has_bias(int r) { return r == 0 || r >= 3; }
+    __host__ __device__ static constexpr bool is_pt(int r) { return r >= 3; }
+    __host__ __device__ static constexpr bool want_scale(int r) { return r == 0 || r >= 3; }
     static constexpr int n_aff = 1, n_pts = 2;
     static constexpr bool has_group = true;
 };
 struct TilePts {    // [P x 8]
-    static constexpr int RT = 8, NT = 1;
+    static constexpr int RT = 8, NT = 1, rule = 1;
     __host__ __device__ static constexpr bool is_err(int) { return false; }
     __host__ __device__ static constexpr bool has_bias(int) { return true; }
+    __host__ __device__ static constexpr bool is_pt(int) { return true; }
+    __host__ __device__ static constexpr bool want_scale(int) { return true; }
     static constexpr int n_aff = 0, n_pts = 8;
+    static constexpr bool has_group = false;
+};
+struct TileSlope3 { // [P, C, C, C, W, W, W] : primal, slope centres, slope widths of one general box with <= 3 vectors;
+                    // the width rows multiply |A| like the err row (reference src/slope_interval_layers.py:11-33)
+    static constexpr int RT = 7, NT = 1, rule = 2;
+    __host__ __device__ static constexpr bool is_err(int r) { return r >= 4; }
+    __host__ __device__ static constexpr bool has_bias(int r) { return r == 0; }
+    __host__ __device__ static constexpr bool is_pt(int) { return false; }
+    __host__ __device__ static constexpr bool want_scale(int r) { return r == 0; }
+    static constexpr int n_aff = 3, n_pts = 0;
     static constexpr bool has_group = false;
 };
 
@@ -386,7 +404,7 @@ struct Engine {
                 }
             }
         }
-        if (Tile::has_group) {
+        if (Tile::rule != 1) {
             f32x2 wa[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) wa[c] = abs2(wv[c]);
@@ -439,6 +457,38 @@ struct Engine {
     __device__ __forceinline__ void epilogue(float (&acc)[ROWS][8], const float (&bias)[8]) const {
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
+            if (Tile::rule == 2) {
+                // slope interval (reference src/slope_interval_layers.py:35-83, src/slope_interval.py:196-206):
+                // slope bounds C -+ W, primal bounds primal -+ sum_v max(upper, -lower), derivative bounds of the
+                // activation on them, interval product, re-centred
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float p = acc[n * RT][c] + bias[c];
+                    float sl[3], su[3], prad = 0.f;
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) {
+                        sl[v] = acc[n * RT + 1 + v][c] - acc[n * RT + 4 + v][c];
+                        su[v] = acc[n * RT + 1 + v][c] + acc[n * RT + 4 + v][c];
+                        prad = prad + fmaxf(su[v], -sl[v]);
+                    }
+                    if (ACT != ACT_NONE) {
+                        const float pl = p - prad, pu = p + prad;
+                        float dfl, dfu;
+                        if (ACT == ACT_RELU) { dfl = pl > 0.f ? 1.f : 0.f; dfu = pu < 0.f ? 0.f : 1.f; }
+                        else { dfl = fminf(expf(pl), 1.f); dfu = fminf(expf(pu), 1.f); }
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) {
+                            const float nl = fminf(sl[v] * dfl, sl[v] * dfu), nu = fmaxf(su[v] * dfl, su[v] * dfu);
+                            const float nc = 0.5f * (nl + nu);
+                            acc[n * RT + 1 + v][c] = nc;
+                            acc[n * RT + 4 + v][c] = nu - nc;
+                        }
+                        acc[n * RT][c] = ACT == ACT_RELU ? fmaxf(p, 0.f) : elu_f(p);
+                    } else {
+                        acc[n * RT][c] = p;
+                    }
+                }
+            }
             if (Tile::has_group) {
                 constexpr int ie = Tile::n_aff + 1;      // err row index inside the tile
                 float base[8], rad[8];
@@ -471,8 +521,7 @@ struct Engine {
             }
 #pragma unroll
             for (int r = 0; r < RT; ++r) {
-                const bool is_pt = Tile::has_group ? (r > Tile::n_aff + 1) : true;
-                if (is_pt) {
+                if (Tile::is_pt(r)) {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         float x = acc[n * RT + r][c] + bias[c];
@@ -743,8 +792,7 @@ struct Engine {
                         const int i = n * RT + r;
                         if (Tile::is_err(r)) out[i] = fmaf(a, wja, out[i]);
                         else out[i] = fmaf(a, wj, out[i]);
-                        const bool want_scale = Tile::has_group ? (r > Tile::n_aff + 1 || r == 0) : true;
-                        if (want_scale) pscale[i] = fmaf(fabsf(a), wja, pscale[i]);
+                        if (Tile::want_scale(r)) pscale[i] = fmaf(fabsf(a), wja, pscale[i]);
                     }
             }
         }
@@ -753,8 +801,7 @@ struct Engine {
 #pragma unroll
             for (int i = 0; i < ROWS; ++i) {
                 out[i] += __shfl_xor_sync(0xffffffffu, out[i], off);
-                const bool want_scale = Tile::has_group ? ((i % RT) > Tile::n_aff + 1 || (i % RT) == 0) : true;
-                if (want_scale) pscale[i] += __shfl_xor_sync(0xffffffffu, pscale[i], off);
+                if (Tile::want_scale(i % RT)) pscale[i] += __shfl_xor_sync(0xffffffffu, pscale[i], off);
             }
         }
         const float b = __ldg(L.bias);

@@ -192,6 +192,51 @@ k_classify_fixed(const __grid_constant__ NetDev net, const BoxSource src, long l
 }
 
 // ------------------------------------------------------------------------------------------------
+// classify (slope_interval): reference src/slope_interval.py:29-50 -- primal + slope centre / width rows of <= 3 box
+// vectors through the net, then primal -+ sum_v max(upper_v, -lower_v) against the offset
+// ------------------------------------------------------------------------------------------------
+template <int WMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+k_classify_slope(const __grid_constant__ NetDev net, const BoxSource src, long long n, float offset,
+                 int* __restrict__ label, float* __restrict__ lower, float* __restrict__ upper,
+                 unsigned char* __restrict__ near_tie) {
+    using E = Engine<WMAX, TileSlope3>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    E eng(net, smem);
+    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
+    for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+        const long long warp_box0 = pass * E::CTA_TILES + (long long)eng.warp * E::SLOTS;
+        if (eng.lane < E::SLOTS) {
+            const long long i = warp_box0 + eng.lane;
+            float4 rows[5];
+            for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n) { BoxSource s2 = src; s2.interval = 0; load_box_rows(s2, i, rows); }   // [centre, vec x3, 0]
+            float* dst = eng.act + eng.lane * 7 * E::G::S;
+            for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
+            for (int r = 4; r < 7; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        __syncwarp();
+        float out[E::ROWS], ps[E::ROWS];
+        eng.run_net(0, net.n_layers, out, ps);
+        if (eng.cg == 0) {
+            const long long i = warp_box0 + eng.t;
+            if (i < n) {
+                float prad = 0.f;
+#pragma unroll
+                for (int v = 0; v < 3; ++v) prad = prad + fmaxf(out[1 + v] + out[4 + v], -(out[1 + v] - out[4 + v]));
+                const float lo = out[0] - prad, up = out[0] + prad;
+                if (lower) lower[i] = lo;
+                if (upper) upper[i] = up;
+                if (label) label[i] = label_of(lo, up, offset);
+                if (near_tie) near_tie[i] = bound_near_tie(lo, up, offset, ps[0], net.tie_rel) ? 1 : 0;
+            }
+        }
+        __syncwarp();
+    }
+    eng.drain();
+}
+
+// ------------------------------------------------------------------------------------------------
 // sdf mode (reference src/sdf.py:31-50): label of a general box from f(centre) and lipschitz * radius, where
 // radius = sqrt(sum_v ||vec_v||^2).  vals / scale come from k_eval_points on the centres (PointSource kind 3).
 // lower / upper = f -+ lipschitz * radius (ours: the reference returns only the label).

@@ -29,9 +29,8 @@ def generate_implicit_from_params(params, mode, **kwargs):
         import sdf
         return sdf.WeakSDFImplicitFunction(mlp.func_from_spec(mode="default"), lipschitz_bound=kwargs.get("sdf_lipschitz", 1.))
     elif mode == "slope_interval":
-        raise _niq.NiqError(_niq.NIQ_EUNSUPPORTED,
-                            f"mode '{mode}' exists in the reference but is outside this backend's hot path "
-                            "(interval, affine_fixed, affine_truncate, affine_all, affine_append, sdf)")
+        import slope_interval
+        return slope_interval.SlopeIntervalImplicitFunction(mlp.func_from_spec(mode="default"))
     else:
         raise RuntimeError("unrecognized mode")
     return affine.AffineImplicitFunction(mlp.func_from_spec(mode="affine"), ctx)

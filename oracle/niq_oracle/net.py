@@ -189,7 +189,8 @@ class AffineContext:
     sdf_lipschitz: float = 1.0          # mode "sdf" (ours: the reference keeps it on sdf.WeakSDFImplicitFunction)
 
     def __post_init__(self):
-        if self.mode not in ("interval", "affine_fixed", "affine_truncate", "affine_append", "affine_all", "sdf"):
+        if self.mode not in ("interval", "affine_fixed", "affine_truncate", "affine_append", "affine_all", "sdf",
+                             "slope_interval"):
             raise ValueError("invalid mode")
         if self.mode == "affine_truncate" and self.truncate_count is None:
             raise ValueError("must specify truncate count")
@@ -394,10 +395,72 @@ def sdf_center_value_and_reach(params, ctx, center, vecs):
     return val, (rad * F32(ctx.sdf_lipschitz)).astype(F32)
 
 
+def _slope_activation(name, primal, sc, sw):
+    """slope_interval_layers.py:35-58 (relu) / :60-83 (elu), batched: primal (N,w), sc / sw (N,v,w)."""
+    sl, su = sc - sw, sc + sw                                              # slope_interval.py:196-199 slope_bounds
+    prad = np.maximum(su, -sl).sum(axis=1, dtype=F32)                      # :201-206 primal_may_contain_bounds
+    pl, pu = primal - prad, primal + prad
+    if name == "relu":
+        dfl = np.where(pl > 0, F32(1), F32(0))
+        dfu = np.where(pu < 0, F32(0), F32(1))
+        new_primal = np.maximum(primal, F32(0))
+    else:
+        with np.errstate(over="ignore"):
+            dfl = np.minimum(np.exp(pl), F32(1))
+            dfu = np.minimum(np.exp(pu), F32(1))
+        new_primal = _elu(primal)
+    nl = np.minimum(sl * dfl[:, None, :], sl * dfu[:, None, :])
+    nu = np.maximum(su * dfl[:, None, :], su * dfu[:, None, :])
+    nc = (F32(0.5) * (nl + nu)).astype(F32)
+    return new_primal.astype(F32), nc, (nu - nc).astype(F32)
+
+
+def slope_forward(params, center, vecs):
+    """slope_interval.py:172-194 (input form) + the 'slope_interval' rules of slope_interval_layers.py through the op
+    list: -> primal (N,), slope centre (N,v), slope width (N,v) of the scalar output, scale (N,) as in affine_forward."""
+    center = np.ascontiguousarray(center, F32)
+    vecs = np.ascontiguousarray(vecs, F32)
+    primal, sc, sw = center, vecs, np.zeros_like(vecs)
+    ops = op_list(params)
+    last_dense = max(i for i, (nm, _) in enumerate(ops) if nm == "dense")
+    scale = None
+    for i_op, (name, args) in enumerate(ops):
+        if name in ("dense", "spatial_transformation"):
+            if name == "dense":
+                A, b = np.asarray(args["A"], F32), args.get("b")
+            else:
+                A, b = _spatial_as_dense(args["R"], args["t"])
+            if i_op == last_dense:
+                scale = (np.abs(primal)[:, :, None] * np.abs(A)[None, :, :]).sum(axis=1, dtype=F32)
+                if b is not None:
+                    scale = scale + np.abs(np.asarray(b, F32))
+                scale = scale.max(axis=-1).astype(F32)
+            primal = primal @ A
+            if b is not None:
+                primal = primal + np.asarray(b, F32)
+            primal = primal.astype(F32)
+            sc = np.matmul(sc, A).astype(F32)
+            sw = np.matmul(sw, np.abs(A)).astype(F32)
+        elif name in ("relu", "elu"):
+            primal, sc, sw = _slope_activation(name, primal, sc, sw)
+        elif name == "squeeze_last":
+            assert primal.shape[-1] == 1
+            primal, sc, sw = primal[:, 0], sc[:, :, 0], sw[:, :, 0]
+        else:
+            raise ValueError(f"oracle: unsupported op '{name}'")
+    return primal, sc, sw, scale
+
+
 def bound_general_box(params, ctx, center, vecs, chunk=None, return_scale=False):
     """-> (lower, upper[, scale]) float32 (N,): affine.py:119-125 applied to the propagated output."""
     center = np.ascontiguousarray(center, F32)
     vecs = np.ascontiguousarray(vecs, F32)
+    if ctx.mode == "slope_interval":
+        # slope_interval.py:37-44: may-contain bounds of the output
+        primal, sc, sw, scale = slope_forward(params, center, vecs)
+        prad = np.maximum(sc + sw, -(sc - sw)).sum(axis=1, dtype=F32)
+        lower, upper = (primal - prad).astype(F32), (primal + prad).astype(F32)
+        return (lower, upper, scale) if return_scale else (lower, upper)
     if ctx.mode == "sdf":
         val, reach = sdf_center_value_and_reach(params, ctx, center, vecs)
         lower, upper = (val - reach).astype(F32), (val + reach).astype(F32)

@@ -159,6 +159,58 @@ def case_classify_sdf(name, lipschitz):
                 gen_label_v1=np.array(glab1, np.int32))
 
 
+def case_classify_slope(name):
+    """slope_interval.SlopeIntervalImplicitFunction: labels (two offsets) + may-contain bounds of axis-aligned boxes,
+    v=1 / v=2 general boxes, and a prepended rigid transform."""
+    m = _ref_modules()
+    jnp = m["jnp"]
+    import slope_interval as si
+    func, params = _load(m, name, "slope_interval")
+    import zlib
+    lo, hi = _boxes(seed=zlib.crc32(f"{name}-slope".encode()) % 1000)
+
+    def bounds(p, center, vecs):
+        out = func.slope_interval_func(p, si.coordinates_in_general_box(center, vecs))
+        sl, su = si.slope_bounds(out)
+        return si.primal_may_contain_bounds(out, sl, su)
+
+    lab, lab_off, lb, ub = [], [], [], []
+    for i in range(lo.shape[0]):
+        l, u = jnp.array(lo[i]), jnp.array(hi[i])
+        lab.append(int(func.classify_box(params, l, u)))
+        lab_off.append(int(func.classify_box(params, l, u, offset=0.05)))
+        c = 0.5 * (l + u)
+        b = bounds(params, c, jnp.diag(u - c))
+        lb.append(float(b[0])); ub.append(float(b[1]))
+    rng = np.random.default_rng(7)
+    cen = rng.uniform(-1, 1, (12, 3)).astype(np.float32)
+    vec = (rng.standard_normal((12, 2, 3)) * (2.0 ** -rng.integers(0, 8, (12, 1, 1)))).astype(np.float32)
+    glab, glb, gub, g1lab, g1lb, g1ub = [], [], [], [], [], []
+    for i in range(12):
+        glab.append(int(func.classify_general_box(params, jnp.array(cen[i]), jnp.array(vec[i]))))
+        b = bounds(params, jnp.array(cen[i]), jnp.array(vec[i])); glb.append(float(b[0])); gub.append(float(b[1]))
+        g1lab.append(int(func.classify_general_box(params, jnp.array(cen[i]), jnp.array(vec[i, :1]))))
+        b = bounds(params, jnp.array(cen[i]), jnp.array(vec[i, :1])); g1lb.append(float(b[0])); g1ub.append(float(b[1]))
+    th = 0.7
+    R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
+    t = np.array([0.2, -0.1, 0.05], np.float32)
+    p2 = m["mlp"].prepend_op(params, m["mlp"].spatial_transformation())
+    p2["0000.spatial_transformation.R"] = jnp.array(R)
+    p2["0000.spatial_transformation.t"] = jnp.array(t)
+    tl, tlb, tub = [], [], []
+    for i in range(9, 18):
+        l, u = jnp.array(lo[i]), jnp.array(hi[i])
+        tl.append(int(func.classify_box(p2, l, u)))
+        c = 0.5 * (l + u)
+        b = bounds(p2, c, jnp.diag(u - c)); tlb.append(float(b[0])); tub.append(float(b[1]))
+    f32 = lambda a: np.array(a, np.float32)
+    i32 = lambda a: np.array(a, np.int32)
+    return dict(box_lower=lo, box_upper=hi, label=i32(lab), label_offset005=i32(lab_off), lower=f32(lb), upper=f32(ub),
+                gen_center=cen, gen_vecs=vec, gen_label=i32(glab), gen_lower=f32(glb), gen_upper=f32(gub),
+                gen1_label=i32(g1lab), gen1_lower=f32(g1lb), gen1_upper=f32(g1ub),
+                xf_R=R, xf_t=t, xf_label=i32(tl), xf_lower=f32(tlb), xf_upper=f32(tub))
+
+
 def case_points(name):
     m = _ref_modules()
     jnp = m["jnp"]
@@ -258,6 +310,9 @@ for _n in SAMPLES:                                   # the af
     CASES[f"classify_{_n}_affine_append"] = (case_classify, (_n, "affine_append", 4))
 for _n, _L in (("fox", 1.0), ("bunny", 2.0), ("hammer", 1.5), ("birdcage_occ", 4.0)):   # the sdf bounder
     CASES[f"classify_{_n}_sdf"] = (case_classify_sdf, (_n, _L))
+for _n in SAMPLES:                                   # the slope_interval bounder
+    CASES[f"classify_{_n}_slope_interval"] = (case_classify_slope, (_n,))
+CASES["tree_fox_slope_d12"] = (case_tree, ("fox", "slope_interval"), dict(split_depth=12, with_exterior_nodes=True))
 CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))
 CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))

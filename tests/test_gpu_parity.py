@@ -206,6 +206,65 @@ def test_classify_sdf_golden_and_oracle(name):
     assert tie.mean() < 0.01
 
 
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_slope_interval_golden_and_oracle(name):
+    """the slope_interval bounder on the engine's 7-row tile (k_classify_slope) against the run of the
+    unmodified reference (labels + may-contain bounds: axis-aligned, offset, v=2 / v=1 general boxes, rigid transform),
+    against the oracle on random boxes, and the soundness property."""
+    import mlp
+    p = sample_params(name)
+    g = golden(f"classify_{name}_slope_interval")
+    ctx = octx("slope_interval")
+    rel = net.tie_rel(p)
+    func = make(p, "slope_interval")
+    _, _, _, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, g["box_lower"], g["box_upper"])
+    check_bounds(lo, up, g["lower"], g["upper"], sc, rel)
+    check_labels(lab, g["label"], g["lower"], g["upper"], sc, rel=rel)
+    lab5 = func.classify_box(p, g["box_lower"], g["box_upper"], offset=0.05)
+    check_labels(lab5, g["label_offset005"], g["lower"], g["upper"], sc, 0.05, rel=rel)
+    for tag, vecs in (("gen", g["gen_vecs"]), ("gen1", g["gen_vecs"][:, :1])):
+        _, _, _, sc = net.classify_general_box(p, ctx, g["gen_center"], vecs, return_scale=True)
+        lab, lo, up, tie = func.bound_general_box(p, g["gen_center"], vecs)
+        check_bounds(lo, up, g[f"{tag}_lower"], g[f"{tag}_upper"], sc, rel)
+        check_labels(lab, g[f"{tag}_label"], g[f"{tag}_lower"], g[f"{tag}_upper"], sc, rel=rel)
+    p2 = mlp.prepend_op(p, mlp.spatial_transformation())
+    p2["0000.spatial_transformation.R"] = g["xf_R"]
+    p2["0000.spatial_transformation.t"] = g["xf_t"]
+    op2 = net.prepend_op(p, net.spatial_transformation(g["xf_R"], g["xf_t"]))
+    _, _, _, sc = net.classify_box(op2, ctx, g["box_lower"][9:18], g["box_upper"][9:18], return_scale=True)
+    lab, lo, up, tie = func.bound_box(p2, g["box_lower"][9:18], g["box_upper"][9:18])
+    check_bounds(lo, up, g["xf_lower"], g["xf_upper"], sc, rel)
+    check_labels(lab, g["xf_label"], g["xf_lower"], g["xf_upper"], sc, rel=rel)
+    # random boxes vs the oracle
+    lo_b, hi_b = random_boxes(19, 8000)
+    olab, olo, oup, sc = net.classify_box(p, ctx, lo_b, hi_b, return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, lo_b, hi_b)
+    check_bounds(lo, up, olo, oup, sc, rel)
+    assert check_labels(lab, olab, olo, oup, sc, rel=rel) < 0.01 * 8000
+    assert np.all(tie | (lab == olab))
+    # soundness
+    rng = np.random.default_rng(2)
+    u = rng.uniform(0, 1, (8000, 4, 3)).astype(np.float32)
+    x = lo_b[:, None, :] + u * (hi_b - lo_b)[:, None, :]
+    f = mlp.eval_points(p, x)
+    slack = 1e-5 * np.maximum(np.abs(lo), np.abs(up))[:, None] + 1e-6
+    assert np.all(f >= lo[:, None] - slack) and np.all(f <= up[:, None] + slack)
+
+
+@pytest.mark.parametrize("width,act", [(256, "relu"), (128, "elu"), (40, "relu")])
+def test_classify_slope_interval_synthetic_widths(width, act):
+    """The 7-row slope tile on the other width classes (256: streamed weights + zero-skipping K loops)."""
+    p = net.random_mlp([3] + [width] * 8 + [1], act, seed=0)
+    lo_b, hi_b = random_boxes(3, 2000, smin=-12, smax=-2)
+    ctx = octx("slope_interval")
+    olab, olo, oup, sc = net.classify_box(p, ctx, lo_b, hi_b, return_scale=True)
+    lab, lo, up, _ = make(p, "slope_interval").bound_box(p, lo_b, hi_b)
+    rel = net.tie_rel(p)
+    check_bounds(lo, up, olo, oup, sc, rel)
+    check_labels(lab, olab, olo, oup, sc, rel=rel)
+
+
 def test_classify_truncate64_golden():
     g = golden("classify_hammer_affine_truncate64")
     p = sample_params("hammer")
@@ -546,6 +605,7 @@ TREE_CASES = {
     "tree_fox_trunc_d9": ("fox", "affine_truncate"),
     "tree_fox_append_d9": ("fox", "affine_append"),
     "tree_fox_sdf_d12": ("fox", "sdf"),
+    "tree_fox_slope_d12": ("fox", "slope_interval"),
     "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
     "tree_fox_fixed_b128": ("fox", "affine_fixed"),
 }

@@ -110,6 +110,29 @@ def test_classify_sdf(name):
     assert name == "hammer" or len(np.unique(g["label"])) >= 2      # (hammer's values dwarf L*radius: all POSITIVE)
 
 
+@pytest.mark.parametrize("name", SAMPLES)
+def test_classify_slope_interval(name):
+    """the slope_interval bounder (src/slope_interval.py:29-50 with the rules of
+    src/slope_interval_layers.py) -- labels and may-contain bounds of axis-aligned boxes, v=2 / v=1 general boxes and
+    a prepended rigid transform, against the run of the unmodified reference."""
+    g = golden(f"classify_{name}_slope_interval")
+    p = sample_params(name)
+    ctx = net.AffineContext("slope_interval")
+    rtol = net.tie_rel(p)
+    lab, lo, up, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    assert_bounds_close(lo, up, g["lower"], g["upper"], sc, rtol)
+    assert_labels(lab, g["label"], lo, up, sc)
+    assert_labels(net.labels_from_bounds(lo, up, 0.05), g["label_offset005"], lo, up, sc, 0.05)
+    for tag, vecs in (("gen", g["gen_vecs"]), ("gen1", g["gen_vecs"][:, :1])):
+        lab, lo, up, sc = net.classify_general_box(p, ctx, g["gen_center"], vecs, return_scale=True)
+        assert_bounds_close(lo, up, g[f"{tag}_lower"], g[f"{tag}_upper"], sc, rtol)
+        assert_labels(lab, g[f"{tag}_label"], lo, up, sc)
+    p2 = net.prepend_op(p, net.spatial_transformation(g["xf_R"], g["xf_t"]))
+    lab, lo, up, sc = net.classify_box(p2, ctx, g["box_lower"][9:18], g["box_upper"][9:18], return_scale=True)
+    assert_bounds_close(lo, up, g["xf_lower"], g["xf_upper"], sc, rtol)
+    assert_labels(lab, g["xf_label"], lo, up, sc)
+
+
 def test_classify_truncate64():
     g = golden("classify_hammer_affine_truncate64")
     ctx = ctx_for("affine_truncate", g["n_trunc"])
@@ -157,6 +180,7 @@ TREE_CASES = {
     "tree_fox_trunc_d9": ("fox", "affine_truncate"),
     "tree_fox_append_d9": ("fox", "affine_append"),
     "tree_fox_sdf_d12": ("fox", "sdf"),
+    "tree_fox_slope_d12": ("fox", "slope_interval"),
     "tree_fox_fixed_thresh": ("fox", "affine_fixed"),
     "tree_fox_fixed_b128": ("fox", "affine_fixed"),
 }
