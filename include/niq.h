@@ -47,7 +47,10 @@ typedef enum niq_op_kind {
     NIQ_OP_RELU = 1,         /* src/mlp.py:283-287, src/affine_layers.py:34-56                              */
     NIQ_OP_ELU = 2,          /* src/mlp.py:289-293, src/affine_layers.py:59-97                              */
     NIQ_OP_SQUEEZE_LAST = 3, /* src/mlp.py:328-332, src/affine_layers.py:164-172                            */
-    NIQ_OP_SPATIAL = 4       /* src/mlp.py:335-347, src/affine_layers.py:175-179 : A = R (3,3), b = t (3)    */
+    NIQ_OP_SPATIAL = 4,      /* src/mlp.py:335-347, src/affine_layers.py:175-179 : A = R (3,3), b = t (3)    */
+    NIQ_OP_SIN = 5,          /* src/mlp.py:296-300, src/affine_layers.py:100-137, src/slope_interval_layers.py:85-110 */
+    NIQ_OP_POW2_ENCODE = 6   /* src/mlp.py:304-322, src/affine_layers.py:140-161: in_dim = 3, out_dim = #coefs (per input
+                                coordinate), A = coefs (out_dim), b = shift (out_dim) or NULL; must be the first op         */
 } niq_op_kind;
 
 typedef struct niq_op_desc {

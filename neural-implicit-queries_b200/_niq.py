@@ -19,7 +19,7 @@ LIB_PATH = os.environ.get("NIQ_LIB") or os.path.join(_HERE, "libniq.so")   # NIQ
 
 NIQ_OK, NIQ_EINVAL, NIQ_ENOMEM, NIQ_ECUDA, NIQ_ECAPACITY, NIQ_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
-OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL = 0, 1, 2, 3, 4
+OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL, OP_SIN, OP_POW2_ENCODE = 0, 1, 2, 3, 4, 5, 6
 MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4, "sdf": 5,
             "slope_interval": 6}
 TREE_INTERIOR, TREE_EXTERIOR = 1, 2
@@ -217,7 +217,7 @@ def params_digest(params):
 
 
 _OP_KINDS = {"dense": OP_DENSE, "relu": OP_RELU, "elu": OP_ELU, "squeeze_last": OP_SQUEEZE_LAST,
-             "spatial_transformation": OP_SPATIAL}
+             "spatial_transformation": OP_SPATIAL, "sin": OP_SIN, "pow2_frequency_encode": OP_POW2_ENCODE}
 
 
 def op_descs(params):
@@ -230,8 +230,8 @@ def op_descs(params):
         name, args = mlp_mod.get_op_data(params, i)
         args.pop("_", None)
         if name not in _OP_KINDS:
-            raise NiqError(NIQ_EUNSUPPORTED, f"op '{name}' is outside the range-analysis hot path of this backend "
-                                             "(supported: dense, relu, elu, squeeze_last, spatial_transformation)")
+            raise NiqError(NIQ_EUNSUPPORTED, f"op '{name}' is not an op of the reference's mlp format (dense, relu, elu, sin, "
+                                             "pow2_frequency_encode, squeeze_last, spatial_transformation)")
         d = descs[i]
         d.kind = _OP_KINDS[name]
         if name == "dense":
@@ -247,6 +247,19 @@ def op_descs(params):
                     raise ValueError("dense.b must have shape (out,)")
                 keep.append(b)
                 d.b = b.ctypes.data
+        elif name == "pow2_frequency_encode":
+            coefs = _f32(args["coefs"])
+            if coefs.ndim != 1:
+                raise ValueError("pow2_frequency_encode.coefs must be 1-D")
+            keep.append(coefs)
+            d.in_dim, d.out_dim = 3, coefs.shape[0]
+            d.A = coefs.ctypes.data
+            if args.get("shift") is not None:
+                shift = _f32(args["shift"])
+                if shift.shape != coefs.shape:
+                    raise ValueError("pow2_frequency_encode.shift must match coefs")
+                keep.append(shift)
+                d.b = shift.ctypes.data
         elif name == "spatial_transformation":
             R, t = _f32(args["R"]), _f32(args["t"])
             if R.shape != (3, 3) or t.shape != (3,):

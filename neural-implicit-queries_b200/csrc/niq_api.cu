@@ -399,22 +399,44 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
                 raw.push_back(std::move(r));
                 break;
             }
+            case NIQ_OP_POW2_ENCODE: {
+                // x (3) -> (x[:,None] * coefs[None,:] + shift).flatten(): a dense layer with one non-zero per column,
+                // A[d][d*c + i] = coefs[i], b = tile(shift).  fma(x_d, coef, 0) rounds once like the reference's product,
+                // the bias add follows it, and err * coefs == err @ |A| because the coefficients are positive.
+                if (!op.A || op.out_dim <= 0 || op.in_dim != 3) return fail(NIQ_EINVAL, "pow2_frequency_encode op %d: needs 3 inputs and coefs", i);
+                if (!raw.empty() && (raw.back().out != 3 || raw.back().act != ACT_NONE))
+                    return fail(NIQ_EUNSUPPORTED, "pow2_frequency_encode op %d: only on the 3-D input (optionally after spatial_transformation)", i);
+                const int nc = op.out_dim;
+                Raw r; r.in = 3; r.out = 3 * nc; r.act = ACT_NONE;
+                r.A.assign((size_t)3 * r.out, 0.f); r.b.assign(r.out, 0.f);
+                for (int d = 0; d < 3; ++d)
+                    for (int k = 0; k < nc; ++k) {
+                        if (!(op.A[k] > 0.f)) return fail(NIQ_EUNSUPPORTED, "pow2_frequency_encode op %d: coefs must be positive", i);
+                        r.A[(size_t)d * r.out + d * nc + k] = op.A[k];
+                        if (op.b) r.b[d * nc + k] = op.b[k];
+                    }
+                raw.push_back(std::move(r));
+                break;
+            }
             case NIQ_OP_RELU:
             case NIQ_OP_ELU:
+            case NIQ_OP_SIN:
                 if (raw.empty() || raw.back().act != ACT_NONE)
-                    return fail(NIQ_EUNSUPPORTED, "op %d: an activation must directly follow a dense / spatial op", i);
-                raw.back().act = op.kind == NIQ_OP_RELU ? ACT_RELU : ACT_ELU;
+                    return fail(NIQ_EUNSUPPORTED, "op %d: an activation must directly follow a dense / spatial / encode op", i);
+                raw.back().act = op.kind == NIQ_OP_RELU ? ACT_RELU : op.kind == NIQ_OP_ELU ? ACT_ELU : ACT_SIN;
                 break;
             case NIQ_OP_SQUEEZE_LAST:
                 if (raw.empty() || raw.back().out != 1) return fail(NIQ_EINVAL, "squeeze_last needs a preceding op with out_dim 1");
                 squeezed = true;
                 break;
             default:
-                return fail(NIQ_EUNSUPPORTED, "op %d: kind %d is outside the hot-path scope (dense, relu, elu, squeeze_last, spatial_transformation)", i, op.kind);
+                return fail(NIQ_EUNSUPPORTED, "op %d: kind %d is not an op of the reference's mlp format", i, op.kind);
         }
     }
     if (raw.empty()) return fail(NIQ_EINVAL, "no dense layer");
     if (raw.front().in != 3) return fail(NIQ_EUNSUPPORTED, "input dimension %d: queries are 3-D", raw.front().in);
+    for (const Raw& r : raw)
+        if (r.act == ACT_SIN && &r == &raw.back()) return fail(NIQ_EUNSUPPORTED, "activation after the final layer is not supported");
     if (raw.back().out != 1) return fail(NIQ_EUNSUPPORTED, "the last dense layer must have out_dim 1 (scalar implicit function)");
     if (raw.back().act != ACT_NONE) return fail(NIQ_EUNSUPPORTED, "activation after the final layer is not supported");
     if ((int)raw.size() > kMaxLayers) return fail(NIQ_EUNSUPPORTED, "more than %d layers", kMaxLayers);
@@ -464,6 +486,7 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
     nd.n_layers = (int)m->layers.size();
     nd.n_nets = 1;
     nd.tie_rel = 1e-5f;
+    for (const HostLayer& L : m->layers) if (L.act == ACT_SIN) nd.tie_rel = 5e-5f;   // sin rule: float32 conditioning ~1.6e-5 (tests)
     for (const HostLayer& L : m->layers) if (L.act == ACT_ELU) nd.tie_rel = 2e-4f;   // ELU rule conditioning
     for (size_t l = 0; l < m->layers.size(); ++l) {
         const HostLayer& L = m->layers[l];

@@ -31,7 +31,7 @@
 
 namespace niq {
 
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_SIN = 3 };
 
 constexpr int kMaxLayers = 32;     // layers of all nets of one launch (cast_rays concatenates funcs)
 constexpr int kMaxChunks = 192;
@@ -197,6 +197,8 @@ __device__ __forceinline__ void relu_lin(float l, float u, float& alpha, float& 
     float a = div_nr(straddle ? u : 1.f, straddle ? (u - l) : 1.f);
     if (!straddle) a = 0.f;                    // u <= 0 (and nan bounds: comparisons false -> nan_to_num -> 0)
     if (l >= 0.f) a = 1.f;
+    if (u < 0.f) a = 0.f;                      // only reachable with l > u (a NEGATIVE radius: err turns negative after a sin
+                                               // layer with alpha < 0, src/affine.py:176); the reference applies it last
     if (a != a) a = 0.f;                       // inf/inf -> nan -> 0 (nan_to_num(nan=0))
     a = fminf(fmaxf(a, 0.f), 1.f);             // also maps +inf -> 1 like nan_to_num + clip
     alpha = a;
@@ -224,6 +226,46 @@ __device__ __forceinline__ void elu_lin(float l, float u, float& alpha, float& b
     float d = 0.5f * fabsf(r_up - r_lo);
     if (l >= 0.f) { a = 1.f; b = 0.f; d = 0.f; }
     alpha = a; beta = b; delta = fabsf(d);
+}
+
+// bounds of cos on [lower, upper]  (reference src/utils.py:209-231: sin_bound(lower + pi/2, upper + pi/2); the Python
+// float constants of the reference become float32 when they meet float32 arrays, so they are float32 literals here)
+__device__ __forceinline__ void cos_bound(float lower, float upper, float& out_lo, float& out_hi) {
+    const float kHalfPi = 1.5707963267948966f, kTwoPi = 6.283185307179586f;
+    float l = lower + kHalfPi, u = upper + kHalfPi;
+    const float fl = sinf(l), fu = sinf(u);
+    l = l / kTwoPi;
+    u = u / kTwoPi;
+    const bool has_min = ceilf(l - 0.75f) < (u - 0.75f);
+    const bool has_max = ceilf(l - 0.25f) < (u - 0.25f);
+    out_lo = has_min ? -1.f : fminf(fl, fu);
+    out_hi = has_max ? 1.f : fmaxf(fl, fu);
+}
+// sin linearisation on [l,u]  (reference src/affine_layers.py:100-137)
+__device__ __forceinline__ void sin_lin(float l, float u, float& alpha, float& beta, float& delta) {
+    const float kTwoPi = 6.283185307179586f;
+    float s_lo, s_hi;
+    cos_bound(l, u, s_lo, s_hi);
+    float a = 0.5f * (s_lo + s_hi);
+    a = fminf(fmaxf(a, -1.f), 1.f);
+    const float iA = acosf(a), iB = -iA;
+    float locs[6];
+    locs[0] = l;
+    locs[1] = u;
+    locs[2] = kTwoPi * ceilf((l + iA) / kTwoPi) - iA;
+    locs[3] = kTwoPi * floorf((u - iA) / kTwoPi) + iA;
+    locs[4] = kTwoPi * ceilf((l + iB) / kTwoPi) - iB;
+    locs[5] = kTwoPi * floorf((u - iB) / kTwoPi) + iB;
+    float r_lo = 0.f, r_hi = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const float x = fminf(fmaxf(locs[i], l), u);
+        const float v = sinf(x) - a * x;
+        r_lo = i == 0 ? v : fminf(r_lo, v);
+        r_hi = i == 0 ? v : fmaxf(r_hi, v);
+    }
+    const float b = 0.5f * (r_hi + r_lo);
+    alpha = a; beta = b; delta = fabsf(r_hi - b);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -475,15 +517,20 @@ struct Engine {
                         const float pl = p - prad, pu = p + prad;
                         float dfl, dfu;
                         if (ACT == ACT_RELU) { dfl = pl > 0.f ? 1.f : 0.f; dfu = pu < 0.f ? 0.f : 1.f; }
-                        else { dfl = fminf(expf(pl), 1.f); dfu = fminf(expf(pu), 1.f); }
+                        else if (ACT == ACT_ELU) { dfl = fminf(expf(pl), 1.f); dfu = fminf(expf(pu), 1.f); }
+                        else cos_bound(pl, pu, dfl, dfu);                 // sin: the derivative can be negative
 #pragma unroll
                         for (int v = 0; v < 3; ++v) {
-                            const float nl = fminf(sl[v] * dfl, sl[v] * dfu), nu = fmaxf(su[v] * dfl, su[v] * dfu);
+                            float nl = fminf(sl[v] * dfl, sl[v] * dfu), nu = fmaxf(su[v] * dfl, su[v] * dfu);
+                            if (ACT == ACT_SIN) {                        // full interval product (:100-104)
+                                nl = fminf(fminf(nl, su[v] * dfl), su[v] * dfu);
+                                nu = fmaxf(fmaxf(sl[v] * dfl, sl[v] * dfu), nu);
+                            }
                             const float nc = 0.5f * (nl + nu);
                             acc[n * RT + 1 + v][c] = nc;
                             acc[n * RT + 4 + v][c] = nu - nc;
                         }
-                        acc[n * RT][c] = ACT == ACT_RELU ? fmaxf(p, 0.f) : elu_f(p);
+                        acc[n * RT][c] = ACT == ACT_RELU ? fmaxf(p, 0.f) : ACT == ACT_ELU ? elu_f(p) : sinf(p);
                     } else {
                         acc[n * RT][c] = p;
                     }
@@ -506,7 +553,8 @@ struct Engine {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         if (ACT == ACT_RELU) relu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
-                        else elu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
+                        else if (ACT == ACT_ELU) elu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
+                        else sin_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
                     }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
@@ -527,6 +575,7 @@ struct Engine {
                         float x = acc[n * RT + r][c] + bias[c];
                         if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
                         else if (ACT == ACT_ELU) x = elu_f(x);
+                        else if (ACT == ACT_SIN) x = sinf(x);
                         acc[n * RT + r][c] = x;
                     }
                 }
@@ -756,6 +805,7 @@ struct Engine {
             // without a runtime branch inside the unrolled loops the scheduler interleaves their chains
             if (L.act == ACT_RELU) epilogue<ACT_RELU>(acc, bias);
             else if (L.act == ACT_ELU) epilogue<ACT_ELU>(acc, bias);
+            else if (L.act == ACT_SIN) epilogue<ACT_SIN>(acc, bias);
             else epilogue<ACT_NONE>(acc, bias);
         }
         if (sp_out) {

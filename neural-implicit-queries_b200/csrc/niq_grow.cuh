@@ -189,7 +189,8 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                         const float b0 = b_cur[c];
                         float al, be, de;
                         if (L.act == ACT_RELU) relu_lin(b0 - rad, b0 + rad, al, be, de);
-                        else elu_lin(b0 - rad, b0 + rad, al, be, de);
+                        else if (L.act == ACT_ELU) elu_lin(b0 - rad, b0 + rad, al, be, de);
+                        else sin_lin(b0 - rad, b0 + rad, al, be, de);
                         b_cur[c] = al * b0 + be;
                         e_cur[c] = al * e_cur[c];
                         alpha[c] = al;

@@ -2,7 +2,7 @@
 
 Mirrors /root/reference/src/mlp.py (names, signatures, key grammar, error types):
   build_spec :14-24, get_op_data :117-131, n_ops :134-144, prepend_op :149-167, load :173-185,
-  save :187-196, op constructors dense :218-250, relu :283, elu :289, squeeze_last :328,
+  save :187-196, op constructors dense :218-250, relu :283, elu :289, sin :296, pow2_frequency_encode :304-315, squeeze_last :328,
   spatial_transformation :335-340, quick_mlp_spec :73-94, func_from_spec :96-113.
 Arrays are NumPy float32 (the reference holds jnp arrays; NumPy arrays are accepted there too).
 Evaluation does not happen here: `func_from_spec` returns a callable that packs `params` into a
@@ -106,6 +106,23 @@ def relu():
 
 def elu():
     return {"elu._": np.zeros((0,), np.float32)}
+
+
+def sin():
+    return {"sin._": np.zeros((0,), np.float32)}
+
+
+def pow2_frequency_encode(count_pow2, start_pow=0, with_shift=True):
+    """src/mlp.py:304-315: positional encoding coefficients 2^k * pi (and the pi shift that turns every second sin into a
+    cos); followed by sin() in the reference's fitting script (src/main_fit_implicit.py:113-115)."""
+    pows = np.power(np.float32(2.), np.arange(start_pow, start_pow + count_pow2, dtype=np.float32)).astype(np.float32)
+    coefs = (pows * np.float32(np.pi)).astype(np.float32)
+    if with_shift:
+        coefs = np.repeat(coefs, 2)
+        shift = np.zeros_like(coefs)
+        shift[1::2] = np.float32(np.pi)
+        return {"pow2_frequency_encode.coefs": coefs, "pow2_frequency_encode.shift": shift}
+    return {"pow2_frequency_encode.coefs": coefs}
 
 
 def squeeze_last():

@@ -150,9 +150,39 @@ def _elu(x):
     return np.where(x > 0, x, np.expm1(safe)).astype(F32)
 
 
+PI = float(np.pi)
+
+
+def _pow2_encode(x, coefs, shift, with_shift):
+    """mlp.py:316-322 / affine_layers.py:147-152, batched over leading axes: (..., d) -> (..., d*c)."""
+    coefs = np.asarray(coefs, F32)
+    out = (np.asarray(x, F32)[..., :, None] * coefs).astype(F32)
+    if with_shift and shift is not None:
+        out = (out + np.asarray(shift, F32)).astype(F32)
+    return out.reshape(out.shape[:-2] + (out.shape[-2] * out.shape[-1],))      # (explicit: interval mode has 0 aff rows)
+
+
+def _sin_bound(lower, upper):
+    """utils.py:209-229"""
+    f_lower, f_upper = np.sin(lower), np.sin(upper)
+    lower = (lower / F32(2. * PI)).astype(F32)
+    upper = (upper / F32(2. * PI)).astype(F32)
+    contains_min = np.ceil(lower - F32(.75)) < (upper - F32(.75))
+    contains_max = np.ceil(lower - F32(.25)) < (upper - F32(.25))
+    out_lower = np.where(contains_min, F32(-1.), np.minimum(f_lower, f_upper))
+    out_upper = np.where(contains_max, F32(1.), np.maximum(f_lower, f_upper))
+    return out_lower.astype(F32), out_upper.astype(F32)
+
+
+def _cos_bound(lower, upper):
+    """utils.py:230-231"""
+    return _sin_bound((lower + F32(PI / 2)).astype(F32), (upper + F32(PI / 2)).astype(F32))
+
+
 def eval_points(params, x):
     """f(x) for x of shape (N,3) -> (N,) float32.  mlp.py:99-111 with the 'default' rules
-    (dense :253-258, relu :283-287, elu :289-293, squeeze_last :328-332, spatial :342-346)."""
+    (dense :253-258, relu :283-287, elu :289-293, sin :296-300, pow2_frequency_encode :316-322, squeeze_last :328-332,
+    spatial :342-346)."""
     h = np.ascontiguousarray(x, dtype=F32)
     for name, args in op_list(params):
         if name == "dense":
@@ -166,6 +196,10 @@ def eval_points(params, x):
             h = np.maximum(h, F32(0))
         elif name == "elu":
             h = _elu(h)
+        elif name == "sin":
+            h = np.sin(h)
+        elif name == "pow2_frequency_encode":
+            h = _pow2_encode(h, args["coefs"], args.get("shift"), True)
         elif name == "squeeze_last":
             assert h.shape[-1] == 1
             h = h[..., 0]
@@ -330,6 +364,39 @@ def _elu_rule(ctx, base, aff, err):
     return _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta)
 
 
+def _sin_coeffs(base, aff, err):
+    """affine_layers.py:100-137 -> (alpha, beta, delta): a not-quite-Chebyshev linearisation of sin on [lower, upper]."""
+    rad = _radius(aff, err)
+    lower, upper = (base - rad).astype(F32), (base + rad).astype(F32)
+    slope_lower, slope_upper = _cos_bound(lower, upper)
+    alpha = (F32(0.5) * (slope_lower + slope_upper)).astype(F32)
+    alpha = np.clip(alpha, F32(-1.), F32(1.))
+    intA = np.arccos(alpha)
+    intB = -intA
+    two_pi = F32(2. * PI)
+
+    def first(x):
+        return (two_pi * np.ceil((lower + x) / two_pi) - x).astype(F32)
+
+    def last(x):
+        return (two_pi * np.floor((upper - x) / two_pi) + x).astype(F32)
+
+    locs = [lower, upper, first(intA), last(intA), first(intB), last(intB)]
+    locs = [np.minimum(np.maximum(x, lower), upper) for x in locs]
+    vals = [(np.sin(x) - alpha * x).astype(F32) for x in locs]
+    r_lower, r_upper = vals[0], vals[0]
+    for v in vals[1:]:
+        r_lower, r_upper = np.minimum(r_lower, v), np.maximum(r_upper, v)
+    beta = (F32(0.5) * (r_upper + r_lower)).astype(F32)
+    delta = (r_upper - beta).astype(F32)
+    return alpha.astype(F32), beta, delta
+
+
+def _sin_rule(ctx, base, aff, err):
+    alpha, beta, delta = _sin_coeffs(base, aff, err)
+    return _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta)
+
+
 def _dense_rule(base, aff, err, A, b):
     """affine_layers.py:11-31 -- base@A+b, every aff row @A, err@|A|."""
     A = np.asarray(A, F32)
@@ -374,8 +441,12 @@ def affine_forward(params, ctx, center, vecs):
         elif name == "spatial_transformation":
             A, b = _spatial_as_dense(args["R"], args["t"])
             base, aff, err = _dense_rule(base, aff, err, A, b)
-        elif name in ("relu", "elu"):
-            base, aff, err = (_relu_rule if name == "relu" else _elu_rule)(ctx, base, aff, err)
+        elif name in ("relu", "elu", "sin"):
+            base, aff, err = {"relu": _relu_rule, "elu": _elu_rule, "sin": _sin_rule}[name](ctx, base, aff, err)
+        elif name == "pow2_frequency_encode":                      # affine_layers.py:140-161
+            base = _pow2_encode(base, args["coefs"], args.get("shift"), True)
+            aff = _pow2_encode(aff, args["coefs"], None, False)
+            err = _pow2_encode(err, args["coefs"], None, False)
         elif name == "squeeze_last":
             assert base.shape[-1] == 1
             base, aff, err = base[:, 0], aff[:, :, 0], err[:, 0]
@@ -400,6 +471,14 @@ def _slope_activation(name, primal, sc, sw):
     sl, su = sc - sw, sc + sw                                              # slope_interval.py:196-199 slope_bounds
     prad = np.maximum(su, -sl).sum(axis=1, dtype=F32)                      # :201-206 primal_may_contain_bounds
     pl, pu = primal - prad, primal + prad
+    if name == "sin":                                               # slope_interval_layers.py:85-110
+        dfl, dfu = _cos_bound(pl.astype(F32), pu.astype(F32))
+        cands = [sl * dfl[:, None, :], sl * dfu[:, None, :], su * dfl[:, None, :], su * dfu[:, None, :]]
+        nl, nu = cands[0], cands[0]
+        for cnd in cands[1:]:
+            nl, nu = np.minimum(nl, cnd), np.maximum(nu, cnd)
+        nc = (F32(0.5) * (nl + nu)).astype(F32)
+        return np.sin(primal).astype(F32), nc, (nu - nc).astype(F32)
     if name == "relu":
         dfl = np.where(pl > 0, F32(1), F32(0))
         dfu = np.where(pu < 0, F32(0), F32(1))
@@ -441,8 +520,12 @@ def slope_forward(params, center, vecs):
             primal = primal.astype(F32)
             sc = np.matmul(sc, A).astype(F32)
             sw = np.matmul(sw, np.abs(A)).astype(F32)
-        elif name in ("relu", "elu"):
+        elif name in ("relu", "elu", "sin"):
             primal, sc, sw = _slope_activation(name, primal, sc, sw)
+        elif name == "pow2_frequency_encode":                      # slope_interval_layers.py:112-126
+            primal = _pow2_encode(primal, args["coefs"], args.get("shift"), True)
+            sc = _pow2_encode(sc, args["coefs"], None, False)
+            sw = _pow2_encode(sw, args["coefs"], None, False)
         elif name == "squeeze_last":
             assert primal.shape[-1] == 1
             primal, sc, sw = primal[:, 0], sc[:, :, 0], sw[:, :, 0]
@@ -534,6 +617,7 @@ def classify_box(params, ctx, lo, hi, offset=0.0, return_bounds=False, return_sc
 
 NEAR_TIE_REL = 1e-5
 NEAR_TIE_REL_ELU = 2e-4
+NEAR_TIE_REL_SIN = 5e-5    # nets with a sin layer: float32 vs float64 of the same formulas differ by up to 1.6e-5 (tests)
 
 
 def tie_rel(params):
@@ -542,7 +626,8 @@ def tie_rel(params):
     delta = |r_upper - r_lower|/2 cancels O(1) terms, so two IEEE-correct implementations that differ by
     1 ulp in exp/log/expm1 disagree by ~1e-7 ABSOLUTE per neuron, amplified by the following layers
     (tests/test_oracle_golden.py::test_elu_rule_conditioning measures it against float64)."""
-    return NEAR_TIE_REL_ELU if any(nm == "elu" for nm, _ in op_list(params)) else NEAR_TIE_REL
+    names = {nm for nm, _ in op_list(params)}
+    return NEAR_TIE_REL_ELU if "elu" in names else NEAR_TIE_REL_SIN if "sin" in names else NEAR_TIE_REL
 
 
 def mode_rel(params, ctx):

@@ -164,6 +164,10 @@ def point_scale(params, x):
             h = np.maximum(h, F32(0))
         elif name == "elu":
             h = net._elu(h)
+        elif name == "sin":
+            h = np.sin(h)
+        elif name == "pow2_frequency_encode":
+            h = net._pow2_encode(h, args["coefs"], args.get("shift"), True)
         h = h.astype(F32, copy=False)
     raise ValueError("no dense layer")
 

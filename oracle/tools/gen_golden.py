@@ -211,6 +211,65 @@ def case_classify_slope(name):
                 xf_R=R, xf_t=t, xf_label=i32(tl), xf_lower=f32(tlb), xf_upper=f32(tub))
 
 
+def _pe_params(m):
+    """A positional-encoding MLP as src/main_fit_implicit.py:113-115 builds it: pow2_frequency_encode(4, start_pow=-1,
+    with_shift) -> sin -> 24 -> 32 -> 32 -> 32 -> 1 relu net, weights from NumPy seed 5 (glorot-normal scale)."""
+    mlp = m["mlp"]
+    jnp = m["jnp"]
+    rng = np.random.default_rng(5)
+    sizes = [24, 32, 32, 32, 1]
+    spec = [mlp.pow2_frequency_encode(4, start_pow=-1, with_shift=True), mlp.sin()]
+    for i in range(len(sizes) - 1):
+        A = (rng.standard_normal((sizes[i], sizes[i + 1])) * np.sqrt(2.0 / (sizes[i] + sizes[i + 1]))).astype(np.float32)
+        b = (rng.standard_normal(sizes[i + 1]) * 0.05).astype(np.float32)
+        spec.append(mlp.dense(sizes[i], sizes[i + 1], A=jnp.array(A), b=jnp.array(b)))
+        if i + 2 != len(sizes):
+            spec.append(mlp.relu())
+    spec.append(mlp.squeeze_last())
+    return mlp.build_spec(spec)
+
+
+def case_pe(mode, n_trunc=8):
+    """sin + pow2_frequency_encode (src/mlp.py:296-322, src/affine_layers.py:100-161, src/slope_interval_layers.py:85-126)
+    on a positional-encoding MLP: labels + bounds in `mode`, point values; the params are stored in the fixture."""
+    m = _ref_modules()
+    jnp = m["jnp"]
+    params = _pe_params(m)
+    path = f"/tmp/niq_pe_mlp_{os.getpid()}.npz"
+    m["mlp"].save(path, params)
+    func, params = m["imu"].generate_implicit_from_file(path, mode, **_mode_kwargs(mode, n_trunc))
+    os.remove(path)
+    out = {"params/" + k: np.array(v) for k, v in params.items()}
+    lo, hi = _boxes(seed=21, n_per_scale=3, scales=range(1, 11))
+    out.update(box_lower=lo, box_upper=hi, n_trunc=n_trunc)
+    if mode == "slope_interval":
+        import slope_interval as si
+
+        def bounds(center, vecs):
+            o = func.slope_interval_func(params, si.coordinates_in_general_box(center, vecs))
+            sl, su = si.slope_bounds(o)
+            return si.primal_may_contain_bounds(o, sl, su)
+    else:
+        affine = m["affine"]
+
+        def bounds(center, vecs):
+            import dataclasses
+            ctx = dataclasses.replace(func.ctx, affine_domain_terms=vecs.shape[0])
+            res = func.affine_func(params, affine.coordinates_in_general_box(ctx, center, vecs), {"ctx": ctx})
+            return affine.may_contain_bounds(ctx, res)
+    lab, lb, ub = [], [], []
+    for i in range(lo.shape[0]):
+        l, u = jnp.array(lo[i]), jnp.array(hi[i])
+        lab.append(int(func.classify_box(params, l, u)))
+        c = 0.5 * (l + u)
+        b = bounds(c, jnp.diag(u - c))
+        lb.append(float(b[0])); ub.append(float(b[1]))
+    pts = np.random.default_rng(3).uniform(-1, 1, (32, 3)).astype(np.float32)
+    out.update(label=np.array(lab, np.int32), lower=np.array(lb, np.float32), upper=np.array(ub, np.float32), points=pts,
+               values=np.array([float(func(params, jnp.array(x))) for x in pts], np.float32))
+    return out
+
+
 def case_points(name):
     m = _ref_modules()
     jnp = m["jnp"]
@@ -313,6 +372,8 @@ for _n, _L in (("fox", 1.0), ("bunny", 2.0), ("hammer", 1.5), ("birdcage_occ", 4
 for _n in SAMPLES:                                   # the slope_interval bounder
     CASES[f"classify_{_n}_slope_interval"] = (case_classify_slope, (_n,))
 CASES["tree_fox_slope_d12"] = (case_tree, ("fox", "slope_interval"), dict(split_depth=12, with_exterior_nodes=True))
+for _mode in ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval"):   # sin + encode ops
+    CASES[f"pe_{_mode}"] = (case_pe, (_mode,))
 CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))
 CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))

@@ -265,6 +265,70 @@ def test_classify_slope_interval_synthetic_widths(width, act):
     check_labels(lab, olab, olo, oup, sc, rel=rel)
 
 
+PE_MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval")
+
+
+@pytest.mark.parametrize("mode", PE_MODES)
+def test_positional_encoding_ops(mode):
+    """sin + pow2_frequency_encode (positional-encoding MLPs of src/main_fit_implicit.py:113-115): the
+    encode op is folded into a dense layer on the host, sin is a third activation rule of the engine / grow kernel.
+    Against the run of the unmodified reference (labels, bounds, point values), the oracle on random boxes, soundness,
+    and a small cast_rays through the persistent kernel."""
+    import mlp
+    import queries
+    import render
+    g = golden(f"pe_{mode}")
+    p = {k.split("/", 1)[1]: g[k] for k in g if k.startswith("params/")}
+    func = make(p, mode, g["n_trunc"])
+    ctx = octx(mode, g["n_trunc"])
+    rel = net.tie_rel(p)                     # 5e-5 for nets with a sin layer (float32 conditioning of the sin rule)
+    _, _, _, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, g["box_lower"], g["box_upper"])
+    okg = np.ones(lab.shape[0], bool)
+    if mode == "affine_truncate":
+        # sin saturates to (alpha, beta, delta) = (0, 0, 1) on boxes that span whole periods: many new rows of EQUAL L1
+        # norm, where a 1-ulp difference in sin decides which are kept -- truncation near-ties, set aside as elsewhere
+        c, v = net.box_to_general(g["box_lower"], g["box_upper"])
+        okg = ~net.truncate_rank_near_tie(p, ctx, c, v, rel=rel)
+        assert okg.sum() >= 5
+    check_bounds(lo[okg], up[okg], g["lower"][okg], g["upper"][okg], sc[okg], rel)
+    check_labels(lab[okg], g["label"][okg], g["lower"][okg], g["upper"][okg], sc[okg], rel=rel)
+    f = func(p, g["points"])
+    assert np.all(np.abs(f - g["values"]) <= RTOL * rays.point_scale(p, g["points"]))
+    n = 4000 if mode in ("interval", "affine_fixed", "slope_interval") else 600
+    lo_b, hi_b = random_boxes(23, n, smin=-8, smax=-1)
+    olab, olo, oup, sc = net.classify_box(p, ctx, lo_b, hi_b, return_scale=True)
+    lab, lo, up, tie = func.bound_box(p, lo_b, hi_b)
+    ok = np.ones(n, bool)
+    if mode == "affine_truncate":
+        c, v = net.box_to_general(lo_b, hi_b)
+        ok = ~net.truncate_rank_near_tie(p, ctx, c, v, rel=rel)
+        assert ok.mean() > 0.2
+    check_bounds(lo[ok], up[ok], olo[ok], oup[ok], sc[ok], rel)
+    assert check_labels(lab[ok], olab[ok], olo[ok], oup[ok], sc[ok], rel=rel) < 0.01 * n
+    rng = np.random.default_rng(2)
+    u = rng.uniform(0, 1, (n, 4, 3)).astype(np.float32)
+    x = lo_b[:, None, :] + u * (hi_b - lo_b)[:, None, :]
+    fx = mlp.eval_points(p, x)
+    slack = 1e-5 * np.maximum(np.abs(lo), np.abs(up))[:, None] + 1e-6
+    if mode != "interval":
+        # (interval mode enters the sin layer with err > 0 and the reference then forms `alpha * err + delta` with a
+        # possibly NEGATIVE alpha, src/affine.py:176 -- its bounds are not sound there, and parity reproduces them)
+        assert np.all(fx >= lo[:, None] - slack) and np.all(fx <= up[:, None] + slack)
+    if mode == "affine_fixed":
+        eye = np.array((2., 1., 2.), np.float32)
+        look, upd, _ = render.look_at(eye)
+        roots, dirs = render.generate_camera_rays(eye, look, upd, res=24, fov_deg=30.)
+        opts = queries.get_default_cast_opts()
+        opts["n_max_step"] = 96
+        t, hit, cnt, n_evals, gtie = queries.cast_rays((func,), (p,), roots, dirs, opts, return_near_tie=True)
+        ot, ohit, ocnt, on_evals, otie = rays.cast_rays((ctx,), (p,), roots, dirs, opts, return_near_tie=True)
+        okr = ~(gtie | otie)
+        assert okr.mean() > 0.9
+        assert np.array_equal(hit[okr], ohit[okr]) and np.array_equal(cnt[okr], ocnt[okr])
+        np.testing.assert_allclose(t[okr], ot[okr], rtol=RTOL)
+
+
 def test_classify_truncate64_golden():
     g = golden("classify_hammer_affine_truncate64")
     p = sample_params("hammer")
@@ -392,7 +456,7 @@ def test_unsupported_and_invalid_arguments():
     with pytest.raises(_niq.NiqError):
         f.classify_box(p, LO, HI)
     bad = dict(p)
-    bad["0001.sin._"] = bad.pop("0001.relu._")
+    bad["0001.softplus._"] = bad.pop("0001.relu._")
     with pytest.raises(RuntimeError):
         make(bad, "affine_fixed").classify_box(bad, LO, HI)
     import kd_tree

@@ -133,6 +133,28 @@ def test_classify_slope_interval(name):
     assert_labels(lab, g["xf_label"], lo, up, sc)
 
 
+PE_MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval")
+
+
+def pe_params(g):
+    return {k.split("/", 1)[1]: g[k] for k in g if k.startswith("params/")}
+
+
+@pytest.mark.parametrize("mode", PE_MODES)
+def test_positional_encoding_ops(mode):
+    """the sin and pow2_frequency_encode ops (src/mlp.py:296-322, src/affine_layers.py:100-161,
+    src/slope_interval_layers.py:85-126) on a positional-encoding MLP, against the run of the unmodified reference."""
+    g = golden(f"pe_{mode}")
+    p = pe_params(g)
+    ctx = ctx_for(mode, g["n_trunc"])
+    lab, lo, up, sc = net.classify_box(p, ctx, g["box_lower"], g["box_upper"], return_scale=True)
+    assert_bounds_close(lo, up, g["lower"], g["upper"], sc)
+    assert_labels(lab, g["label"], lo, up, sc)
+    f = net.eval_points(p, g["points"])
+    assert np.all(np.abs(f - g["values"]) <= RTOL * rays.point_scale(p, g["points"]))
+    assert len(np.unique(g["label"])) == 3
+
+
 def test_classify_truncate64():
     g = golden("classify_hammer_affine_truncate64")
     ctx = ctx_for("affine_truncate", g["n_trunc"])
