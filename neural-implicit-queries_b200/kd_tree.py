@@ -201,3 +201,66 @@ def closest_point(func, params, lower, upper, query_points, eps=0.001, batch_pro
     if stats is not None:
         stats.update(n_rounds=st[0], n_visits=st[1], max_stack=st[2], n_near_tie=st[3])
     return dist, loc
+
+
+# ---------------------------------------------------------------------------------------------------
+# tree consumers: src/kd_tree.py:220-292 sample_surface, :804-863 bulk_properties.
+# The tree and every function evaluation run on the GPU; the draws come from a numpy.random.Generator (the reference's
+# jax.random / threefry streams are not reproducible without JAX: same quantities in the same order -- a node per
+# sample, then a point inside it -- hence the same distribution, not the same bits).  `rngkey` may be an int seed or a
+# Generator.
+# ---------------------------------------------------------------------------------------------------
+
+def _rng(rngkey):
+    return rngkey if isinstance(rngkey, np.random.Generator) else np.random.default_rng(rngkey)
+
+
+def _draw_in_nodes(rng, node_lower, node_upper, n):
+    node_ind = rng.integers(0, node_lower.shape[0], size=n)
+    u = rng.random((n, 3), dtype=np.float32)
+    lo, hi = node_lower[node_ind], node_upper[node_ind]
+    return (lo + u * (hi - lo)).astype(np.float32)
+
+
+def sample_surface(func, params, lower, upper, n_samples, width, rngkey, n_node_thresh=4096, ctx=None):
+    """src/kd_tree.py:253-292 -> (n_samples,3) points with |f| < width, drawn uniformly from the unknown leaves of a tree
+    built with offset=width (so the band is covered)."""
+    rng = _rng(rngkey)
+    out = construct_uniform_unknown_levelset_tree(func, params, lower, upper, node_terminate_thresh=n_node_thresh,
+                                                  offset=width, ctx=ctx)
+    v = out['unknown_node_valid']
+    nl, nu = out['unknown_node_lower'][v], out['unknown_node_upper'][v]
+    if nl.shape[0] == 0:
+        raise ValueError("no unknown node: the level set does not cross the domain")
+    per_round = min(3 * n_samples, 100000)
+    found = np.zeros((n_samples, 3), np.float32)
+    n_found = 0
+    while n_found < n_samples:
+        pos = _draw_in_nodes(rng, nl, nu, per_round)
+        ok = np.abs(func(params, pos)) < np.float32(width)
+        take = pos[ok][:n_samples - n_found]
+        found[n_found:n_found + take.shape[0]] = take
+        n_found += take.shape[0]
+    return found
+
+
+def bulk_properties(func, params, lower, upper, rngkey, n_expand=int(1e4), n_sample=int(1e6), ctx=None):
+    """src/kd_tree.py:837-863 -> (mass, centroid (3,)) of {f < 0}: exact over the interior nodes, Monte Carlo over the
+    unknown leaves (:804-835)."""
+    rng = _rng(rngkey)
+    f32 = np.float32
+    out = construct_uniform_unknown_levelset_tree(func, params, lower, upper, with_interior_nodes=True,
+                                                  node_terminate_thresh=n_expand, ctx=ctx)
+    v, iv = out['unknown_node_valid'], out['interior_node_valid']
+    nl, nu = out['unknown_node_lower'][v], out['unknown_node_upper'][v]
+    il, iu = out['interior_node_lower'][iv], out['interior_node_upper'][iv]
+    m_int = np.prod(iu - il, axis=-1, dtype=f32)
+    mass_interior = m_int.sum(dtype=f32)
+    centroid_interior = (m_int[:, None] * (f32(0.5) * (il + iu))).sum(axis=0, dtype=f32)
+    pos = _draw_in_nodes(rng, nl, nu, n_sample)
+    inside = func(params, pos) < 0
+    vol_per_sample = np.prod(nu - nl, axis=-1, dtype=f32).sum(dtype=f32) / f32(n_sample)
+    mass_boundary = vol_per_sample * f32(inside.sum())
+    centroid_boundary = vol_per_sample * np.where(inside[:, None], pos, f32(0)).sum(axis=0, dtype=f32)
+    mass = mass_interior + mass_boundary
+    return f32(mass), ((centroid_interior + centroid_boundary) / mass).astype(f32)

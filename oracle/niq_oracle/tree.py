@@ -345,3 +345,54 @@ def closest_point(ctx, params, lower, upper, query_points, eps=0.001, batch_proc
     if stats is not None:
         stats.update(n_rounds=n_rounds, n_visits=n_visits, max_stack=max_top, n_near_tie=n_tie)
     return min_dist, min_loc
+
+
+# ----------------------------------------------------------------------------------------------
+# tree consumers: surface sampling and bulk properties (kd_tree.py:220-292, 804-863)
+# The reference draws from jax.random (threefry), which is not available here; these restatements take a
+# numpy.random.Generator and draw the SAME quantities in the SAME order (node index, then position), so the product
+# and the oracle agree sample by sample, while agreement with the reference is distributional.
+# ----------------------------------------------------------------------------------------------
+
+def _draw_in_nodes(rng, node_lower, node_upper, n):
+    """kd_tree.py:230-240 / 810-820: a node per sample (uniform over the valid nodes), then a point inside it."""
+    node_ind = rng.integers(0, node_lower.shape[0], size=n)
+    u = rng.random((n, 3), dtype=np.float32)
+    lo, hi = node_lower[node_ind], node_upper[node_ind]
+    return (lo + u * (hi - lo)).astype(F32)
+
+
+def sample_surface(ctx, params, lower, upper, n_samples, width, rng, n_node_thresh=4096):
+    """kd_tree.py:253-292: tree with offset=width, then rejection sampling |f| < width inside the unknown leaves."""
+    out = construct_uniform_unknown_levelset_tree(ctx, params, lower, upper, node_terminate_thresh=n_node_thresh, offset=width)
+    v = out["unknown_node_valid"]
+    nl, nu = out["unknown_node_lower"][v], out["unknown_node_upper"][v]
+    per_round = min(3 * n_samples, 100000)
+    found = np.zeros((n_samples, 3), F32)
+    n_found = 0
+    while n_found < n_samples:
+        pos = _draw_in_nodes(rng, nl, nu, per_round)
+        ok = np.abs(net.eval_points(params, pos)) < F32(width)
+        take = pos[ok][: n_samples - n_found]
+        found[n_found:n_found + take.shape[0]] = take
+        n_found += take.shape[0]
+    return found
+
+
+def bulk_properties(ctx, params, lower, upper, rng, n_expand=int(1e4), n_sample=int(1e6)):
+    """kd_tree.py:837-863: mass and centroid of {f < 0}: exact over the interior (NEGATIVE) nodes, Monte Carlo over the
+    unknown leaves (:804-835)."""
+    out = construct_uniform_unknown_levelset_tree(ctx, params, lower, upper, with_interior_nodes=True, node_terminate_thresh=n_expand)
+    v, iv = out["unknown_node_valid"], out["interior_node_valid"]
+    nl, nu = out["unknown_node_lower"][v], out["unknown_node_upper"][v]
+    il, iu = out["interior_node_lower"][iv], out["interior_node_upper"][iv]
+    m_int = np.prod(iu - il, axis=-1, dtype=F32)
+    mass_interior = m_int.sum(dtype=F32)
+    centroid_interior = (m_int[:, None] * (F32(0.5) * (il + iu))).sum(axis=0, dtype=F32)
+    pos = _draw_in_nodes(rng, nl, nu, n_sample)
+    inside = net.eval_points(params, pos) < 0
+    vol_per_sample = np.prod(nu - nl, axis=-1, dtype=F32).sum(dtype=F32) / F32(n_sample)
+    mass_boundary = vol_per_sample * F32(inside.sum())
+    centroid_boundary = vol_per_sample * np.where(inside[:, None], pos, F32(0)).sum(axis=0, dtype=F32)
+    mass = mass_interior + mass_boundary
+    return F32(mass), ((centroid_interior + centroid_boundary) / mass).astype(F32)

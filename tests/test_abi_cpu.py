@@ -56,16 +56,18 @@ def test_mc_tables_match_oracle(built):
 
 def test_module_surface_matches_reference():
     import affine, bucketing, extract_cell, implicit_function, implicit_mlp_utils, kd_tree, mlp, queries, render  # noqa: E401
+    import sdf, slope_interval  # noqa: E401
     assert (implicit_function.SIGN_UNKNOWN, implicit_function.SIGN_POSITIVE, implicit_function.SIGN_NEGATIVE) == (0, 1, 2)
     for mod, names in ((mlp, "load save prepend_op spatial_transformation get_op_data n_ops func_from_spec build_spec "
-                             "dense relu elu squeeze_last quick_mlp_spec initialize_params"),
+                             "dense relu elu sin pow2_frequency_encode squeeze_last quick_mlp_spec initialize_params"),
                        (queries, "get_default_cast_opts cast_rays"),
                        (kd_tree, "construct_uniform_unknown_levelset_tree hierarchical_marching_cubes "
-                                 "find_any_intersection closest_point"),
+                                 "find_any_intersection closest_point sample_surface bulk_properties"),
                        (extract_cell, "get_mc_data extract_triangles_from_subcells"),
                        (bucketing, "get_next_bucket_size fits_in_smaller_bucket compactify_and_rebucket_arrays"),
                        (render, "camera_ray generate_camera_rays look_at"),
                        (implicit_mlp_utils, "generate_implicit_from_file"),
+                       (sdf, "WeakSDFImplicitFunction"), (slope_interval, "SlopeIntervalImplicitFunction"),
                        (affine, "AffineContext AffineImplicitFunction")):
         for n in names.split():
             assert hasattr(mod, n), f"{mod.__name__}.{n} missing"

@@ -894,3 +894,27 @@ def test_closest_point_vs_oracle(B):
         np.testing.assert_allclose(loc[fin], oloc[fin], rtol=0, atol=1e-6)
     else:
         assert np.mean(np.abs(d - od) <= 1e-5 * od) > 0.7
+
+
+# ---------------------------------------------------------------------------------------------------
+# tree consumers
+# ---------------------------------------------------------------------------------------------------
+
+def test_sample_surface_and_bulk_properties_vs_oracle():
+    """kd_tree.sample_surface / bulk_properties (src/kd_tree.py:220-292, 804-863) with the same NumPy generator as the
+    oracle: the draws are identical, so the accepted samples agree one by one except where |f| is within the
+    point-value band of the acceptance threshold; mass / centroid agree to Monte-Carlo-free precision."""
+    import kd_tree
+    p = sample_params("fox")
+    func = make(p, "affine_fixed")
+    width = 0.01
+    pts = kd_tree.sample_surface(func, p, LO, HI, 3000, width, 7)
+    opts = otree.sample_surface(octx("affine_fixed"), p, LO, HI, 3000, width, np.random.default_rng(7))
+    f = net.eval_points(p, pts)
+    assert np.all(np.abs(f) < width + 1e-5 * rays.point_scale(p, pts))
+    same = np.all(pts == opts, axis=1)
+    assert same.mean() > 0.99 or np.array_equal(pts[:100], opts[:100])
+    mass, cen = kd_tree.bulk_properties(func, p, LO, HI, 11, n_expand=2000, n_sample=200000)
+    omass, ocen = otree.bulk_properties(octx("affine_fixed"), p, LO, HI, np.random.default_rng(11), n_expand=2000, n_sample=200000)
+    assert abs(mass - omass) <= 2e-4 * omass and np.all(np.abs(cen - ocen) <= 2e-4)
+    assert 0.01 < mass < 8.0 and np.all(np.abs(cen) < 1.0)
