@@ -369,7 +369,7 @@ def run_ours(args):
             "gpu_launches": int(gpu_launches), "step_ms": [round(x, 2) for x in step_ms],
             "clocks": clk,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": 2.1e6, "traffic_note": "dram__bytes_read+write per launch from the ncu --set full capture of the same kernel at 18 tiles (profiles/): 2.1 MB, i.e. the weights once; not memory-bound",
+                         "traffic": 2.14e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the same kernel at 18 tiles (profiles/r1_final_cast_rays256_ncu_full_summary.txt): 2.14 MB read (the weights once), 0 written; not memory-bound",
                          "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / peak_tflops,
                          "executed_over_algorithmic_flops": achieved / algorithmic,
                          "note": "achieved = EXECUTED FP32 FMA flops (device counter: columns that are exactly zero after a relu layer are skipped, "

@@ -450,7 +450,9 @@ def test_unsupported_and_invalid_arguments():
     import implicit_mlp_utils
     p = sample_params("fox")
     with pytest.raises(RuntimeError):
-        implicit_mlp_utils.generate_implicit_from_params(p, "slope_interval")
+        implicit_mlp_utils.generate_implicit_from_params(p, "tanh_interval")          # not a mode of the reference
+    with pytest.raises(_niq.NiqError):                                              # not built
+        implicit_mlp_utils.generate_implicit_from_params(p, "slope_interval").min_distance_to_zero(p, LO, HI)
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_truncate", affine_n_truncate=8,
                                                          affine_truncate_policy="relative")
     with pytest.raises(_niq.NiqError):
@@ -506,7 +508,8 @@ def test_cast_rays_golden(case):
         assert n_evals == int(g["n_evals"])
 
 
-@pytest.mark.parametrize("name,mode,res", [("fox", "affine_fixed", 96), ("bunny", "affine_fixed", 48), ("hammer", "interval", 32)])
+@pytest.mark.parametrize("name,mode,res", [("fox", "affine_fixed", 96), ("bunny", "affine_fixed", 48), ("hammer", "interval", 32),
+                                           ("fox", "slope_interval", 24), ("fox", "sdf", 24)])
 def test_cast_rays_vs_oracle(name, mode, res):
     import queries
     import render
@@ -524,7 +527,7 @@ def test_cast_rays_vs_oracle(name, mode, res):
     np.testing.assert_array_equal(cnt[ok], ocnt[ok])
     np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL, atol=0)
     assert (hit == 0).any()
-    assert mode == "interval" or (hit > 0).any()      # interval bounds are so loose that rays crawl to the step limit
+    assert mode in ("interval", "sdf") or (hit > 0).any()      # interval bounds are so loose that rays crawl to the step limit
     if ok.all():
         assert n_evals == on_evals
 
