@@ -129,3 +129,72 @@ def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_
     dist.all_gather(parts, pack.to(dev), group=group)
     allp = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
     return allp[:, :3].copy(), allp[:, 3:].copy()
+
+
+def _gather_rows(local, world, rank, group, width, dtype):
+    """all_gather of per-rank (n_r, width) float32 blocks of different lengths -> list of arrays (one collective of
+    counts, one padded all_gather)."""
+    import torch
+    import torch.distributed as dist
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    cnt = torch.tensor([local.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    pack = torch.zeros((cap, width), dtype=dtype)
+    pack[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local))
+    parts = [torch.empty((cap, width), dtype=dtype, device=dev) for _ in range(world)]
+    dist.all_gather(parts, pack.to(dev), group=group)
+    return [p.cpu().numpy()[:c] for p, c in zip(parts, counts)]
+
+
+def closest_point_sharded(func, params, lower, upper, query_points, eps=0.001, batch_process_size=2 ** 26, cp_fn=None,
+                          group=None):
+    """closest_point with the QUERIES partitioned across ranks (contiguous ranges) and one gather of (dist, loc) =
+    16 B/query.  Exact only in the `batch_process_size >= stack` regime, where the reference's algorithm is
+    level-synchronous per query and the queries do not interact (with the default global window of 2048 the LIFO stack
+    couples them: SURVEY.md F6) -- hence the large default window here.  Every rank returns the full result."""
+    import torch
+    import torch.distributed as dist
+    if cp_fn is None:
+        import kd_tree
+        cp_fn = kd_tree.closest_point
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    q = np.ascontiguousarray(query_points, np.float32)
+    bounds = np.linspace(0, q.shape[0], world + 1).astype(np.int64)
+    mine = q[bounds[rank]:bounds[rank + 1]]
+    if mine.shape[0]:
+        d, loc = cp_fn(func, params, lower, upper, mine, eps=eps, batch_process_size=batch_process_size)
+    else:
+        d, loc = np.zeros(0, np.float32), np.zeros((0, 3), np.float32)
+    if world == 1:
+        return d, loc
+    parts = _gather_rows(np.concatenate((d[:, None], loc), axis=1).astype(np.float32), world, rank, group, 4, torch.float32)
+    allp = np.concatenate(parts)
+    return allp[:, 0].copy(), allp[:, 1:].copy()
+
+
+def find_any_intersection_batch_sharded(func_tuple, params_of, n_queries, lower, upper, eps, isect_fn=None, group=None):
+    """A BATCH of pairwise intersection queries (e.g. one per rigid transform) dealt round-robin to the ranks; a single
+    query does not shard (<= a few thousand nodes, global early exit: SURVEY.md 8(e) "replicas only").
+    `params_of(i)` -> params_tuple of query i.  -> (found (n,) bool, loc (n,3)) on every rank."""
+    import torch
+    import torch.distributed as dist
+    if isect_fn is None:
+        import kd_tree
+        isect_fn = kd_tree.find_any_intersection
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    mine = np.arange(rank, n_queries, world)
+    rows = np.zeros((len(mine), 5), np.float32)
+    for j, i in enumerate(mine):
+        found, _, _, loc = isect_fn(func_tuple, params_of(int(i)), lower, upper, eps)
+        rows[j] = (i, float(bool(found)), *np.asarray(loc, np.float32))
+    if world > 1:
+        rows = np.concatenate(_gather_rows(rows, world, rank, group, 5, torch.float32))
+    order = np.argsort(rows[:, 0], kind="stable")
+    rows = rows[order]
+    return rows[:, 1] > 0.5, rows[:, 2:].copy()

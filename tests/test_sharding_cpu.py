@@ -53,8 +53,17 @@ def _worker(rank, world, port, q):
 
     build = lambda f, p, lo, hi, split_depth: tree.construct_uniform_unknown_levelset_tree(f, p, lo, hi, split_depth=split_depth)
     lo, hi = sharding.tree_sharded(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), 9, top_depth=4, build_fn=build)
+    # closest point sharded by query (window >= stack regime) and a batch of intersection queries dealt round-robin
+    qp = np.random.default_rng(3).uniform(-1, 1, (5, 3)).astype(np.float32)
+    cp = lambda f, p, lo_, hi_, pts, eps, batch_process_size: tree.closest_point(f, p, lo_, hi_, pts, eps=eps, batch_process_size=batch_process_size)
+    cd, cl = sharding.closest_point_sharded(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), qp, eps=0.4,
+                                            batch_process_size=4096, cp_fn=cp)
+    shifts = [(0.0, 0.0, 0.0), (1.9, 0.0, 0.0), (0.3, 0.2, 0.0)]
+    params_of = lambda i: (params, net.prepend_op(params, net.spatial_transformation(np.eye(3, dtype=np.float32), np.array(shifts[i], np.float32))))
+    isect = lambda fs, ps, lo_, hi_, eps: tree.find_any_intersection(fs, ps, lo_, hi_, eps)
+    fi, fl = sharding.find_any_intersection_batch_sharded((octx, octx), params_of, 3, np.full(3, -1, np.float32), np.full(3, 1, np.float32), 0.1, isect_fn=isect)
     if rank == 0:
-        q.put((t, h, c, n_ev, lo, hi))
+        q.put((t, h, c, n_ev, lo, hi, cd, cl, fi, fl))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -68,7 +77,7 @@ def test_sharded_rays_and_tree_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    t, h, c, n_ev, lo, hi = q.get(timeout=500)
+    t, h, c, n_ev, lo, hi, cd, cl, fi, fl = q.get(timeout=500)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -87,3 +96,11 @@ def test_sharded_rays_and_tree_world2_gloo():
     canon = lambda a, b: np.unique(np.concatenate((a, b), axis=1), axis=0)
     np.testing.assert_array_equal(canon(lo, hi), canon(ref["unknown_node_lower"][v], ref["unknown_node_upper"][v]))
     assert lo.shape[0] == int(v.sum())
+    # closest point: per-query results of the sharded call equal the single-process call in the same regime
+    qp = np.random.default_rng(3).uniform(-1, 1, (5, 3)).astype(np.float32)
+    rd, rl = tree.closest_point(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), qp, eps=0.4, batch_process_size=4096)
+    np.testing.assert_array_equal(cd, rd)
+    np.testing.assert_array_equal(cl, rl)
+    # intersection batch: identity transform intersects, a shift of 1.9 does not
+    assert fi.shape == (3,) and bool(fi[0]) and not bool(fi[1]) and fl.shape == (3, 3)
+    assert np.all(fl[1] == -777.)
