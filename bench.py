@@ -303,7 +303,6 @@ def run_ours(args):
     gpu_launches = ctx.launch_count() - launches0
     total_ms = float(sum(step_ms))
     ray_steps = int(c_d.sum().item())
-    assert int((h_d != 0).sum().item()) == 0 or True
 
     # ---- e2e through the public API (host buffers) ----
     e2e_step()

@@ -445,9 +445,10 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
 
     niq_mlp* m = new niq_mlp();
     m->ctx = c;
+    struct MlpGuard { niq_mlp* m; bool ok = false; ~MlpGuard() { if (!ok) niq_mlp_destroy(m); } } guard{m};   // no leak on any error path
     int maxw = 8;
     for (size_t l = 0; l + 1 < raw.size(); ++l) maxw = std::max(maxw, raw[l].out);
-    if (maxw > 256) { delete m; return fail(NIQ_EUNSUPPORTED, "hidden width %d > 256", maxw); }
+    if (maxw > 256) return fail(NIQ_EUNSUPPORTED, "hidden width %d > 256", maxw);
     m->wmax = maxw <= 32 ? 32 : maxw <= 64 ? 64 : maxw <= 128 ? 128 : 256;
 
     std::vector<float> hw, hb;
@@ -458,7 +459,7 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
         L.dot = (l + 1 == raw.size());
         L.in_pad = l == 0 ? 4 : m->layers[l - 1].out_pad;
         L.out_pad = L.dot ? 1 : round_up(L.out_dim, 8);
-        if (!L.dot && raw[l].out == 1) { delete m; return fail(NIQ_EUNSUPPORTED, "hidden layer of width 1"); }
+        if (!L.dot && raw[l].out == 1) return fail(NIQ_EUNSUPPORTED, "hidden layer of width 1");
         L.w_off = hw.size();
         hw.resize(hw.size() + (size_t)L.in_pad * (L.dot ? 1 : L.out_pad), 0.f);
         for (int j = 0; j < L.in_dim; ++j)
@@ -498,7 +499,7 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
         const int row = L.dot ? 1 : L.out_pad;
         int kc_max = L.dot ? L.in_pad : std::max(8, (kChunkFloats / row) / 8 * 8);   // multiple of 8: pipelined main loop
         for (int k0 = 0; k0 < L.in_pad; k0 += kc_max) {
-            if (n_chunks >= kMaxChunks) { niq_mlp_destroy(m); return fail(NIQ_EUNSUPPORTED, "weight stream needs more than %d chunks", kMaxChunks); }
+            if (n_chunks >= kMaxChunks) return fail(NIQ_EUNSUPPORTED, "weight stream needs more than %d chunks", kMaxChunks);
             ChunkDev& C = nd.chunks[n_chunks++];
             C.k0 = k0; C.kc = std::min(kc_max, L.in_pad - k0);
             C.src = m->d_weights + L.w_off + (size_t)k0 * row;
@@ -516,6 +517,7 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
     nd.resident = 0;
     nd.w_region_floats = (int)hw.size() + kResidentPad;
     m->total_floats = (int)hw.size();
+    guard.ok = true;
     *out = m;
     return NIQ_OK;
 }
