@@ -343,6 +343,26 @@ def run_ours(args):
         tree_dev_ms = ctx.timer_stop()
         tr.close()
 
+    # ---- optional: the WHOLE 1920x1080 image once (this rank's share of it for N > 1), to check the sub-sample's rate ----
+    full_image = None
+    if args.full_image:
+        mine_full = sharding.rank_pixels(RES_X, RES_Y, TILE, rank, world, 1)
+        rf = torch.from_numpy(roots[mine_full]).to(dev)
+        df = torch.from_numpy(dirs[mine_full]).to(dev)
+        nf = int(mine_full.shape[0])
+        tf_ = torch.zeros(nf, dtype=torch.float32, device=dev)
+        hf = torch.zeros(nf, dtype=torch.int32, device=dev)
+        cf = torch.zeros(nf, dtype=torch.int32, device=dev)
+        barrier()
+        ctx.timer_start()
+        queries.cast_rays_device((func,), (params,), nf, rf.data_ptr(), df.data_ptr(), tf_.data_ptr(), hf.data_ptr(), cf.data_ptr(),
+                                 opts, want_n_evals=False, ctx=ctx)
+        ms_full = ctx.timer_stop()
+        barrier()
+        full_image = {"rays_this_rank": nf, "ms": ms_full, "rays_per_s_this_rank": nf / (ms_full * 1e-3),
+                      "ray_steps": int(cf.sum().item()), "hits": int((hf != 0).sum().item())}
+        del rf, df, tf_, hf, cf
+
     if world > 1:
         red = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
@@ -398,6 +418,8 @@ def run_ours(args):
             out["cpu_baseline"] = {"value": r.shape[0] / dt, "unit": "rays/s", "cores": nw, "kind": "port",
                                    "sample": f"{r.shape[0]} rays (whole 16x16 tiles, seed 0) x all 512 steps, {nw} processes x 1 BLAS thread",
                                    "ray_steps_per_s": st / dt}
+        if full_image is not None:
+            out["full_image"] = full_image
         if args.extra:
             out["extra"] = extra_metrics(ctx)
         print(json.dumps(out), flush=True)
@@ -499,6 +521,7 @@ def main():
     ap.add_argument("--tiles", type=int, default=74, help="16x16 ray tiles per GPU per step")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--extra", action="store_true", help="also time the sample-input configs (secondary numbers)")
+    ap.add_argument("--full-image", action="store_true", help="additionally cast the whole 1920x1080 image once (about a minute on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
