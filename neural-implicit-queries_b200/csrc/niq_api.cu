@@ -598,18 +598,25 @@ static int launch_eval_points_w(niq_ctx* c, NetDev net, int total_floats, const 
     CU(cudaGetLastError());
     return NIQ_OK;
 }
+template <int WMAX, class Tile>
+static int launch_cast_rays_wt(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, long long n, int interval,
+                               const float* roots, const float* dirs, float* t, int* hit, int* cnt,
+                               unsigned char* tie, unsigned long long* queue) {
+    using E = Engine<WMAX, Tile>;
+    const size_t smem = place_weights<E>(c, net, total_floats);
+    TRY(set_smem(k_cast_rays<WMAX, Tile>, smem));
+    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
+    LaunchTimer lt(c, 0);
+    k_cast_rays<WMAX, Tile><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
 template <int WMAX>
 static int launch_cast_rays_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, long long n, int interval,
                               const float* roots, const float* dirs, float* t, int* hit, int* cnt,
-                              unsigned char* tie, unsigned long long* queue) {
-    using E = Engine<WMAX, TileRay>;
-    const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_cast_rays<WMAX>, smem));
-    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
-    LaunchTimer lt(c, 0);
-    k_cast_rays<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
-    CU(cudaGetLastError());
-    return NIQ_OK;
+                              unsigned char* tie, unsigned long long* queue, bool slope = false) {
+    if (slope) return launch_cast_rays_wt<WMAX, TileRaySlope>(c, net, total_floats, o, n, 0, roots, dirs, t, hit, cnt, tie, queue);
+    return launch_cast_rays_wt<WMAX, TileRay>(c, net, total_floats, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
 }
 static int launch_classify_fixed(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
                                  int* label, float* lower, float* upper, unsigned char* tie) {
@@ -870,7 +877,8 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
     co.shrink = o->interval_shrink_fac; co.n_max_step = o->n_max_step; co.n_substeps = o->n_substeps;
     co.init_step = (1.0f * o->interval_init_size) * o->max_dist;     // reference src/queries.py:149
 
-    if (is_fixed_mode(&cfgs[0])) {
+    const bool slope = cfgs[0].mode == NIQ_MODE_SLOPE_INTERVAL;
+    if (is_fixed_mode(&cfgs[0]) || slope) {
         // concatenate the funcs' layer / chunk tables into one stream
         NetDev net{};
         int wmax = 32, total_floats = 0;
@@ -899,13 +907,13 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
         CU(cudaMemsetAsync(queue.p, 0, 8, c->stream));
         const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
         switch (wmax) {
-            case 32: TRY(launch_cast_rays_w<32>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
-            case 64: TRY(launch_cast_rays_w<64>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
-            case 128: TRY(launch_cast_rays_w<128>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
-            default: TRY(launch_cast_rays_w<256>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>())); break;
+            case 32: TRY(launch_cast_rays_w<32>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
+            case 64: TRY(launch_cast_rays_w<64>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
+            case 128: TRY(launch_cast_rays_w<128>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
+            default: TRY(launch_cast_rays_w<256>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
         }
     } else {
-        return fail(NIQ_EUNSUPPORTED, "cast_rays with affine_all / affine_truncate runs through the host-level stepping loop of the Python layer");
+        return fail(NIQ_EUNSUPPORTED, "cast_rays in this mode runs through the host-level stepping loop of the Python layer");
     }
 
     // N_evals of the reference (src/queries.py:137,164-173): lanes evaluated per iteration incl. bucket padding

@@ -160,12 +160,21 @@ struct TilePts {    // [P x 8]
 };
 struct TileSlope3 { // [P, C, C, C, W, W, W] : primal, slope centres, slope widths of one general box with <= 3 vectors;
                     // the width rows multiply |A| like the err row (reference src/slope_interval_layers.py:11-33)
-    static constexpr int RT = 7, NT = 1, rule = 2;
+    static constexpr int RT = 7, NT = 1, rule = 2, n_vec = 3;
     __host__ __device__ static constexpr bool is_err(int r) { return r >= 4; }
     __host__ __device__ static constexpr bool has_bias(int r) { return r == 0; }
     __host__ __device__ static constexpr bool is_pt(int) { return false; }
     __host__ __device__ static constexpr bool want_scale(int r) { return r == 0; }
     static constexpr int n_aff = 3, n_pts = 0;
+    static constexpr bool has_group = false;
+};
+struct TileRaySlope { // [P, C, W, pt, pt] : one ray step in slope_interval mode (v = 1) + f(start), f(start+eps)
+    static constexpr int RT = 5, NT = 2, rule = 2, n_vec = 1;
+    __host__ __device__ static constexpr bool is_err(int r) { return r == 2; }
+    __host__ __device__ static constexpr bool has_bias(int r) { return r == 0 || r >= 3; }
+    __host__ __device__ static constexpr bool is_pt(int r) { return r >= 3; }
+    __host__ __device__ static constexpr bool want_scale(int r) { return r == 0 || r >= 3; }
+    static constexpr int n_aff = 1, n_pts = 2;
     static constexpr bool has_group = false;
 };
 
@@ -503,18 +512,19 @@ struct Engine {
     __device__ __forceinline__ void epilogue(float (&acc)[ROWS][8], const float (&bias)[8]) const {
 #pragma unroll
         for (int n = 0; n < NT; ++n) {
-            if (Tile::rule == 2) {
-                // slope interval (reference src/slope_interval_layers.py:35-83, src/slope_interval.py:196-206):
+            if constexpr (Tile::rule == 2) {
+                // slope interval (reference src/slope_interval_layers.py:35-110, src/slope_interval.py:196-206):
                 // slope bounds C -+ W, primal bounds primal -+ sum_v max(upper, -lower), derivative bounds of the
-                // activation on them, interval product, re-centred
+                // activation on them, interval product, re-centred.  Rows: [P, C x n_vec, W x n_vec, ...]
+                constexpr int NV = Tile::n_vec;
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                     const float p = acc[n * RT][c] + bias[c];
-                    float sl[3], su[3], prad = 0.f;
+                    float sl[NV], su[NV], prad = 0.f;
 #pragma unroll
-                    for (int v = 0; v < 3; ++v) {
-                        sl[v] = acc[n * RT + 1 + v][c] - acc[n * RT + 4 + v][c];
-                        su[v] = acc[n * RT + 1 + v][c] + acc[n * RT + 4 + v][c];
+                    for (int v = 0; v < NV; ++v) {
+                        sl[v] = acc[n * RT + 1 + v][c] - acc[n * RT + 1 + NV + v][c];
+                        su[v] = acc[n * RT + 1 + v][c] + acc[n * RT + 1 + NV + v][c];
                         prad = prad + fmaxf(su[v], -sl[v]);
                     }
                     if (ACT != ACT_NONE) {
@@ -524,7 +534,7 @@ struct Engine {
                         else if (ACT == ACT_ELU) { dfl = fminf(expf(pl), 1.f); dfu = fminf(expf(pu), 1.f); }
                         else cos_bound(pl, pu, dfl, dfu);                 // sin: the derivative can be negative
 #pragma unroll
-                        for (int v = 0; v < 3; ++v) {
+                        for (int v = 0; v < NV; ++v) {
                             float nl = fminf(sl[v] * dfl, sl[v] * dfu), nu = fmaxf(su[v] * dfl, su[v] * dfu);
                             if (ACT == ACT_SIN) {                        // full interval product (:100-104)
                                 nl = fminf(fminf(nl, su[v] * dfl), su[v] * dfu);
@@ -532,7 +542,7 @@ struct Engine {
                             }
                             const float nc = 0.5f * (nl + nu);
                             acc[n * RT + 1 + v][c] = nc;
-                            acc[n * RT + 4 + v][c] = nu - nc;
+                            acc[n * RT + 1 + NV + v][c] = nu - nc;
                         }
                         acc[n * RT][c] = ACT == ACT_RELU ? fmaxf(p, 0.f) : ACT == ACT_ELU ? elu_f(p) : sinf(p);
                     } else {

@@ -328,13 +328,13 @@ struct CastOpts {
     int n_max_step, n_substeps;
 };
 
-template <int WMAX>
+template <int WMAX, class Tile = TileRay>
 __global__ void __launch_bounds__(kThreads, 1)
 k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, int interval_mode,
             const float* __restrict__ roots, const float* __restrict__ dirs,
             float* __restrict__ out_t, int* __restrict__ out_hit, int* __restrict__ out_count,
             unsigned char* __restrict__ out_tie, unsigned long long* __restrict__ queue) {
-    using E = Engine<WMAX, TileRay>;
+    using E = Engine<WMAX, Tile>;      // TileRay: [base, aff, err, pt, pt]; TileRaySlope: [primal, centre, width, pt, pt]
     extern __shared__ __align__(128) unsigned char smem[];
     E eng(net, smem);
     const int lane = eng.lane;
@@ -384,7 +384,10 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
                 const float te = t + o.hit_eps;
                 float4 rows[5];
                 rows[0] = make_float4(psx + hx, psy + hy, psz + hz, 0.f);
-                if (interval_mode) {
+                if (Tile::rule == 2) {                                   // slope_interval: centre = the half vector, width = 0
+                    rows[1] = make_float4(hx, hy, hz, 0.f);
+                    rows[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (interval_mode) {
                     rows[1] = make_float4(0.f, 0.f, 0.f, 0.f);
                     rows[2] = make_float4(fabsf(hx), fabsf(hy), fabsf(hz), 0.f);
                 } else {
@@ -412,7 +415,8 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
             __syncwarp();
             if (live) {
                 const float* d = eng.fin + lane * 8;
-                const float rad = fabsf(d[1]) + d[2];
+                // affine: rad = |aff| + err (src/affine.py:119-125); slope: max(C + W, -(C - W)) (src/slope_interval.py:201-206)
+                const float rad = Tile::rule == 2 ? fmaxf(d[1] + d[2], -(d[1] - d[2])) : fabsf(d[1]) + d[2];
                 const float lo = d[0] - rad, up = d[0] + rad;
                 const int lab = label_of(lo, up, 0.f);
                 can_step = can_step && (lab == SIGN_POSITIVE || lab == SIGN_NEGATIVE);

@@ -1,7 +1,7 @@
 """`queries` module surface of the reference for the hot path: get_default_cast_opts and cast_rays
 (/root/reference/src/queries.py:23-36, :39-175).
 
-interval / affine_fixed: ONE persistent CUDA kernel (csrc/niq_kernels.cuh k_cast_rays) marches every ray
+interval / affine_fixed / slope_interval: ONE persistent CUDA kernel (csrc/niq_kernels.cuh k_cast_rays) marches every ray
 to termination with an in-kernel work queue -- no per-iteration host round trip, no bucket padding.
 affine_all / affine_truncate: the reference's host-level iteration (one pass per step, order-preserving
 compaction) with the bound / point evaluations on the GPU (one CTA per ray segment, niq_grow.cuh)."""
@@ -51,7 +51,7 @@ def cast_rays(funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie=Fals
     if roots.ndim != 2 or roots.shape[1] != 3 or roots.shape != dirs.shape:
         raise ValueError("roots and dirs must both have shape (N,3)")
     modes = {f.ctx.mode for f in funcs_tuple}
-    if modes <= {"interval", "affine_fixed"} and len(modes) == 1:
+    if len(modes) == 1 and modes <= {"interval", "affine_fixed", "slope_interval"}:
         return _cast_rays_persistent(ctx, funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie)
     return _cast_rays_host_loop(ctx, funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie)
 
