@@ -223,3 +223,34 @@ def cast_rays(funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie=Fals
     if return_near_tie:
         return out_t, out_hit_id, out_count, N_evals, near_tie_out
     return out_t, out_hit_id, out_count, N_evals
+
+
+# ----------------------------------------------------------------------------------------------
+# the direct caller of cast_rays: normals + 'normal' shading + image assembly (render.py:53-165)
+# ----------------------------------------------------------------------------------------------
+
+def outward_normals(params_tuple, hit_pos, hit_ids, eps):
+    """render.py:53-90, method 'finite_differences'."""
+    hit_pos = np.ascontiguousarray(hit_pos, F32)
+    eps = F32(eps)
+    offsets = np.array(((+eps, -eps, -eps), (-eps, -eps, +eps), (-eps, +eps, -eps), (+eps, +eps, +eps)), F32)
+    x_pts = (hit_pos[:, None, :] + offsets[None, :, :]).astype(F32)
+    out = np.zeros_like(hit_pos)
+    for i_func, params in enumerate(params_tuple, start=1):
+        samples = net.eval_points(params, x_pts.reshape(-1, 3)).reshape(-1, 4)
+        grad = (offsets[None, :, :] * samples[:, :, None]).sum(axis=1, dtype=F32)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            grad = (grad / np.linalg.norm(grad, axis=-1, keepdims=True)).astype(F32)
+        out = np.where((np.asarray(hit_ids) == i_func)[:, None], grad, out).astype(F32)
+    return out
+
+
+def render_image(ctx_tuple, params_tuple, eye_pos, look_dir, up_dir, res, fov_deg, opts):
+    """render.py:94-150 with frustum=False, shading='normal', no tonemap."""
+    roots, dirs = generate_camera_rays(eye_pos, look_dir, up_dir, res=res, fov_deg=fov_deg)
+    t, hit, cnt, n_eval = cast_rays(ctx_tuple, params_tuple, roots, dirs, opts)
+    hit_pos = (roots + t[:, None] * dirs).astype(F32)
+    nrm = outward_normals(params_tuple, hit_pos, hit, opts["hit_eps"])
+    color = ((nrm + F32(1.)) / F32(2.)).astype(F32)
+    img = np.where((hit != 0)[:, None], color, np.ones((res * res, 3), F32)).astype(F32)
+    return img.reshape(res, res, 3), t.reshape(res, res), cnt.reshape(res, res), hit.reshape(res, res), n_eval

@@ -270,6 +270,19 @@ def case_pe(mode, n_trunc=8):
     return out
 
 
+def case_render(name, mode, res):
+    """render.render_image (src/render.py:94-150): frustum=False, shading='normal' -- image, depth, counts, hit ids."""
+    m = _ref_modules()
+    jnp, render = m["jnp"], m["render"]
+    func, params = _load(m, name, mode)
+    eye = jnp.array((2., 1., 2.))
+    look, up, left = render.look_at(eye)
+    opts = m["queries"].get_default_cast_opts()
+    img, depth, counts, hit_ids, n_eval, _ = render.render_image(func, params, eye, look, up, left, res, 30., False, opts, shading="normal")
+    return dict(img=np.array(img, np.float32), depth=np.array(depth, np.float32), counts=np.array(counts, np.int32),
+                hit_ids=np.array(hit_ids, np.int32), n_eval=np.int64(n_eval), res=res)
+
+
 def case_points(name):
     m = _ref_modules()
     jnp = m["jnp"]
@@ -374,6 +387,7 @@ for _n in SAMPLES:                                   # the sl
 CASES["tree_fox_slope_d12"] = (case_tree, ("fox", "slope_interval"), dict(split_depth=12, with_exterior_nodes=True))
 for _mode in ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval"):   # sin + encode ops
     CASES[f"pe_{_mode}"] = (case_pe, (_mode,))
+CASES["render_fox_fixed_r10"] = (case_render, ("fox", "affine_fixed", 10))      # the caller of cast_rays
 CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))
 CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))

@@ -921,3 +921,44 @@ def test_sample_surface_and_bulk_properties_vs_oracle():
     omass, ocen = otree.bulk_properties(octx("affine_fixed"), p, LO, HI, np.random.default_rng(11), n_expand=2000, n_sample=200000)
     assert abs(mass - omass) <= 2e-4 * omass and np.all(np.abs(cen - ocen) <= 2e-4)
     assert 0.01 < mass < 8.0 and np.all(np.abs(cen) < 1.0)
+
+
+# ---------------------------------------------------------------------------------------------------
+# the caller of cast_rays: render.render_image
+# ---------------------------------------------------------------------------------------------------
+
+def test_render_image_golden_and_oracle():
+    """render.render_image (src/render.py:94-150; frustum=False, shading='normal'): hit ids / counts / depth as cast_rays,
+    colours from finite-difference normals (4 GPU point evaluations eps=1e-3 apart per hit: tolerance 2e-3 absolute =
+    the point-value band over the difference magnitude)."""
+    import queries
+    import render
+    import _niq
+    p = sample_params("fox")
+    func = make(p, "affine_fixed")
+    g = golden("render_fox_fixed_r10")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    img, depth, cnt, hit, n_eval, _ = render.render_image(func, p, eye, look, up, left, int(g["res"]), 30.0, False, opts)
+    assert img.shape == (10, 10, 3) and img.dtype == np.float32 and hit.dtype == np.int32
+    np.testing.assert_array_equal(hit, g["hit_ids"])
+    np.testing.assert_array_equal(cnt, g["counts"])
+    assert n_eval == int(g["n_eval"])
+    np.testing.assert_allclose(depth, g["depth"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(img, g["img"], rtol=0, atol=2e-3)
+    # a larger image against the oracle
+    res = 64
+    img, depth, cnt, hit, n_eval, _ = render.render_image(func, p, eye, look, up, left, res, 30.0, False, opts)
+    oimg, odepth, ocnt, ohit, on = rays.render_image((octx("affine_fixed"),), (p,), eye, look, up, res, 30.0, opts)
+    same = (hit == ohit) & (cnt == ocnt)
+    assert same.mean() > 0.995
+    np.testing.assert_allclose(depth[same], odepth[same], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(img[same], oimg[same], rtol=0, atol=2e-3)
+    x = np.linspace(0, 1, 33, dtype=np.float32)                      # tonemap (src/render.py:152-158) is a pure formula
+    ref = ((x.astype(np.float64) * (1 + x.astype(np.float64) / 0.75 ** 2)) / (1 + x.astype(np.float64))) ** (1 / 2.2)
+    np.testing.assert_allclose(render.tonemap_image(x), ref, rtol=1e-5, atol=1e-7)
+    with pytest.raises(_niq.NiqError):
+        render.render_image(func, p, eye, look, up, left, 8, 30.0, True, opts)
+    with pytest.raises(ValueError):
+        render.render_image((func, func), (p,), eye, look, up, left, 8, 30.0, False, opts)

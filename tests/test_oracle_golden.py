@@ -300,3 +300,21 @@ def test_mc_tables_match_reference_hash():
     assert hashlib.sha256(tri.astype(np.int8).tobytes()).hexdigest() == mc_tables.TRI_TABLE_SHA256
     assert (tri[:, 15] == -1).all() and tri.max() == 11
     assert edges.shape == (12, 2) and vc.shape == (8, 3)
+
+
+def test_render_image():
+    """The caller of cast_rays (src/render.py:53-165): camera rays -> cast_rays -> finite-difference
+    normals -> 'normal' shading.  Normals are differences of 4 point values eps=1e-3 apart, so the colour tolerance
+    is the point-value band (1e-5 relative of the evaluation scale) divided by the difference magnitude."""
+    g = golden("render_fox_fixed_r10")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = rays.look_at(eye)
+    img, depth, cnt, hit, n_eval = rays.render_image((net.AffineContext("affine_fixed"),), (sample_params("fox"),), eye, look, up,
+                                                     int(g["res"]), 30.0, rays.get_default_cast_opts())
+    np.testing.assert_array_equal(hit, g["hit_ids"])
+    np.testing.assert_array_equal(cnt, g["counts"])
+    assert n_eval == int(g["n_eval"])
+    np.testing.assert_allclose(depth, g["depth"], rtol=RTOL, atol=0)
+    assert (g["hit_ids"] != 0).sum() > 10
+    np.testing.assert_allclose(img, g["img"], rtol=0, atol=2e-3)
+    assert np.all(img[g["hit_ids"] == 0] == 1.0)
