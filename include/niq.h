@@ -169,6 +169,28 @@ int niq_cast_rays(niq_ctx* ctx, int32_t n_funcs, const niq_mlp* const* mlps, con
                   const niq_cast_opts* opts, int64_t n, const float* roots, const float* dirs,
                   float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals, uint8_t* near_tie, int mem);
 
+/* ---- cast_rays_frustum: src/queries.py:178-587 -------------------------------------------------- */
+/* cam_params of src/queries.py:197 (root_pos, look_dir, up_dir, left_dir, fov_x, fov_y, res_x, res_y).  The caller
+ * evaluates the transcendental constants once in float32: tan(deg2rad(fov)/2) (src/render.py:17-24) and
+ * deg2rad(fov)/2 (src/queries.py:352-353).                                                              */
+typedef struct niq_camera {
+    float root[3], look[3], up[3], left[3];
+    float tan_half_fov_x, tan_half_fov_y;
+    float half_fov_x, half_fov_y;
+    int32_t res_x, res_y;
+} niq_camera;
+
+/* Frusta of pixels [x0, y0, x1, y1) marched together and split when they grow wider than refine_width_fac * step or
+ * stall (src/queries.py:350-360); init_ranges (n_init,4) int32 = the initial tiles (src/queries.py:495-501).
+ * Outputs are (res_x, res_y) row-major images as the reference returns them (pixel (x,y) at x*res_y + y):
+ * t f32, hit_id i32, count i32 (the truncated fractional step count), near_tie u8 optional.  n_evals = the
+ * reference's N_evals (padded array length of every marching iteration, src/queries.py:523), replayed from per-iteration
+ * termination / split counts.  interval and affine_fixed modes (one persistent kernel with a device work queue).  */
+int niq_cast_rays_frustum(niq_ctx* ctx, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
+                          const niq_cast_opts* opts, const niq_camera* cam, float refine_width_fac,
+                          int64_t n_init, const int32_t* init_ranges,
+                          float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals, uint8_t* near_tie, int mem);
+
 /* ---- level-set kd-tree: src/kd_tree.py:19-218 -------------------------------------------------- */
 enum { NIQ_TREE_INTERIOR = 1, NIQ_TREE_EXTERIOR = 2 };  /* flags: also collect NEGATIVE / POSITIVE nodes */
 /* split_depth < 0 means "None"; node_terminate_thresh <= 0 means "None" (at least one must be given).

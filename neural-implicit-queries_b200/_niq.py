@@ -30,7 +30,7 @@ SYMBOLS = (
     "niq_ctx_launch_count", "niq_ctx_timer_start", "niq_ctx_timer_stop", "niq_ctx_kernel_ms",
     "niq_ctx_kernel_timing", "niq_ctx_exec_macs", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
     "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
-    "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_tree_build", "niq_tree_build_roots", "niq_tree_count",
+    "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_cast_rays_frustum", "niq_tree_build", "niq_tree_build_roots", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
     "niq_mesh_count", "niq_mesh_copy", "niq_mesh_destroy", "niq_mc_tables", "niq_find_any_intersection",
     "niq_closest_point",
@@ -51,6 +51,13 @@ class CastOpts(C.Structure):
     _fields_ = [("hit_eps", C.c_float), ("max_dist", C.c_float), ("n_max_step", C.c_int32),
                 ("n_substeps", C.c_int32), ("safety_factor", C.c_float), ("interval_grow_fac", C.c_float),
                 ("interval_shrink_fac", C.c_float), ("interval_init_size", C.c_float)]
+
+
+class Camera(C.Structure):
+    """niq_camera (include/niq.h): cam_params of src/queries.py:197 with the float32 transcendental constants precomputed."""
+    _fields_ = [("root", C.c_float * 3), ("look", C.c_float * 3), ("up", C.c_float * 3), ("left", C.c_float * 3),
+                ("tan_half_fov_x", C.c_float), ("tan_half_fov_y", C.c_float), ("half_fov_x", C.c_float),
+                ("half_fov_y", C.c_float), ("res_x", C.c_int32), ("res_y", C.c_int32)]
 
 
 class NiqError(RuntimeError):

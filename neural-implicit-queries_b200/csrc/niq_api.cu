@@ -849,6 +849,32 @@ static int next_bucket(long long s, long long* out) {    // reference src/bucket
     return fail(NIQ_EINVAL, "max bucket size exceeded");
 }
 
+// concatenate the funcs' layer / chunk tables into one weight stream (cast_rays / cast_rays_frustum evaluate every func per step)
+static int concat_nets(int n_funcs, const niq_mlp* const* mlps, NetDev& net, int& wmax, int& total_floats) {
+    wmax = 32; total_floats = 0;
+    for (int f = 0; f < n_funcs; ++f) {
+        const NetDev& s = mlps[f]->net;
+        if (net.n_layers + s.n_layers > kMaxLayers || net.n_chunks + s.n_chunks > kMaxChunks)
+            return fail(NIQ_EUNSUPPORTED, "too many layers / weight chunks for one cast_rays launch");
+        for (int l = 0; l < s.n_layers; ++l) {
+            LayerDev L = s.layers[l];
+            L.chunk_begin += net.n_chunks; L.chunk_end += net.n_chunks;
+            net.layers[net.n_layers + l] = L;
+        }
+        for (int k = 0; k < s.n_chunks; ++k) {
+            net.chunks[net.n_chunks + k] = s.chunks[k];
+            net.chunks[net.n_chunks + k].smem_off += total_floats;     // nets sit one after the other when resident
+        }
+        total_floats += mlps[f]->total_floats;
+        net.n_layers += s.n_layers; net.n_chunks += s.n_chunks;
+        net.tie_rel = std::max(net.tie_rel, s.tie_rel);
+        net.sparse = f == 0 ? s.sparse : std::min(net.sparse, s.sparse);
+        wmax = std::max(wmax, mlps[f]->wmax);
+    }
+    net.n_nets = n_funcs;
+    return NIQ_OK;
+}
+
 extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
                              const niq_cast_opts* o, int64_t n, const float* roots, const float* dirs, float* t,
                              int32_t* hit_id, int32_t* count, int64_t* n_evals, uint8_t* tie, int mem) {
@@ -879,29 +905,9 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
 
     const bool slope = cfgs[0].mode == NIQ_MODE_SLOPE_INTERVAL;
     if (is_fixed_mode(&cfgs[0]) || slope) {
-        // concatenate the funcs' layer / chunk tables into one stream
         NetDev net{};
         int wmax = 32, total_floats = 0;
-        for (int f = 0; f < n_funcs; ++f) {
-            const NetDev& s = mlps[f]->net;
-            if (net.n_layers + s.n_layers > kMaxLayers || net.n_chunks + s.n_chunks > kMaxChunks)
-                return fail(NIQ_EUNSUPPORTED, "too many layers / weight chunks for one cast_rays launch");
-            for (int l = 0; l < s.n_layers; ++l) {
-                LayerDev L = s.layers[l];
-                L.chunk_begin += net.n_chunks; L.chunk_end += net.n_chunks;
-                net.layers[net.n_layers + l] = L;
-            }
-            for (int k = 0; k < s.n_chunks; ++k) {
-                net.chunks[net.n_chunks + k] = s.chunks[k];
-                net.chunks[net.n_chunks + k].smem_off += total_floats;     // nets sit one after the other when resident
-            }
-            total_floats += mlps[f]->total_floats;
-            net.n_layers += s.n_layers; net.n_chunks += s.n_chunks;
-            net.tie_rel = std::max(net.tie_rel, s.tie_rel);
-            net.sparse = f == 0 ? s.sparse : std::min(net.sparse, s.sparse);
-            wmax = std::max(wmax, mlps[f]->wmax);
-        }
-        net.n_nets = n_funcs;
+        TRY(concat_nets(n_funcs, mlps, net, wmax, total_floats));
         DevBuf queue(c);
         TRY(queue.alloc(8));
         CU(cudaMemsetAsync(queue.p, 0, 8, c->stream));
@@ -939,6 +945,127 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
             if (nb < cur) cur = nb;
         }
         *n_evals = evals;
+    }
+    TRY(dt.flush(c)); TRY(dh.flush(c)); TRY(dc.flush(c)); TRY(dtie.flush(c));
+    FINAL_SYNC(c);
+    return NIQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// cast_rays_frustum (src/queries.py:178-587)
+// ------------------------------------------------------------------------------------------------
+template <int WMAX>
+static int launch_cast_frustum_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, const FrustCam& cam, int interval,
+                                 const FrustQueue& q, long long n_pixels) {
+    using E = Engine<WMAX, TileFrustum>;
+    const size_t smem = place_weights<E>(c, net, total_floats);
+    TRY(set_smem(k_cast_frustum<WMAX>, smem));
+    const long long n_pass = (n_pixels + E::CTA_TILES - 1) / E::CTA_TILES;
+    LaunchTimer lt(c, 0);
+    k_cast_frustum<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, cam, interval, q);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+
+extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
+                                     const niq_cast_opts* o, const niq_camera* cam, float refine_width_fac, int64_t n_init,
+                                     const int32_t* init_ranges, float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals,
+                                     uint8_t* tie, int mem) {
+    if (!c || !mlps || !cfgs || !o || !cam || n_funcs < 1 || n_init < 1 || !init_ranges)
+        return fail(NIQ_EINVAL, "niq_cast_rays_frustum: bad argument");
+    if (cam->res_x < 1 || cam->res_y < 1) return fail(NIQ_EINVAL, "niq_cast_rays_frustum: image resolution must be positive");
+    if (!t || !hit_id || !count) return fail(NIQ_EINVAL, "niq_cast_rays_frustum: NULL array");
+    if (o->n_substeps < 1) return fail(NIQ_EINVAL, "n_substeps must be >= 1");
+    for (int f = 0; f < n_funcs; ++f) {
+        if (!mlps[f]) return fail(NIQ_EINVAL, "mlp %d is NULL", f);
+        TRY(check_cfg(&cfgs[f]));
+        if (cfgs[f].mode != cfgs[0].mode) return fail(NIQ_EUNSUPPORTED, "all funcs of one cast_rays_frustum call must use the same mode");
+    }
+    if (!is_fixed_mode(&cfgs[0]))
+        return fail(NIQ_EUNSUPPORTED, "cast_rays_frustum in this mode runs through the host-level loop of the Python layer");
+    const long long n = (long long)cam->res_x * cam->res_y;
+    if (n_init > n) return fail(NIQ_EINVAL, "niq_cast_rays_frustum: more initial frusta than pixels");
+    if (n_evals) *n_evals = 0;
+    CU(cudaSetDevice(c->device));
+    timer_touch(c);
+    InBuf dinit(c); OutBuf dt(c), dh(c), dc(c), dtie(c);
+    // the initial ranges always come from the host (a few hundred tiles), whatever `mem` says about the images
+    TRY(dinit.stage(c, init_ranges, (size_t)n_init * 16, NIQ_MEM_HOST));
+    TRY(dt.stage(c, t, (size_t)n * 4, mem));
+    TRY(dh.stage(c, hit_id, (size_t)n * 4, mem));
+    TRY(dc.stage(c, count, (size_t)n * 4, mem));
+    TRY(dtie.stage(c, tie, (size_t)n, mem));
+
+    CastOpts co{};
+    co.hit_eps = o->hit_eps; co.max_dist = o->max_dist; co.safety = o->safety_factor; co.grow = o->interval_grow_fac;
+    co.shrink = o->interval_shrink_fac; co.n_max_step = o->n_max_step; co.n_substeps = o->n_substeps;
+    co.init_step = (1.0f * o->interval_init_size) * o->max_dist;     // reference src/queries.py:505
+    FrustCam fc{};
+    for (int d = 0; d < 3; ++d) { fc.root[d] = cam->root[d]; fc.look[d] = cam->look[d]; fc.up[d] = cam->up[d]; fc.left[d] = cam->left[d]; }
+    fc.tan_x = cam->tan_half_fov_x; fc.tan_y = cam->tan_half_fov_y; fc.half_fov_x = cam->half_fov_x; fc.half_fov_y = cam->half_fov_y;
+    fc.res_x = cam->res_x; fc.res_y = cam->res_y; fc.refine_fac = refine_width_fac;
+
+    NetDev net{};
+    int wmax = 32, total_floats = 0;
+    TRY(concat_nets(n_funcs, mlps, net, wmax, total_floats));
+
+    // every frustum covers >= 1 pixel and a split only partitions pixels: <= n records are ever pushed, <= n finish
+    FrustQueue q{};
+    q.cap = n_init + n;
+    q.n_bins = o->n_max_step / o->n_substeps + 3;
+    DevBuf rec(c), ready(c), ctrl(c), fin(c), hist(c);
+    TRY(rec.alloc((size_t)q.cap * sizeof(FrustRec)));
+    TRY(ready.alloc((size_t)q.cap * 4));
+    TRY(ctrl.alloc(8 * 8));
+    TRY(fin.alloc((size_t)n * sizeof(FrustFin)));
+    TRY(hist.alloc((size_t)q.n_bins * 8));
+    CU(cudaMemsetAsync(ready.p, 0, (size_t)q.cap * 4, c->stream));
+    CU(cudaMemsetAsync(hist.p, 0, (size_t)q.n_bins * 8, c->stream));
+    q.rec = rec.as<FrustRec>(); q.ready = ready.as<int>(); q.ctrl = ctrl.as<unsigned long long>(); q.fin = fin.as<FrustFin>();
+    q.hist_term = hist.as<unsigned int>(); q.hist_ref = hist.as<unsigned int>() + q.n_bins;
+    {
+        LaunchTimer lt(c, 1);
+        k_frustum_init<<<(int)((n_init + 255) / 256), 256, 0, c->stream>>>(q, dinit.as<int>(), n_init, co.init_step);
+        CU(cudaGetLastError());
+    }
+    const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
+    switch (wmax) {
+        case 32: TRY(launch_cast_frustum_w<32>(c, net, total_floats, co, fc, interval, q, n)); break;
+        case 64: TRY(launch_cast_frustum_w<64>(c, net, total_floats, co, fc, interval, q, n)); break;
+        case 128: TRY(launch_cast_frustum_w<128>(c, net, total_floats, co, fc, interval, q, n)); break;
+        default: TRY(launch_cast_frustum_w<256>(c, net, total_floats, co, fc, interval, q, n)); break;
+    }
+    {
+        LaunchTimer lt(c, 1);
+        const int blocks = (int)std::min<long long>((n + 7) / 8, 8ll * c->prop.multiProcessorCount);
+        k_frustum_fill<<<std::max(blocks, 1), 256, 0, c->stream>>>(q.fin, q.ctrl, fc.res_y, dt.as<float>(), dh.as<int>(), dc.as<int>(),
+                                                                   dtie.as<unsigned char>());
+        CU(cudaGetLastError());
+    }
+    // N_evals (src/queries.py:523-548): the padded array length of every marching iteration, replayed from the
+    // per-iteration termination / split counts
+    {
+        std::vector<unsigned int> h(2 * (size_t)q.n_bins);
+        unsigned long long hc[8];
+        TRY(read_back(c, hist.p, h.size() * 4, h.data()));
+        TRY(read_back(c, ctrl.p, sizeof(hc), hc));
+        if (hc[4] != 0ull) return fail(NIQ_ECAPACITY, "cast_rays_frustum: work queue overflow (%llu records)", hc[4]);
+        if (hc[2] != 0ull) return fail(NIQ_ECUDA, "cast_rays_frustum: %llu frusta left unfinished", hc[2]);
+        if (n_evals) {
+            long long size = n_init, empty_start = n_init, alive = n_init, evals = 0;
+            for (int k = 0; k < q.n_bins; ++k) {
+                evals += size;
+                const long long n_valid = alive - (long long)h[k];
+                if (n_valid <= 0) break;
+                const long long n_ref = (long long)h[q.n_bins + k];
+                long long nb;
+                TRY(next_bucket(n_valid + n_ref, &nb));
+                if (empty_start + n_ref > size || nb < size) { size = nb; empty_start = n_valid; }
+                empty_start += n_ref;
+                alive = n_valid + n_ref;
+            }
+            *n_evals = evals;
+        }
     }
     TRY(dt.flush(c)); TRY(dh.flush(c)); TRY(dc.flush(c)); TRY(dtie.flush(c));
     FINAL_SYNC(c);

@@ -149,6 +149,15 @@ struct TileRay {    // [B, A, E, P, P] : one ray step = segment bound (v=1) + f(
     static constexpr int n_aff = 1, n_pts = 2;
     static constexpr bool has_group = true;
 };
+struct TileFrustum { // [B, A, A, A, E, P, P] : one frustum step = general-box bound (v=3) + f(start), f(start+eps) on the mid ray
+    static constexpr int RT = 7, NT = 1, rule = 0;
+    __host__ __device__ static constexpr bool is_err(int r) { return r == 4; }
+    __host__ __device__ static constexpr bool has_bias(int r) { return r == 0 || r >= 5; }
+    __host__ __device__ static constexpr bool is_pt(int r) { return r >= 5; }
+    __host__ __device__ static constexpr bool want_scale(int r) { return r == 0 || r >= 5; }
+    static constexpr int n_aff = 3, n_pts = 2;
+    static constexpr bool has_group = true;
+};
 struct TilePts {    // [P x 8]
     static constexpr int RT = 8, NT = 1, rule = 1;
     __host__ __device__ static constexpr bool is_err(int) { return false; }

@@ -462,6 +462,267 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
     eng.drain();
 }
 
+// ------------------------------------------------------------------------------------------------
+// cast_rays_frustum (interval / affine_fixed): persistent frustum marching with a device work queue.
+// Reference src/queries.py:178-587.  One warp slot = one frustum of pixels [x0,x1) x [y0,y1); lane s keeps the state
+// of slot s.  A frustum that must be split keeps child A in its slot and pushes child B on the global queue; empty
+// slots hold a ticket (an index of the queue) and adopt the record once it has been published.  Every frustum carries
+// its own iteration index k, so nothing is iteration-synchronous; the per-iteration termination / split counts that the
+// reference's N_evals depends on are histogrammed by k.  A finished frustum goes to the `fin` list; k_frustum_fill paints
+// its pixels (= the reference's split-to-single-pixel phase :558-577 followed by the pixel scatter :442-456).
+// ------------------------------------------------------------------------------------------------
+struct FrustRec { int x0, y0, x1, y1; float t, step, count; int k_tie; };      // k_tie = k | (near_tie << 30)
+struct FrustFin { int x0, y0, x1, y1; float t; int hit_id, count, tie; };
+struct FrustCam {
+    float root[3], look[3], up[3], left[3];
+    float tan_x, tan_y, half_fov_x, half_fov_y;
+    int res_x, res_y;
+    float refine_fac;
+};
+struct FrustQueue {
+    FrustRec* rec; int* ready; long long cap;          // records + publication flags
+    unsigned long long* ctrl;                          // [0] tickets issued, [1] records pushed, [2] outstanding frusta, [3] finished, [4] overflow
+    FrustFin* fin;
+    unsigned int* hist_term; unsigned int* hist_ref; int n_bins;
+};
+
+__global__ void k_frustum_init(FrustQueue q, const int* __restrict__ ranges, long long n_init, float init_step) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < n_init) {
+        FrustRec r;
+        r.x0 = ranges[4 * i]; r.y0 = ranges[4 * i + 1]; r.x1 = ranges[4 * i + 2]; r.y1 = ranges[4 * i + 3];
+        r.t = 0.f; r.step = init_step; r.count = 0.f; r.k_tie = 0;
+        q.rec[i] = r;
+        q.ready[i] = 1;
+    }
+    if (i == 0) { q.ctrl[0] = 0ull; q.ctrl[1] = (unsigned long long)n_init; q.ctrl[2] = (unsigned long long)n_init; q.ctrl[3] = 0ull; q.ctrl[4] = 0ull; }
+}
+
+// render.camera_ray (src/render.py:17-24): normalize(look + left*(tx*tan_x) + up*(ty*tan_y))
+__device__ __forceinline__ void frustum_cam_ray(const FrustCam& cam, float tx, float ty, float r[3]) {
+    const float a = tx * cam.tan_x, b = ty * cam.tan_y;
+    float p[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) p[d] = (cam.look[d] + cam.left[d] * a) + cam.up[d] * b;
+    const float len = sqrtf((p[0] * p[0] + p[1] * p[1]) + p[2] * p[2]);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) r[d] = p[d] / len;
+}
+
+template <int WMAX>
+__global__ void __launch_bounds__(kThreads, 1)
+k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __grid_constant__ FrustCam cam, int interval_mode,
+               FrustQueue q) {
+    using E = Engine<WMAX, TileFrustum>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    E eng(net, smem);
+    const int lane = eng.lane;
+    const bool owner = lane < E::SLOTS;
+    volatile unsigned long long* ctrl = q.ctrl;
+
+    // per-slot state (meaningful in lanes < SLOTS)
+    bool live = false, tie = false;
+    long long ticket = -1;
+    int x0 = 0, y0 = 0, x1 = 1, y1 = 1, k = 0;
+    float t = 0.f, step = 0.f, count = 0.f;
+    // per-iteration substep state (src/queries.py:317-322)
+    int sub = 0, n_inner = 0, hit_id = 0;
+    bool is_hit = false, demands = false;
+
+    bool cta_live = true;
+    while (cta_live) {
+        // ---- empty slots take a ticket, then adopt the record once it is published ----
+        const unsigned need = __ballot_sync(0xffffffffu, owner && !live && ticket < 0);
+        if (need) {
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(q.ctrl, (unsigned long long)__popc(need));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (owner && !live && ticket < 0) ticket = (long long)base + __popc(need & ((1u << lane) - 1u));
+        }
+        if (owner && !live && ticket >= 0 && ticket < q.cap) {
+            if (*((volatile int*)(q.ready + ticket)) != 0) {
+                __threadfence();
+                const int4 a = __ldcg(reinterpret_cast<const int4*>(q.rec + ticket));
+                const float4 b = __ldcg(reinterpret_cast<const float4*>(q.rec + ticket) + 1);
+                x0 = a.x; y0 = a.y; x1 = a.z; y1 = a.w;
+                t = b.x; step = b.y; count = b.z;
+                const int kt = __float_as_int(b.w);
+                k = kt & 0x3fffffff; tie = (kt >> 30) & 1;
+                live = true; ticket = -1;
+                sub = 0; n_inner = 0; hit_id = 0; is_hit = false; demands = false;
+            }
+        }
+        if (eng.resident && !__any_sync(0xffffffffu, live)) {
+            // nothing to evaluate in this warp: leave when every frustum has finished, else wait for work
+            if (ctrl[2] == 0ull) break;
+            __nanosleep(256);
+            continue;
+        }
+
+        // ---- frustum geometry (src/queries.py:272-315); recomputed per pass, it is a few hundred flops ----
+        float mid[3] = {0.f, 0.f, 0.f}, rf[3] = {0.f, 0.f, 0.f}, uf[3] = {0.f, 0.f, 0.f}, t_adj = 0.f;
+        if (live) {
+            const float dx = (float)cam.res_x + 1.f, dy = (float)cam.res_y + 1.f;
+            const float xc_lo = (2.f * (float)x0) / dx - 1.f, xc_up = (2.f * (float)(x1 - 1)) / dx - 1.f;
+            const float yc_lo = (2.f * (float)y0) / dy - 1.f, yc_up = (2.f * (float)(y1 - 1)) / dy - 1.f;
+            float r_uu[3], r_lu[3], r_ul[3], r_ll[3];
+            frustum_cam_ray(cam, xc_up, yc_up, r_uu);
+            frustum_cam_ray(cam, xc_lo, yc_up, r_lu);
+            frustum_cam_ray(cam, xc_up, yc_lo, r_ul);
+            frustum_cam_ray(cam, xc_lo, yc_lo, r_ll);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) mid[d] = 0.5f * (r_uu[d] + r_ll[d]);
+            const float len = sqrtf((mid[0] * mid[0] + mid[1] * mid[1]) + mid[2] * mid[2]);
+#pragma unroll
+            for (int d = 0; d < 3; ++d) mid[d] = mid[d] / len;
+            const float expand = 1.f / len;                 // the spherical cap reaches a little beyond the flat box
+            t_adj = (t + step) * expand;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                rf[d] = ((r_uu[d] - r_lu[d]) * t_adj) / 2.f;
+                uf[d] = ((r_uu[d] - r_ul[d]) * t_adj) / 2.f;
+            }
+        }
+
+        // ---- one substep: all funcs share t; can_step = AND, hit_id = last func whose signs differ ----
+        bool can_step = !is_hit;
+        if (live && !is_hit) n_inner += 1;
+        int l0 = 0;
+        for (int f = 0; f < net.n_nets; ++f) {
+            int l1 = l0;
+            while (!net.layers[l1].last_of_net) ++l1;
+            ++l1;
+            if (live) {
+                const float cm = 0.5f * (t + t_adj), cv = 0.5f * (t_adj - t), te = t + o.hit_eps;
+                float4 rows[7];
+                rows[0] = make_float4(cam.root[0] + cm * mid[0], cam.root[1] + cm * mid[1], cam.root[2] + cm * mid[2], 0.f);
+                const float4 v0 = make_float4(cv * mid[0], cv * mid[1], cv * mid[2], 0.f);
+                const float4 v1 = make_float4(rf[0], rf[1], rf[2], 0.f), v2 = make_float4(uf[0], uf[1], uf[2], 0.f);
+                if (interval_mode) {
+                    rows[1] = rows[2] = rows[3] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    rows[4] = make_float4((fabsf(v0.x) + fabsf(v1.x)) + fabsf(v2.x), (fabsf(v0.y) + fabsf(v1.y)) + fabsf(v2.y),
+                                          (fabsf(v0.z) + fabsf(v1.z)) + fabsf(v2.z), 0.f);
+                } else {
+                    rows[1] = v0; rows[2] = v1; rows[3] = v2;
+                    rows[4] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                rows[5] = make_float4(cam.root[0] + t * mid[0], cam.root[1] + t * mid[1], cam.root[2] + t * mid[2], 0.f);
+                rows[6] = make_float4(cam.root[0] + te * mid[0], cam.root[1] + te * mid[1], cam.root[2] + te * mid[2], 0.f);
+                float* dst = eng.act + lane * 7 * E::G::S;
+#pragma unroll
+                for (int r = 0; r < 7; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
+            }
+            __syncwarp();
+            float out[E::ROWS], ps[E::ROWS];
+            eng.run_net(l0, l1, out, ps);
+            if (eng.cg == 0) {        // hand base, radius, the two point values and their scales to the slot's owner lane
+                float* d = eng.fin + eng.t * 8;
+                d[0] = out[0];
+                d[1] = ((fabsf(out[1]) + fabsf(out[2])) + fabsf(out[3])) + out[4];
+                d[2] = out[5]; d[3] = out[6];
+                d[4] = ps[0]; d[5] = ps[5]; d[6] = ps[6];
+            }
+            __syncwarp();
+            if (live) {
+                const float* d = eng.fin + lane * 8;
+                const float lo = d[0] - d[1], up = d[0] + d[1];
+                const int lab = label_of(lo, up, 0.f);
+                can_step = can_step && (lab == SIGN_POSITIVE || lab == SIGN_NEGATIVE);
+                const float v0 = d[2], v1 = d[3];
+                const int s0 = (v0 > 0.f) - (v0 < 0.f), s1 = (v1 > 0.f) - (v1 < 0.f);
+                const bool this_hit = (s0 != s1) || (v0 != v0) || (v1 != v1);   // sign(nan)=nan != anything
+                if (this_hit) hit_id = f + 1;
+                is_hit = is_hit || this_hit;
+                tie = tie || bound_near_tie(lo, up, 0.f, d[4], net.tie_rel) || fabsf(v0) <= kNearTieRel * d[5] ||
+                      fabsf(v1) <= kNearTieRel * d[6];
+            }
+            __syncwarp();
+            l0 = l1;
+        }
+
+        // ---- step update (src/queries.py:249-266), then the end-of-iteration logic (:339-365) ----
+        if (live) {
+            const bool single = (x0 + 1 == x1) && (y0 + 1 == y1);
+            const float this_step = can_step ? step : (single ? o.hit_eps : 0.f);   // larger frusta may not inch forward
+            if (!is_hit) t = t + this_step * o.safety;
+            step = can_step ? step * o.grow : step * o.shrink;
+            demands = demands || (step < o.hit_eps) || is_hit;
+            step = fmaxf(step, o.hit_eps);
+            sub += 1;
+            if (is_hit) {
+                // the remaining substeps re-evaluate the same points: t and hit_id stay, the step keeps shrinking
+                for (; sub < o.n_substeps; ++sub) step = fmaxf(step * o.shrink, o.hit_eps);
+            }
+            if (sub >= o.n_substeps) {
+                const int w = x1 - x0, h = y1 - y0, area = w * h;
+                count = count + (float)n_inner * (1.0f / (float)area);
+                const bool done = (is_hit && area == 1) || (t > o.max_dist) || (k * o.n_substeps >= o.n_max_step);
+                const int kb = k < q.n_bins ? k : q.n_bins - 1;
+                if (done) {
+                    const unsigned long long fi = atomicAdd(q.ctrl + 3, 1ull);
+                    FrustFin fr;
+                    fr.x0 = x0; fr.y0 = y0; fr.x1 = x1; fr.y1 = y1; fr.t = t; fr.hit_id = hit_id; fr.count = (int)count; fr.tie = tie ? 1 : 0;
+                    q.fin[fi] = fr;
+                    atomicAdd(q.hist_term + kb, 1u);
+                    __threadfence();
+                    atomicAdd(q.ctrl + 2, ~0ull);                       // outstanding -= 1
+                    live = false;
+                } else {
+                    const float wx = (2.f * sinf((cam.half_fov_x * (float)w) / (float)cam.res_x)) * t;
+                    const float wy = (2.f * sinf((cam.half_fov_y * (float)h) / (float)cam.res_y)) * t;
+                    const float lim = cam.refine_fac * step;
+                    const bool refine = (wx > lim || wy > lim || demands) && (w > 1 || h > 1);
+                    k += 1;
+                    if (refine) {
+                        // split the longer pixel axis, x on ties (src/queries.py:371-432); B goes to the queue
+                        atomicAdd(q.hist_ref + kb, 1u);
+                        FrustRec b;
+                        b.x0 = x0; b.y0 = y0; b.x1 = x1; b.y1 = y1;
+                        if (w >= h) { const int xm = (x0 + x1) / 2; b.x0 = xm; x1 = xm; }
+                        else { const int ym = (y0 + y1) / 2; b.y0 = ym; y1 = ym; }
+                        b.t = t; b.step = step; b.count = count; b.k_tie = k | (tie ? (1 << 30) : 0);
+                        atomicAdd(q.ctrl + 2, 1ull);                    // outstanding += 1, before the record can be adopted
+                        const unsigned long long bi = atomicAdd(q.ctrl + 1, 1ull);
+                        if ((long long)bi < q.cap) {
+                            reinterpret_cast<int4*>(q.rec + bi)[0] = make_int4(b.x0, b.y0, b.x1, b.y1);
+                            reinterpret_cast<float4*>(q.rec + bi)[1] = make_float4(b.t, b.step, b.count, __int_as_float(b.k_tie));
+                            __threadfence();
+                            *((volatile int*)(q.ready + bi)) = 1;
+                        } else {
+                            atomicAdd(q.ctrl + 4, 1ull);                // cannot happen: at most one frustum per pixel
+                            atomicAdd(q.ctrl + 2, ~0ull);
+                        }
+                    }
+                    sub = 0; n_inner = 0; hit_id = 0; is_hit = false; demands = false;
+                }
+            }
+        }
+        // ---- does anyone still have work?  resident weights: each warp retires on its own (above);
+        //      streamed weights: every warp takes part in the ring's hand-over, so the CTA leaves together ----
+        if (!eng.resident) cta_live = __syncthreads_or((live || ctrl[2] != 0ull) ? 1 : 0) != 0;
+    }
+    eng.drain();
+}
+
+// a finished frustum paints its pixels: out[x * res_y + y] (the reference's (res_x, res_y) images)
+__global__ void k_frustum_fill(const FrustFin* __restrict__ fin, const unsigned long long* __restrict__ ctrl, int res_y,
+                               float* __restrict__ out_t, int* __restrict__ out_hit, int* __restrict__ out_count,
+                               unsigned char* __restrict__ out_tie) {
+    const long long n_fin = (long long)ctrl[3];
+    const long long warp0 = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = (gridDim.x * (long long)blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (long long i = warp0; i < n_fin; i += n_warps) {
+        const FrustFin f = fin[i];
+        const int h = f.y1 - f.y0, area = (f.x1 - f.x0) * h;
+        for (int p = lane; p < area; p += 32) {
+            const long long pix = (long long)(f.x0 + p / h) * res_y + (f.y0 + p % h);
+            out_t[pix] = f.t; out_hit[pix] = f.hit_id; out_count[pix] = f.count;
+            if (out_tie) out_tie[pix] = (unsigned char)f.tie;
+        }
+    }
+}
+
 // iteration histogram for N_evals (reference src/queries.py:164): hist[it] = #rays finishing in iteration it
 __global__ void k_iter_hist(const int* __restrict__ count, long long n, int n_substeps, int n_bins,
                             unsigned long long* __restrict__ hist) {

@@ -2,8 +2,8 @@
 (:229-242): the INPUT generator of cast_rays (BASELINE configs 1 and 5).  Host NumPy float32.
 `res_y` generalises the reference's square image (same per-axis formula) for 1920x1080.
 Also the direct CALLER of cast_rays: outward_normals (:53-90, finite differences: 4 GPU point
-evaluations per hit), shade_image 'normal' (:160-165), tonemap_image (:152-158) and render_image (:94-150) without the
-frustum path and without matcap shading (image assets, GUI)."""
+evaluations per hit), shade_image 'normal' (:160-165), tonemap_image (:152-158) and render_image (:94-150), both the ray and the frustum
+branch, without matcap shading (image assets, GUI)."""
 import numpy as np
 
 import geometry
@@ -102,11 +102,14 @@ def render_image(funcs_tuple, params_tuple, eye_pos, look_dir, up_dir, left_dir,
     if not isinstance(params_tuple, tuple): params_tuple = (params_tuple,)
     if len(params_tuple) != len(funcs_tuple):
         raise ValueError("render_image tuple arguments should all be same length")
-    if frustum:
-        import _niq
-        raise _niq.NiqError(_niq.NIQ_EUNSUPPORTED, "cast_rays_frustum is not built (SURVEY 8(f) row 1): use frustum=False")
     ray_roots, ray_dirs = generate_camera_rays(eye_pos, look_dir, up_dir, res=res, fov_deg=fov_deg)
-    t_raycast, hit_ids, counts, n_eval = queries.cast_rays(funcs_tuple, params_tuple, ray_roots, ray_dirs, opts, ctx=ctx)
+    if frustum:
+        cam_params = eye_pos, look_dir, up_dir, left_dir, fov_deg, fov_deg, res, res
+        t_raycast, hit_ids, counts, n_eval = queries.cast_rays_frustum(funcs_tuple, params_tuple, cam_params, opts, ctx=ctx)
+        # the (res_x, res_y) images are transposed into the ray order of generate_camera_rays (src/render.py:124-126)
+        t_raycast, hit_ids, counts = t_raycast.transpose().flatten(), hit_ids.transpose().flatten(), counts.transpose().flatten()
+    else:
+        t_raycast, hit_ids, counts, n_eval = queries.cast_rays(funcs_tuple, params_tuple, ray_roots, ray_dirs, opts, ctx=ctx)
     hit_pos = (ray_roots + t_raycast[:, None] * ray_dirs).astype(np.float32)
     hit_normals = outward_normals(funcs_tuple, params_tuple, hit_pos, hit_ids, opts['hit_eps'], ctx=ctx)
     hit_color = shade_image(shading, ray_dirs, hit_pos, hit_normals, hit_ids, up_dir, matcaps, shading_color_tuple, shading_color_func)

@@ -73,8 +73,8 @@ def eye(n, dtype=None):
     return narrow(_np.eye(n, dtype=_np.float32 if dtype is None else _dt(dtype)))
 
 
-def linspace(start, stop, num=50):
-    """JAX's float32 linspace: start*(1-s) + stop*s for s = i/(num-1), endpoint appended."""
+def linspace(start, stop, num=50, dtype=None):
+    """JAX's float32 linspace: start*(1-s) + stop*s for s = i/(num-1), endpoint appended; integer dtype: floor."""
     start = _np.asarray(_raw(start), _np.float32)
     stop = _np.asarray(_raw(stop), _np.float32)
     div = _np.float32(num - 1)
@@ -83,6 +83,8 @@ def linspace(start, stop, num=50):
     s = s.reshape(shp)
     body = (start[None, ...] * (_np.float32(1) - s)).astype(_np.float32) + (stop[None, ...] * s).astype(_np.float32)
     out = _np.concatenate((body, _np.broadcast_to(stop, start.shape)[None, ...]), axis=0)
+    if dtype is not None and _np.issubdtype(_dt(dtype), _np.integer):
+        out = _np.floor(out).astype(_dt(dtype))
     return narrow(out)
 
 

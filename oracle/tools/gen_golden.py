@@ -283,6 +283,28 @@ def case_render(name, mode, res):
                 hit_ids=np.array(hit_ids, np.int32), n_eval=np.int64(n_eval), res=res)
 
 
+def case_frustum(names, mode, res, n_side, n_substeps=1):
+    """queries.cast_rays_frustum (src/queries.py:178-587): out_t / out_hit_id / out_count as returned, (res_x, res_y)."""
+    m = _ref_modules()
+    jnp, queries, render = m["jnp"], m["queries"], m["render"]
+    funcs, params = [], []
+    for nm in names:
+        f, p = _load(m, nm, mode)
+        funcs.append(f)
+        params.append(p)
+    eye = jnp.array((2.0, 1.0, 2.0))
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = n_side
+    opts["n_substeps"] = n_substeps
+    cam = (eye, look, up, left, 30., 30., res, res)
+    with np.errstate(all="ignore"):
+        t, hit, cnt, n_evals = queries.cast_rays_frustum(tuple(funcs), tuple(params), cam, opts)
+    return dict(eye=np.array(eye), look=np.array(look), up=np.array(up), left=np.array(left), res=res, n_side=n_side,
+                n_substeps=n_substeps, out_t=np.array(t, np.float32), out_hit_id=np.array(hit, np.int32),
+                out_count=np.array(cnt, np.int32), n_evals=int(n_evals))
+
+
 def case_points(name):
     m = _ref_modules()
     jnp = m["jnp"]
@@ -388,6 +410,9 @@ CASES["tree_fox_slope_d12"] = (case_tree, ("fox", "slope_interval"), dict(split_
 for _mode in ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval"):   # sin + encode ops
     CASES[f"pe_{_mode}"] = (case_pe, (_mode,))
 CASES["render_fox_fixed_r10"] = (case_render, ("fox", "affine_fixed", 10))      # the caller of cast_rays
+CASES["frust_fox_fixed_r12_s4"] = (case_frustum, (("fox",), "affine_fixed", 12, 4))
+CASES["frust_fox_bunny_interval_r10_s2_sub2"] = (case_frustum, (("fox", "bunny"), "interval", 10, 2, 2))
+CASES["frust_hammer_fixed_r9_s3_sub3"] = (case_frustum, (("hammer",), "affine_fixed", 9, 3, 3))
 CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))
 CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))

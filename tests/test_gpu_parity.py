@@ -958,7 +958,110 @@ def test_render_image_golden_and_oracle():
     x = np.linspace(0, 1, 33, dtype=np.float32)                      # tonemap (src/render.py:152-158) is a pure formula
     ref = ((x.astype(np.float64) * (1 + x.astype(np.float64) / 0.75 ** 2)) / (1 + x.astype(np.float64))) ** (1 / 2.2)
     np.testing.assert_allclose(render.tonemap_image(x), ref, rtol=1e-5, atol=1e-7)
-    with pytest.raises(_niq.NiqError):
-        render.render_image(func, p, eye, look, up, left, 8, 30.0, True, opts)
     with pytest.raises(ValueError):
         render.render_image((func, func), (p,), eye, look, up, left, 8, 30.0, False, opts)
+
+
+# ---------------------------------------------------------------------------------------------------
+# cast_rays_frustum
+# ---------------------------------------------------------------------------------------------------
+FRUSTUM_CASES = {
+    "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
+    "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
+    "frust_fox_bunny_interval_r10_s2_sub2": (("fox", "bunny"), "interval"),
+}
+
+
+def _frustum_inputs(g):
+    import queries
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = int(g["n_side"])
+    opts["n_substeps"] = int(g["n_substeps"])
+    res = int(g["res"])
+    return (g["eye"], g["look"], g["up"], g["left"], 30.0, 30.0, res, res), opts
+
+
+@pytest.mark.parametrize("case", sorted(FRUSTUM_CASES))
+def test_cast_rays_frustum_golden(case):
+    """The persistent frustum kernel (k_cast_frustum) and the host-level loop, both against the unmodified reference."""
+    import queries
+    names, mode = FRUSTUM_CASES[case]
+    g = golden(case)
+    cam, opts = _frustum_inputs(g)
+    ps = tuple(sample_params(n) for n in names)
+    funcs = tuple(make(p, mode) for p in ps)
+    import _niq
+    host_loop = lambda *a: queries._cast_rays_frustum_host_loop(_niq.default_context(), *a)
+    for impl in (queries.cast_rays_frustum, host_loop):
+        t, hit, cnt, n_evals, tie = impl(funcs, ps, cam, opts, True)
+        assert t.shape == g["out_t"].shape and t.dtype == np.float32 and hit.dtype == np.int32 and cnt.dtype == np.int32
+        ok = ~tie
+        assert ok.mean() > 0.6
+        np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
+        np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
+        np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
+        if not tie.any():
+            assert n_evals == int(g["n_evals"])
+
+
+@pytest.mark.parametrize("name,mode,res,n_side,n_sub", [("fox", "affine_fixed", 64, 16, 1), ("bunny", "affine_fixed", 40, 8, 1),
+                                                        ("birdcage_occ", "interval", 24, 4, 2), ("fox", "affine_truncate", 16, 4, 1),
+                                                        ("fox", "slope_interval", 16, 4, 1)])
+def test_cast_rays_frustum_vs_oracle(name, mode, res, n_side, n_sub):
+    """Larger images against the oracle.  A pixel is compared when no decision of its frustum chain was inside the 1e-5
+    band in EITHER implementation (a flipped split changes the whole subtree of pixels)."""
+    import queries
+    import render
+    p = sample_params(name)
+    func = make(p, mode)
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = n_side
+    opts["n_substeps"] = n_sub
+    cam = (eye, look, up, left, 30.0, 30.0, res, res)
+    t, hit, cnt, n_evals, tie = queries.cast_rays_frustum((func,), (p,), cam, opts, return_near_tie=True)
+    ot, ohit, ocnt, on, otie = rays.cast_rays_frustum((octx(mode),), (p,), cam, opts, return_near_tie=True)
+    ok = ~(tie | otie)
+    assert ok.mean() > 0.9
+    np.testing.assert_array_equal(hit[ok], ohit[ok])
+    np.testing.assert_array_equal(cnt[ok], ocnt[ok])
+    np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL, atol=0)
+    assert (hit != 0).any() and (hit == 0).any()
+    if not (tie | otie).any():
+        assert n_evals == on
+
+
+def test_cast_rays_frustum_wide_streamed_and_render():
+    """A 256-wide net (weights streamed through the ring: every warp of a CTA leaves together) against the oracle, the
+    frustum branch of render.render_image, and argument errors."""
+    import queries
+    import render
+    p = net.random_mlp([3, 256, 256, 256, 1], "relu", seed=5)
+    func = make(p, "affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = 4
+    opts["n_max_step"] = 24
+    cam = (eye, look, up, left, 30.0, 30.0, 20, 20)
+    t, hit, cnt, n_evals, tie = queries.cast_rays_frustum((func,), (p,), cam, opts, return_near_tie=True)
+    ot, ohit, ocnt, on, otie = rays.cast_rays_frustum((octx("affine_fixed"),), (p,), cam, opts, return_near_tie=True)
+    ok = ~(tie | otie)
+    assert ok.mean() > 0.9
+    np.testing.assert_array_equal(hit[ok], ohit[ok])
+    np.testing.assert_array_equal(cnt[ok], ocnt[ok])
+    np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL, atol=0)
+
+    pf = sample_params("fox")
+    ff = make(pf, "affine_fixed")
+    o2 = queries.get_default_cast_opts()
+    img, depth, counts, hit_ids, n_eval, _ = render.render_image(ff, pf, eye, look, up, left, 32, 30.0, True, o2)
+    t2, h2, c2, n2 = queries.cast_rays_frustum((ff,), (pf,), (eye, look, up, left, 30.0, 30.0, 32, 32), o2)
+    np.testing.assert_array_equal(hit_ids, h2.T)            # render transposes the (res_x, res_y) images (src/render.py:124-126)
+    np.testing.assert_array_equal(depth, t2.T)
+    assert img.shape == (32, 32, 3) and n_eval == n2 and np.all(img[hit_ids == 0] == 1.0)
+    with pytest.raises(ValueError):
+        queries.cast_rays_frustum((ff,), (pf,), (eye, look, up, left, 30.0, 30.0, 8, 8), o2)      # n_side_init 16 > res
+    with pytest.raises(ValueError):
+        queries.cast_rays_frustum((ff, ff), (pf,), (eye, look, up, left, 30.0, 30.0, 32, 32), o2)

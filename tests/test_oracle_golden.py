@@ -318,3 +318,61 @@ def test_render_image():
     assert (g["hit_ids"] != 0).sum() > 10
     np.testing.assert_allclose(img, g["img"], rtol=0, atol=2e-3)
     assert np.all(img[g["hit_ids"] == 0] == 1.0)
+
+
+FRUSTUM_CASES = {
+    "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
+    "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
+    "frust_fox_bunny_interval_r10_s2_sub2": (("fox", "bunny"), "interval"),
+}
+
+
+def frustum_inputs(g):
+    opts = rays.get_default_cast_opts()
+    opts["n_side_init"] = int(g["n_side"])
+    opts["n_substeps"] = int(g["n_substeps"])
+    res = int(g["res"])
+    return (g["eye"], g["look"], g["up"], g["left"], 30.0, 30.0, res, res), opts
+
+
+@pytest.mark.parametrize("case", sorted(FRUSTUM_CASES))
+def test_cast_rays_frustum(case):
+    """queries.cast_rays_frustum (src/queries.py:178-587): (res_x, res_y) images of t / hit id /
+    truncated fractional step count and N_evals, against the unmodified reference."""
+    names, mode = FRUSTUM_CASES[case]
+    g = golden(case)
+    cam, opts = frustum_inputs(g)
+    iters = []
+    t, hit, cnt, n_evals, tie = rays.cast_rays_frustum(tuple(net.AffineContext(mode) for _ in names), tuple(sample_params(n) for n in names),
+                                                       cam, opts, return_near_tie=True, iter_counts=iters)
+    ok = ~tie
+    assert ok.mean() > 0.6 and t.shape == (int(g["res"]), int(g["res"]))
+    np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
+    np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
+    np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
+    if mode == "affine_fixed":
+        assert (g["out_hit_id"] != 0).any()
+    else:                                                    # the loose interval bounds crawl: every frustum ends on the step limit
+        assert (g["out_count"] > 100).all()
+    if not tie.any():
+        assert n_evals == int(g["n_evals"])
+    # host logic of the product (no GPU needed): initial tiles and the N_evals replay from per-iteration counts
+    import queries
+    n_side = int(g["n_side"])
+    init = queries._initial_frusta(int(g["res"]), int(g["res"]), n_side)
+    assert init.shape == (n_side * n_side, 4) and init.dtype == np.int32
+    assert ((init[:, 2] - init[:, 0]) * (init[:, 3] - init[:, 1])).sum() == int(g["res"]) ** 2
+    assert queries._frustum_n_evals(n_side * n_side, [a for a, _ in iters], [b for _, b in iters]) == n_evals
+
+
+def test_initial_frusta_uneven_tiles():
+    """src/queries.py:495-501 with a resolution the tile count does not divide: floor of the float32 linspace."""
+    import queries
+    init = queries._initial_frusta(50, 37, 16)
+    xt = np.floor(np.linspace(0, 50, 17, dtype=np.float32)).astype(np.int32)
+    yt = np.floor(np.linspace(0, 37, 17, dtype=np.float32)).astype(np.int32)
+    np.testing.assert_array_equal(init[:16, 0], xt[:-1])
+    np.testing.assert_array_equal(init[:16, 2], xt[1:])
+    np.testing.assert_array_equal(init[::16, 1], yt[:-1])
+    np.testing.assert_array_equal(init[::16, 3], yt[1:])
+    assert ((init[:, 2] - init[:, 0]) * (init[:, 3] - init[:, 1])).sum() == 50 * 37
