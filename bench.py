@@ -456,6 +456,13 @@ def extra_metrics(ctx):
     dt, r = timed(lambda: queries.cast_rays((f,), (p,), roots, dirs, queries.get_default_cast_opts(), ctx=ctx))
     ex["cfg1_fox_512x512_cast_rays"] = {"rays_per_s": roots.shape[0] / dt, "ray_steps_per_s": int(r[2].sum()) / dt, "ms": dt * 1e3,
                                         "hits": int((r[1] > 0).sum()), "tflops_algorithmic": 10 * 7296 * int(r[2].sum()) / dt / 1e12}
+    # the frustum variant of the same image (src/queries.py:178-587): frusta of pixels marched together, then split
+    look, up, left = render.look_at(eye)
+    for res in (512, 1024):
+        cam = (eye, look, up, left, 30., 30., res, res)
+        dt, r = timed(lambda: queries.cast_rays_frustum((f,), (p,), cam, queries.get_default_cast_opts(), ctx=ctx))
+        ex[f"cfg1_fox_{res}x{res}_cast_rays_frustum"] = {"pixels_per_s": res * res / dt, "ms": dt * 1e3, "hits": int((r[1] > 0).sum()),
+                                                        "n_evals_reference_count": int(r[3])}
     p = mlps["bunny"]
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
     for depth in (12, 21):
