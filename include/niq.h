@@ -185,11 +185,15 @@ typedef struct niq_camera {
  * Outputs are (res_x, res_y) row-major images as the reference returns them (pixel (x,y) at x*res_y + y):
  * t f32, hit_id i32, count i32 (the truncated fractional step count), near_tie u8 optional.  n_evals = the
  * reference's N_evals (padded array length of every marching iteration, src/queries.py:523), replayed from per-iteration
- * termination / split counts.  interval and affine_fixed modes (one persistent kernel with a device work queue).  */
+ * termination / split counts.  iter_counts (HOST, optional): those counts, int64[2 * (n_max_step / n_substeps + 3)] =
+ * terminated per iteration, then split per iteration (a sharded caller sums them over the ranks before the replay).
+ * Pixels outside the initial tiles are left zero.  interval and affine_fixed modes (one persistent kernel with a
+ * device work queue).                                                                                     */
 int niq_cast_rays_frustum(niq_ctx* ctx, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
                           const niq_cast_opts* opts, const niq_camera* cam, float refine_width_fac,
                           int64_t n_init, const int32_t* init_ranges,
-                          float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals, uint8_t* near_tie, int mem);
+                          float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals, int64_t* iter_counts,
+                          uint8_t* near_tie, int mem);
 
 /* ---- level-set kd-tree: src/kd_tree.py:19-218 -------------------------------------------------- */
 enum { NIQ_TREE_INTERIOR = 1, NIQ_TREE_EXTERIOR = 2 };  /* flags: also collect NEGATIVE / POSITIVE nodes */

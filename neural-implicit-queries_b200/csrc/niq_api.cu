@@ -970,7 +970,7 @@ static int launch_cast_frustum_w(niq_ctx* c, NetDev net, int total_floats, const
 extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
                                      const niq_cast_opts* o, const niq_camera* cam, float refine_width_fac, int64_t n_init,
                                      const int32_t* init_ranges, float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals,
-                                     uint8_t* tie, int mem) {
+                                     int64_t* iter_counts, uint8_t* tie, int mem) {
     if (!c || !mlps || !cfgs || !o || !cam || n_funcs < 1 || n_init < 1 || !init_ranges)
         return fail(NIQ_EINVAL, "niq_cast_rays_frustum: bad argument");
     if (cam->res_x < 1 || cam->res_y < 1) return fail(NIQ_EINVAL, "niq_cast_rays_frustum: image resolution must be positive");
@@ -995,6 +995,12 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
     TRY(dh.stage(c, hit_id, (size_t)n * 4, mem));
     TRY(dc.stage(c, count, (size_t)n * 4, mem));
     TRY(dtie.stage(c, tie, (size_t)n, mem));
+
+    // pixels outside the initial tiles (a rank's share of a sharded image) stay zero
+    CU(cudaMemsetAsync(dt.dev, 0, (size_t)n * 4, c->stream));
+    CU(cudaMemsetAsync(dh.dev, 0, (size_t)n * 4, c->stream));
+    CU(cudaMemsetAsync(dc.dev, 0, (size_t)n * 4, c->stream));
+    if (dtie.dev) CU(cudaMemsetAsync(dtie.dev, 0, (size_t)n, c->stream));
 
     CastOpts co{};
     co.hit_eps = o->hit_eps; co.max_dist = o->max_dist; co.safety = o->safety_factor; co.grow = o->interval_grow_fac;
@@ -1051,6 +1057,7 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
         TRY(read_back(c, ctrl.p, sizeof(hc), hc));
         if (hc[4] != 0ull) return fail(NIQ_ECAPACITY, "cast_rays_frustum: work queue overflow (%llu records)", hc[4]);
         if (hc[2] != 0ull) return fail(NIQ_ECUDA, "cast_rays_frustum: %llu frusta left unfinished", hc[2]);
+        if (iter_counts) for (size_t i = 0; i < h.size(); ++i) iter_counts[i] = (int64_t)h[i];
         if (n_evals) {
             long long size = n_init, empty_start = n_init, alive = n_init, evals = 0;
             for (int k = 0; k < q.n_bins; ++k) {

@@ -213,9 +213,12 @@ def _frustum_n_evals(n_init, n_term, n_refine):
     return n_evals
 
 
-def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie=False, ctx=None):
+def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie=False, ctx=None, init_ranges=None,
+                      iter_counts=None):
     """src/queries.py:465-587.  cam_params = (root_pos, look_dir, up_dir, left_dir, fov_x, fov_y, res_x, res_y)
-    -> (out_t (res_x,res_y) f32, out_hit_id i32, out_count i32, N_evals[, near_tie bool])."""
+    -> (out_t (res_x,res_y) f32, out_hit_id i32, out_count i32, N_evals[, near_tie bool]).
+    Extras for the multi-GPU partition (sharding.cast_rays_frustum_sharded): init_ranges (k,4) int32 replaces the initial
+    tiles (pixels outside them stay zero); iter_counts, a list, receives (terminated, split) of every iteration."""
     ctx = ctx or _niq.default_context()
     if isinstance(funcs_tuple, list): funcs_tuple = tuple(funcs_tuple)
     if isinstance(params_tuple, list): params_tuple = tuple(params_tuple)
@@ -225,21 +228,29 @@ def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, in_opts, return_nea
     res_x, res_y = int(cam_params[6]), int(cam_params[7])
     if n_side < 1 or n_side > min(res_x, res_y):
         raise ValueError("cast_rays_frustum: n_side_init must be in 1..min(res_x, res_y)")
+    if init_ranges is None:
+        init_ranges = _initial_frusta(res_x, res_y, n_side)
+    init_ranges = np.ascontiguousarray(init_ranges, np.int32).reshape(-1, 4)
     modes = {f.ctx.mode for f in funcs_tuple}
-    if len(modes) == 1 and modes <= {"interval", "affine_fixed"}:
-        return _cast_rays_frustum_persistent(ctx, funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie)
-    return _cast_rays_frustum_host_loop(ctx, funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie)
+    impl = _cast_rays_frustum_persistent if len(modes) == 1 and modes <= {"interval", "affine_fixed"} else _cast_rays_frustum_host_loop
+    return impl(ctx, funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie, init_ranges, iter_counts)
 
 
-def _cast_rays_frustum_persistent(ctx, funcs_tuple, params_tuple, cam_params, opts, return_near_tie):
+def _cast_rays_frustum_persistent(ctx, funcs_tuple, params_tuple, cam_params, opts, return_near_tie, init=None, iter_counts=None):
     nf = len(funcs_tuple)
     mlps = [ctx.mlp(p) for p in params_tuple]
     handles = (C.c_void_p * nf)(*[m.handle for m in mlps])
     cfgs = (_niq.ModeCfg * nf)(*[_niq.mode_cfg(f.ctx) for f in funcs_tuple])
     o = _opts_struct(opts)
     cam = _frustum_cam(cam_params)
-    init = _initial_frusta(cam.res_x, cam.res_y, int(opts['n_side_init']))
+    if init is None:
+        init = _initial_frusta(cam.res_x, cam.res_y, int(opts['n_side_init']))
     n = cam.res_x * cam.res_y
+    n_bins = int(opts['n_max_step']) // int(opts['n_substeps']) + 3
+    iters = np.zeros(2 * n_bins, np.int64)
+    if init.shape[0] == 0:                                   # a rank without tiles (more ranks than tiles)
+        z = np.zeros((cam.res_x, cam.res_y), np.float32)
+        return (z, z.astype(np.int32), z.astype(np.int32), 0) + ((z.astype(bool),) if return_near_tie else ())
     t = np.zeros(n, np.float32)
     hit = np.zeros(n, np.int32)
     cnt = np.zeros(n, np.int32)
@@ -247,15 +258,18 @@ def _cast_rays_frustum_persistent(ctx, funcs_tuple, params_tuple, cam_params, op
     n_evals = C.c_int64(0)
     _niq.check(_niq.lib().niq_cast_rays_frustum(ctx.handle, C.c_int32(nf), handles, cfgs, C.byref(o), C.byref(cam),
                                                 C.c_float(opts['refine_width_fac']), C.c_int64(init.shape[0]), _niq.ptr(init),
-                                                _niq.ptr(t), _niq.ptr(hit), _niq.ptr(cnt), C.byref(n_evals), _niq.ptr(tie),
-                                                C.c_int(_niq.MEM_HOST)))
+                                                _niq.ptr(t), _niq.ptr(hit), _niq.ptr(cnt), C.byref(n_evals), _niq.ptr(iters),
+                                                _niq.ptr(tie), C.c_int(_niq.MEM_HOST)))
+    if iter_counts is not None:
+        last = int(np.nonzero(iters[:n_bins] + iters[n_bins:])[0].max()) + 1 if iters.any() else 0
+        iter_counts.extend(zip(iters[:last].tolist(), iters[n_bins:n_bins + last].tolist()))
     shp = (cam.res_x, cam.res_y)
     if return_near_tie:
         return t.reshape(shp), hit.reshape(shp), cnt.reshape(shp), int(n_evals.value), tie.reshape(shp).astype(bool)
     return t.reshape(shp), hit.reshape(shp), cnt.reshape(shp), int(n_evals.value)
 
 
-def _cast_rays_frustum_host_loop(ctx, funcs_tuple, params_tuple, cam_params, opts, return_near_tie):
+def _cast_rays_frustum_host_loop(ctx, funcs_tuple, params_tuple, cam_params, opts, return_near_tie, init=None, iter_counts=None):
     """The reference's host-level iteration over a compact list of live frusta (no padding entries; N_evals is replayed
     from the per-iteration counts), bounds and point values on the GPU.  Serves the modes without a persistent kernel."""
     import mlp
@@ -273,7 +287,7 @@ def _cast_rays_frustum_host_loop(ctx, funcs_tuple, params_tuple, cam_params, opt
                  + up[None, :] * (ty * tan_y).astype(f32)[:, None]).astype(f32)
         return (plane / np.sqrt((plane * plane).sum(axis=-1, keepdims=True, dtype=f32))).astype(f32)
 
-    rng = _initial_frusta(res_x, res_y, int(opts['n_side_init']))
+    rng = _initial_frusta(res_x, res_y, int(opts['n_side_init'])) if init is None else np.array(init, np.int32).reshape(-1, 4)
     n_init = rng.shape[0]
     t = np.zeros(n_init, f32)
     size = (np.ones(n_init, f32) * f32(opts['interval_init_size']) * f32(opts['max_dist'])).astype(f32)
@@ -352,6 +366,8 @@ def _cast_rays_frustum_host_loop(ctx, funcs_tuple, params_tuple, cam_params, opt
         t = np.concatenate((t[keep], t[refine])); size = np.concatenate((size[keep], size[refine]))
         count = np.concatenate((count[keep], count[refine])); tie = np.concatenate((tie[keep], tie[refine]))
     N_evals = _frustum_n_evals(n_init, n_term, n_refine)
+    if iter_counts is not None:
+        iter_counts.extend(zip(n_term, n_refine))
     if return_near_tie:
         return out_t, out_hit, out_count, N_evals, out_tie
     return out_t, out_hit, out_count, N_evals

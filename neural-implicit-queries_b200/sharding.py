@@ -72,6 +72,41 @@ def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y
     return out_t, out_h, out_c, int(ev.item())
 
 
+def cast_rays_frustum_sharded(funcs_tuple, params_tuple, cam_params, opts, cast_fn=None, group=None):
+    """cast_rays_frustum with the INITIAL TILES (src/queries.py:495-501) dealt round-robin to the ranks of `group`: a frustum
+    never leaves its initial tile, so the ranks share no state.  Every rank marches its own tiles (pixels outside them
+    stay zero), one all_reduce(SUM) of the three (res_x, res_y) images = 12 B/pixel assembles the result on every rank, and
+    one more of the per-iteration (terminated, split) counts lets each rank replay the reference's N_evals for the WHOLE
+    image.  `cast_fn(funcs, params, cam, opts, init_ranges, iter_counts)` defaults to queries.cast_rays_frustum."""
+    import torch
+    import torch.distributed as dist
+    import queries
+    if cast_fn is None:
+        cast_fn = lambda f, p, cam, o, init, it: queries.cast_rays_frustum(f, p, cam, o, init_ranges=init, iter_counts=it)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    res_x, res_y = int(cam_params[6]), int(cam_params[7])
+    init = queries._initial_frusta(res_x, res_y, int(opts['n_side_init']))
+    iters = []
+    t, hit, cnt = cast_fn(funcs_tuple, params_tuple, cam_params, opts, init[rank::world], iters)[:3]
+    n_bins = int(opts['n_max_step']) // int(opts['n_substeps']) + 3
+    counts = np.zeros((2, n_bins), np.int64)
+    for k, (a, b) in enumerate(iters):
+        counts[0, k], counts[1, k] = a, b
+    if world > 1:
+        backend = dist.get_backend(group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        img = torch.from_numpy(np.stack((t.view(np.int32), hit, cnt)).astype(np.int32)).to(dev)   # disjoint pixels: x + 0 is exact on the bits
+        dist.all_reduce(img, group=group)
+        cts = torch.from_numpy(counts).to(dev)
+        dist.all_reduce(cts, group=group)
+        img = img.cpu().numpy()
+        t, hit, cnt = img[0].view(np.float32), img[1], img[2]
+        counts = cts.cpu().numpy()
+    n_evals = queries._frustum_n_evals(init.shape[0], counts[0].tolist(), counts[1].tolist())
+    return np.ascontiguousarray(t), np.ascontiguousarray(hit), np.ascontiguousarray(cnt), n_evals
+
+
 def deal_boxes(n_boxes, rank, world):
     """Indices of the frontier boxes (top-of-tree leaves) owned by `rank`: round-robin."""
     return np.arange(rank, n_boxes, world, dtype=np.int64)

@@ -362,10 +362,11 @@ def subdivide_frusta(sub_mask, empty_start_ind, valid_mask, frust_range, arrs):
     return valid_mask, out_range, outs
 
 
-def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, opts, return_near_tie=False, iter_counts=None):
+def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, opts, return_near_tie=False, iter_counts=None, init_ranges=None):
     """queries.py:465-587 -> (out_t (res_x,res_y) f32, out_hit_id i32, out_count i32, N_evals[, near_tie]).
     N_evals counts the padded array length of every marching iteration (queries.py:523), NOT times n_substeps.
-    iter_counts (ours): a list that receives (terminated, split) per iteration."""
+    iter_counts (ours): a list that receives (terminated, split) per iteration; init_ranges (ours): replaces the initial
+    tiles (a rank's share of a sharded image; the other pixels stay zero)."""
     root_pos, look_dir, up_dir, left_dir, fov_x, fov_y, res_x, res_y = cam_params
     n_substeps = int(opts["n_substeps"])
     N_out = res_x * res_y
@@ -378,6 +379,9 @@ def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, opts, return_near_t
     x_start, x_end = np.tile(x_ticks[:-1], N_side_init), np.tile(x_ticks[1:], N_side_init)
     y_start, y_end = np.repeat(y_ticks[:-1], N_side_init), np.repeat(y_ticks[1:], N_side_init)
     cur_range = np.stack((x_start, y_start, x_end, y_end), axis=-1).astype(np.int32)
+    if init_ranges is not None:
+        cur_range = np.array(init_ranges, np.int32).reshape(-1, 4)
+        N_init = cur_range.shape[0]
     cur_t = np.zeros(N_init, F32)
     cur_size = (np.ones(N_init, F32) * F32(opts["interval_init_size"]) * F32(opts["max_dist"])).astype(F32)
     cur_count = np.zeros(N_init, F32)
@@ -454,7 +458,8 @@ def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, opts, return_near_t
             needs, fin_start, fin_valid, fin_range, [fin_t, fin_hit, fin_count, fin_tie])
         fin_start += int(needs.sum())
     # (3) one pixel per frustum; the float count lands in an int image: truncation (queries.py:442-456)
-    assert fin_start == N_out
+    assert fin_start == N_out or init_ranges is not None
+    fin_range, fin_t, fin_hit, fin_count, fin_tie = (a[:fin_start] for a in (fin_range, fin_t, fin_hit, fin_count, fin_tie))
     out_t = np.zeros((res_x, res_y), F32)
     out_hit = np.zeros((res_x, res_y), np.int32)
     out_count = np.zeros((res_x, res_y), np.int32)

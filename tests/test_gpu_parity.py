@@ -1066,3 +1066,39 @@ def test_cast_rays_frustum_wide_streamed_and_render():
         queries.cast_rays_frustum((ff,), (pf,), (eye, look, up, left, 30.0, 30.0, 8, 8), o2)      # n_side_init 16 > res
     with pytest.raises(ValueError):
         queries.cast_rays_frustum((ff, ff), (pf,), (eye, look, up, left, 30.0, 30.0, 32, 32), o2)
+
+
+def test_cast_rays_frustum_tile_shares_equal_whole_image():
+    """The multi-GPU partition of frustum casting (sharding.cast_rays_frustum_sharded) on one device: marching the initial
+    tiles in two disjoint shares and summing the images / iteration counts gives the single-call result bit for bit."""
+    import queries
+    import render
+    import sharding
+    p = sample_params("fox")
+    func = make(p, "affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = 8
+    cam = (eye, look, up, left, 30.0, 30.0, 48, 40)
+    t, hit, cnt, n_evals = queries.cast_rays_frustum((func,), (p,), cam, opts)
+    init = queries._initial_frusta(48, 40, 8)
+    acc = [np.zeros((48, 40), np.float32), np.zeros((48, 40), np.int32), np.zeros((48, 40), np.int32)]
+    n_bins = 512 + 3
+    counts = np.zeros((2, n_bins), np.int64)
+    for r in range(2):
+        it = []
+        part = queries.cast_rays_frustum((func,), (p,), cam, opts, init_ranges=init[r::2], iter_counts=it)
+        for a, b in zip(acc, part[:3]):
+            a += b
+        for k, (x, y) in enumerate(it):
+            counts[0, k] += x; counts[1, k] += y
+    np.testing.assert_array_equal(acc[0], t)
+    np.testing.assert_array_equal(acc[1], hit)
+    np.testing.assert_array_equal(acc[2], cnt)
+    assert queries._frustum_n_evals(64, counts[0].tolist(), counts[1].tolist()) == n_evals
+    # world size 1 through the sharding entry point
+    st, sh, sc, sn = sharding.cast_rays_frustum_sharded((func,), (p,), cam, opts)
+    np.testing.assert_array_equal(st, t)
+    np.testing.assert_array_equal(sh, hit)
+    assert sn == n_evals and (hit != 0).any()

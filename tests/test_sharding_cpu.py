@@ -62,8 +62,15 @@ def _worker(rank, world, port, q):
     params_of = lambda i: (params, net.prepend_op(params, net.spatial_transformation(np.eye(3, dtype=np.float32), np.array(shifts[i], np.float32))))
     isect = lambda fs, ps, lo_, hi_, eps: tree.find_any_intersection(fs, ps, lo_, hi_, eps)
     fi, fl = sharding.find_any_intersection_batch_sharded((octx, octx), params_of, 3, np.full(3, -1, np.float32), np.full(3, 1, np.float32), 0.1, isect_fn=isect)
+    # frustum casting: initial tiles dealt round-robin, images summed, N_evals replayed from the summed iteration counts
+    fopts = rays.get_default_cast_opts()
+    fopts["n_side_init"] = 3
+    _, _, left = rays.look_at(eye)
+    cam = (eye, look, up, left, 30., 30., 12, 12)
+    fcast = lambda f, p, cam_, o, init, it: rays.cast_rays_frustum(f, p, cam_, o, init_ranges=init, iter_counts=it)
+    fr = sharding.cast_rays_frustum_sharded((octx,), (params,), cam, fopts, cast_fn=fcast)
     if rank == 0:
-        q.put((t, h, c, n_ev, lo, hi, cd, cl, fi, fl))
+        q.put((t, h, c, n_ev, lo, hi, cd, cl, fi, fl, fr))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -77,7 +84,7 @@ def test_sharded_rays_and_tree_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    t, h, c, n_ev, lo, hi, cd, cl, fi, fl = q.get(timeout=500)
+    t, h, c, n_ev, lo, hi, cd, cl, fi, fl, fr = q.get(timeout=500)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -104,3 +111,12 @@ def test_sharded_rays_and_tree_world2_gloo():
     # intersection batch: identity transform intersects, a shift of 1.9 does not
     assert fi.shape == (3,) and bool(fi[0]) and not bool(fi[1]) and fl.shape == (3, 3)
     assert np.all(fl[1] == -777.)
+    # frustum casting: the sharded images and N_evals equal the single-process call bit for bit
+    fopts = rays.get_default_cast_opts()
+    fopts["n_side_init"] = 3
+    _, _, left = rays.look_at(eye)
+    rt, rh, rc, rn = rays.cast_rays_frustum((octx,), (params,), (eye, look, up, left, 30., 30., 12, 12), fopts)
+    np.testing.assert_array_equal(fr[0], rt)
+    np.testing.assert_array_equal(fr[1], rh)
+    np.testing.assert_array_equal(fr[2], rc)
+    assert fr[3] == rn and (rh != 0).any()
