@@ -36,3 +36,9 @@ fs.bound_box(syn, c - 0.01 * h, c + 0.01 * h)
 imu.generate_implicit_from_params(syn, "slope_interval").bound_box(syn, c - 0.01 * h, c + 0.01 * h)
 o = queries.get_default_cast_opts(); o["n_max_step"] = 6
 queries.cast_rays((fs,), (syn,), roots, dirs, o); print("streamed sparse ok", flush=True)
+cam = (eye, look, up, render.look_at(eye)[2], 30., 30., 12, 12)
+fo = queries.get_default_cast_opts(); fo["n_side_init"] = 3
+queries.cast_rays_frustum((f,), (p,), cam, fo); print("frustum resident ok", flush=True)
+fo2 = dict(fo); fo2["n_max_step"] = 8; fo2["n_substeps"] = 2
+queries.cast_rays_frustum((fs,), (syn,), cam, fo2); print("frustum streamed ok", flush=True)
+queries.cast_rays_frustum((imu.generate_implicit_from_params(p, "interval"),), (p,), cam, fo2); print("frustum interval ok", flush=True)
