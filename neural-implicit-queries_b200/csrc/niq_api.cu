@@ -343,6 +343,10 @@ static size_t place_weights(niq_ctx* c, NetDev& net, int total_floats) {
         return res;
     }
     net.resident = 0;
+    {   // development knob: head start (cycles) of warps 0-3 over warps 4-7 in the streamed ray kernel
+        const char* e = getenv("NIQ_DEPHASE");
+        net.dephase = e ? atoi(e) : 0;
+    }
     return E::smem_bytes();
 }
 

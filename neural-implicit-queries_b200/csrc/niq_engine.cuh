@@ -65,6 +65,7 @@ struct NetDev {               // passed by value (__grid_constant__) to every en
     int w_region_floats;      // resident: size of the weight region (incl. over-read padding)
     float tie_rel;            // near-tie band: 1e-5 (relu-only nets) or 2e-4 (nets with elu)
     int sparse;               // 1: drop exactly-zero columns after relu layers (write_back_sparse); 0: dense K loops
+    int dephase;              // streamed ray kernels: cycles of head start the warps 0-3 get over warps 4-7 (same SM sub-partitions)
     unsigned long long* exec_macs;   // optional device counter of executed MACs / RT (see Engine::exec_macs)
     LayerDev layers[kMaxLayers];
     ChunkDev chunks[kMaxChunks];

@@ -339,6 +339,23 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
     E eng(net, smem);
     const int lane = eng.lane;
     const bool owner = lane < E::SLOTS;
+    // Streamed weights: every warp must consume the same chunk sequence, i.e. run the same number of steps, but there is
+    // NO per-step CTA barrier (it would put the two warps of every SM sub-partition back in lock-step once per step, so
+    // their activation epilogues could never overlap the other warp's FMA loop).  Work only ever runs out (the ray queue
+    // is consumed, nothing is pushed): a warp that has run dry says so once; the LAST warp to do so fixes the common
+    // final step count two steps ahead of its own, which no warp can have passed because the ring keeps the warps within
+    // kStages chunks (less than one step) of each other.
+    volatile int* exit_ctl = reinterpret_cast<volatile int*>(smem + 48);      // [0] warps that ran dry, [1] final step count
+    if (!eng.resident) {
+        if (threadIdx.x == 0) { exit_ctl[0] = 0; exit_ctl[1] = 0x7fffffff; }
+        __syncthreads();
+        if (eng.warp >= 4 && net.dephase > 0) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < (long long)net.dephase) {}
+        }
+    }
+    int steps_done = 0;
+    bool said_dry = false;
 
     // per-slot ray state (meaningful in lanes < SLOTS)
     long long ray = -1;
@@ -455,9 +472,21 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
         }
         // ---- does anyone in the CTA still have work? (queue not exhausted or a live ray) ----
         const bool more = owner && (ray >= 0 || (long long)(*((volatile unsigned long long*)queue)) < n);
-        // streamed weights: every warp takes part in the ring's CTA barriers, so the CTA leaves together;
-        // resident weights: no CTA barrier anywhere, each warp retires on its own
-        cta_live = eng.resident ? (__any_sync(0xffffffffu, more) != 0) : (__syncthreads_or(more ? 1 : 0) != 0);
+        // resident weights: each warp retires on its own; streamed weights: the common final step count (see the top)
+        const bool warp_more = __any_sync(0xffffffffu, more) != 0;
+        if (eng.resident) {
+            cta_live = warp_more;
+        } else {
+            ++steps_done;
+            if (!warp_more && !said_dry) {
+                said_dry = true;
+                if (lane == 0) {
+                    const int before = atomicAdd(const_cast<int*>(exit_ctl), 1);
+                    if (before == kWarps - 1) { exit_ctl[1] = steps_done + 2; __threadfence_block(); }
+                }
+            }
+            cta_live = __shfl_sync(0xffffffffu, steps_done < exit_ctl[1] ? 1 : 0, 0) != 0;   // lane 0's read decides for the warp
+        }
     }
     eng.drain();
 }
@@ -528,6 +557,16 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
     // per-iteration substep state (src/queries.py:317-322)
     int sub = 0, n_inner = 0, hit_id = 0;
     bool is_hit = false, demands = false;
+
+    // streamed weights: no per-step CTA barrier; the warps agree on a common final step count as in k_cast_rays.  Here a
+    // warp has run dry for good once it has SEEN the counter of outstanding frusta at zero (nothing can be pushed after that).
+    volatile int* exit_ctl = reinterpret_cast<volatile int*>(smem + 48);      // [0] warps that ran dry, [1] final step count
+    if (!eng.resident) {
+        if (threadIdx.x == 0) { exit_ctl[0] = 0; exit_ctl[1] = 0x7fffffff; }
+        __syncthreads();
+    }
+    int steps_done = 0;
+    bool said_dry = false;
 
     bool cta_live = true;
     while (cta_live) {
@@ -697,9 +736,24 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
                 }
             }
         }
-        // ---- does anyone still have work?  resident weights: each warp retires on its own (above);
-        //      streamed weights: every warp takes part in the ring's hand-over, so the CTA leaves together ----
-        if (!eng.resident) cta_live = __syncthreads_or((live || ctrl[2] != 0ull) ? 1 : 0) != 0;
+        // ---- resident weights: each warp retires on its own (above); streamed weights: common final step count ----
+        if (!eng.resident) {
+            ++steps_done;
+            const bool any_live = __any_sync(0xffffffffu, live) != 0;
+            if (!said_dry && !any_live) {
+                int dry = 0;
+                if (lane == 0) dry = ctrl[2] == 0ull ? 1 : 0;
+                dry = __shfl_sync(0xffffffffu, dry, 0);
+                if (dry) {
+                    said_dry = true;
+                    if (lane == 0) {
+                        const int before = atomicAdd(const_cast<int*>(exit_ctl), 1);
+                        if (before == kWarps - 1) { exit_ctl[1] = steps_done + 2; __threadfence_block(); }
+                    }
+                }
+            }
+            cta_live = __shfl_sync(0xffffffffu, steps_done < exit_ctl[1] ? 1 : 0, 0) != 0;
+        }
     }
     eng.drain();
 }
