@@ -484,6 +484,10 @@ def extra_metrics(ctx):
     fB = implicit_mlp_utils.generate_implicit_from_params(pB, "affine_truncate", **kw)
     rng = np.random.default_rng(0)
     n_q, n_found, n_nodes, n_rounds, t_tot, t_max = 24, 0, 0, 0, 0.0, 0.0
+    # warm-up on a disjoint pair (the longest kind of query: ~19 rounds), so that no timed query pays first-use allocations
+    pB["0000.spatial_transformation.R"] = np.eye(3, dtype=np.float32)
+    pB["0000.spatial_transformation.t"] = np.array((1.45, 0., 0.), np.float32)
+    kd_tree.find_any_intersection((fA, fB), (pA, pB), lo, hi, 1e-3, ctx=ctx)
     for i in range(n_q + 1):
         th = rng.uniform(0, 2 * np.pi)
         pB["0000.spatial_transformation.R"] = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)

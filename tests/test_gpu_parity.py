@@ -1102,3 +1102,25 @@ def test_cast_rays_frustum_tile_shares_equal_whole_image():
     np.testing.assert_array_equal(st, t)
     np.testing.assert_array_equal(sh, hit)
     assert sn == n_evals and (hit != 0).any()
+
+
+def test_cast_rays_frustum_uneven_tiles_non_square():
+    """res_x != res_y and a tile count that divides neither (initial tiles of 3-4 x 2-3 pixels) against the oracle."""
+    import queries
+    import render
+    p = sample_params("fox")
+    func = make(p, "affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    cam = (eye, look, up, left, 30.0, 30.0, 50, 37)
+    t, hit, cnt, n_evals, tie = queries.cast_rays_frustum((func,), (p,), cam, opts, return_near_tie=True)
+    ot, ohit, ocnt, on, otie = rays.cast_rays_frustum((octx("affine_fixed"),), (p,), cam, opts, return_near_tie=True)
+    assert t.shape == (50, 37)
+    ok = ~(tie | otie)
+    assert ok.mean() > 0.9 and (hit != 0).any()
+    np.testing.assert_array_equal(hit[ok], ohit[ok])
+    np.testing.assert_array_equal(cnt[ok], ocnt[ok])
+    np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL, atol=0)
+    if not (tie | otie).any():
+        assert n_evals == on
