@@ -187,8 +187,8 @@ typedef struct niq_camera {
  * reference's N_evals (padded array length of every marching iteration, src/queries.py:523), replayed from per-iteration
  * termination / split counts.  iter_counts (HOST, optional): those counts, int64[2 * (n_max_step / n_substeps + 3)] =
  * terminated per iteration, then split per iteration (a sharded caller sums them over the ranks before the replay).
- * Pixels outside the initial tiles are left zero.  interval and affine_fixed modes (one persistent kernel with a
- * device work queue).                                                                                     */
+ * Pixels outside the initial tiles are left zero.  interval, affine_fixed and slope_interval modes (one persistent
+ * kernel with a device work queue).                                                                                    */
 int niq_cast_rays_frustum(niq_ctx* ctx, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
                           const niq_cast_opts* opts, const niq_camera* cam, float refine_width_fac,
                           int64_t n_init, const int32_t* init_ranges,

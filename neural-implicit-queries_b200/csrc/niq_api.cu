@@ -958,17 +958,23 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
 // ------------------------------------------------------------------------------------------------
 // cast_rays_frustum (src/queries.py:178-587)
 // ------------------------------------------------------------------------------------------------
-template <int WMAX>
-static int launch_cast_frustum_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, const FrustCam& cam, int interval,
-                                 const FrustQueue& q, long long n_pixels) {
-    using E = Engine<WMAX, TileFrustum>;
+template <int WMAX, class Tile>
+static int launch_cast_frustum_wt(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, const FrustCam& cam, int interval,
+                                  const FrustQueue& q, long long n_pixels) {
+    using E = Engine<WMAX, Tile>;
     const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_cast_frustum<WMAX>, smem));
+    TRY(set_smem(k_cast_frustum<WMAX, Tile>, smem));
     const long long n_pass = (n_pixels + E::CTA_TILES - 1) / E::CTA_TILES;
     LaunchTimer lt(c, 0);
-    k_cast_frustum<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, cam, interval, q);
+    k_cast_frustum<WMAX, Tile><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, cam, interval, q);
     CU(cudaGetLastError());
     return NIQ_OK;
+}
+template <int WMAX>
+static int launch_cast_frustum_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, const FrustCam& cam, int interval,
+                                 const FrustQueue& q, long long n_pixels, bool slope) {
+    if (slope) return launch_cast_frustum_wt<WMAX, TileFrustumSlope>(c, net, total_floats, o, cam, 0, q, n_pixels);
+    return launch_cast_frustum_wt<WMAX, TileFrustum>(c, net, total_floats, o, cam, interval, q, n_pixels);
 }
 
 extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
@@ -985,7 +991,8 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
         TRY(check_cfg(&cfgs[f]));
         if (cfgs[f].mode != cfgs[0].mode) return fail(NIQ_EUNSUPPORTED, "all funcs of one cast_rays_frustum call must use the same mode");
     }
-    if (!is_fixed_mode(&cfgs[0]))
+    const bool slope = cfgs[0].mode == NIQ_MODE_SLOPE_INTERVAL;
+    if (!is_fixed_mode(&cfgs[0]) && !slope)
         return fail(NIQ_EUNSUPPORTED, "cast_rays_frustum in this mode runs through the host-level loop of the Python layer");
     const long long n = (long long)cam->res_x * cam->res_y;
     if (n_init > n) return fail(NIQ_EINVAL, "niq_cast_rays_frustum: more initial frusta than pixels");
@@ -1040,10 +1047,10 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
     }
     const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
     switch (wmax) {
-        case 32: TRY(launch_cast_frustum_w<32>(c, net, total_floats, co, fc, interval, q, n)); break;
-        case 64: TRY(launch_cast_frustum_w<64>(c, net, total_floats, co, fc, interval, q, n)); break;
-        case 128: TRY(launch_cast_frustum_w<128>(c, net, total_floats, co, fc, interval, q, n)); break;
-        default: TRY(launch_cast_frustum_w<256>(c, net, total_floats, co, fc, interval, q, n)); break;
+        case 32: TRY(launch_cast_frustum_w<32>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
+        case 64: TRY(launch_cast_frustum_w<64>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
+        case 128: TRY(launch_cast_frustum_w<128>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
+        default: TRY(launch_cast_frustum_w<256>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
     }
     {
         LaunchTimer lt(c, 1);

@@ -159,6 +159,15 @@ struct TileFrustum { // [B, A, A, A, E, P, P] : one frustum step = general-box b
     static constexpr int n_aff = 3, n_pts = 2;
     static constexpr bool has_group = true;
 };
+struct TileFrustumSlope { // [P, C, C, C, W, W, W, pt, pt] : one frustum step in slope_interval mode (3 box vectors) + the two points
+    static constexpr int RT = 9, NT = 1, rule = 2, n_vec = 3;
+    __host__ __device__ static constexpr bool is_err(int r) { return r >= 4 && r <= 6; }
+    __host__ __device__ static constexpr bool has_bias(int r) { return r == 0 || r >= 7; }
+    __host__ __device__ static constexpr bool is_pt(int r) { return r >= 7; }
+    __host__ __device__ static constexpr bool want_scale(int r) { return r == 0 || r >= 7; }
+    static constexpr int n_aff = 3, n_pts = 2;
+    static constexpr bool has_group = false;
+};
 struct TilePts {    // [P x 8]
     static constexpr int RT = 8, NT = 1, rule = 1;
     __host__ __device__ static constexpr bool is_err(int) { return false; }

@@ -538,11 +538,12 @@ __device__ __forceinline__ void frustum_cam_ray(const FrustCam& cam, float tx, f
     for (int d = 0; d < 3; ++d) r[d] = p[d] / len;
 }
 
-template <int WMAX>
+template <int WMAX, class Tile = TileFrustum>
 __global__ void __launch_bounds__(kThreads, 1)
 k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __grid_constant__ FrustCam cam, int interval_mode,
                FrustQueue q) {
-    using E = Engine<WMAX, TileFrustum>;
+    using E = Engine<WMAX, Tile>;     // TileFrustum: [base, aff x3, err, pt, pt]; TileFrustumSlope: [primal, centre x3, width x3, pt, pt]
+    constexpr int RT = Tile::RT;
     extern __shared__ __align__(128) unsigned char smem[];
     E eng(net, smem);
     const int lane = eng.lane;
@@ -633,11 +634,14 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
             ++l1;
             if (live) {
                 const float cm = 0.5f * (t + t_adj), cv = 0.5f * (t_adj - t), te = t + o.hit_eps;
-                float4 rows[7];
+                float4 rows[RT];
                 rows[0] = make_float4(cam.root[0] + cm * mid[0], cam.root[1] + cm * mid[1], cam.root[2] + cm * mid[2], 0.f);
                 const float4 v0 = make_float4(cv * mid[0], cv * mid[1], cv * mid[2], 0.f);
                 const float4 v1 = make_float4(rf[0], rf[1], rf[2], 0.f), v2 = make_float4(uf[0], uf[1], uf[2], 0.f);
-                if (interval_mode) {
+                if (Tile::rule == 2) {                    // slope_interval: centres = the box vectors, widths = 0
+                    rows[1] = v0; rows[2] = v1; rows[3] = v2;
+                    rows[4] = rows[5] = rows[6] = make_float4(0.f, 0.f, 0.f, 0.f);
+                } else if (interval_mode) {
                     rows[1] = rows[2] = rows[3] = make_float4(0.f, 0.f, 0.f, 0.f);
                     rows[4] = make_float4((fabsf(v0.x) + fabsf(v1.x)) + fabsf(v2.x), (fabsf(v0.y) + fabsf(v1.y)) + fabsf(v2.y),
                                           (fabsf(v0.z) + fabsf(v1.z)) + fabsf(v2.z), 0.f);
@@ -645,11 +649,11 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
                     rows[1] = v0; rows[2] = v1; rows[3] = v2;
                     rows[4] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
-                rows[5] = make_float4(cam.root[0] + t * mid[0], cam.root[1] + t * mid[1], cam.root[2] + t * mid[2], 0.f);
-                rows[6] = make_float4(cam.root[0] + te * mid[0], cam.root[1] + te * mid[1], cam.root[2] + te * mid[2], 0.f);
-                float* dst = eng.act + lane * 7 * E::G::S;
+                rows[RT - 2] = make_float4(cam.root[0] + t * mid[0], cam.root[1] + t * mid[1], cam.root[2] + t * mid[2], 0.f);
+                rows[RT - 1] = make_float4(cam.root[0] + te * mid[0], cam.root[1] + te * mid[1], cam.root[2] + te * mid[2], 0.f);
+                float* dst = eng.act + lane * RT * E::G::S;
 #pragma unroll
-                for (int r = 0; r < 7; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
+                for (int r = 0; r < RT; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
             }
             __syncwarp();
             float out[E::ROWS], ps[E::ROWS];
@@ -657,9 +661,16 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
             if (eng.cg == 0) {        // hand base, radius, the two point values and their scales to the slot's owner lane
                 float* d = eng.fin + eng.t * 8;
                 d[0] = out[0];
-                d[1] = ((fabsf(out[1]) + fabsf(out[2])) + fabsf(out[3])) + out[4];
-                d[2] = out[5]; d[3] = out[6];
-                d[4] = ps[0]; d[5] = ps[5]; d[6] = ps[6];
+                if (Tile::rule == 2) {                    // src/slope_interval.py:201-206: sum_v max(C + W, -(C - W))
+                    float prad = 0.f;
+#pragma unroll
+                    for (int v = 0; v < 3; ++v) prad = prad + fmaxf(out[1 + v] + out[4 + v], -(out[1 + v] - out[4 + v]));
+                    d[1] = prad;
+                } else {
+                    d[1] = ((fabsf(out[1]) + fabsf(out[2])) + fabsf(out[3])) + out[4];
+                }
+                d[2] = out[RT - 2]; d[3] = out[RT - 1];
+                d[4] = ps[0]; d[5] = ps[RT - 2]; d[6] = ps[RT - 1];
             }
             __syncwarp();
             if (live) {

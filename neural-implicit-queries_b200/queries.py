@@ -232,7 +232,7 @@ def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, in_opts, return_nea
         init_ranges = _initial_frusta(res_x, res_y, n_side)
     init_ranges = np.ascontiguousarray(init_ranges, np.int32).reshape(-1, 4)
     modes = {f.ctx.mode for f in funcs_tuple}
-    impl = _cast_rays_frustum_persistent if len(modes) == 1 and modes <= {"interval", "affine_fixed"} else _cast_rays_frustum_host_loop
+    impl = _cast_rays_frustum_persistent if len(modes) == 1 and modes <= {"interval", "affine_fixed", "slope_interval"} else _cast_rays_frustum_host_loop
     return impl(ctx, funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie, init_ranges, iter_counts)
 
 
@@ -271,7 +271,8 @@ def _cast_rays_frustum_persistent(ctx, funcs_tuple, params_tuple, cam_params, op
 
 def _cast_rays_frustum_host_loop(ctx, funcs_tuple, params_tuple, cam_params, opts, return_near_tie, init=None, iter_counts=None):
     """The reference's host-level iteration over a compact list of live frusta (no padding entries; N_evals is replayed
-    from the per-iteration counts), bounds and point values on the GPU.  Serves the modes without a persistent kernel."""
+    from the per-iteration counts), bounds and point values on the GPU.  Serves the modes without a persistent kernel
+    (affine_all / affine_truncate / affine_append / sdf)."""
     import mlp
     f32 = np.float32
     cam = _frustum_cam(cam_params)

@@ -1006,7 +1006,7 @@ def test_cast_rays_frustum_golden(case):
 
 @pytest.mark.parametrize("name,mode,res,n_side,n_sub", [("fox", "affine_fixed", 64, 16, 1), ("bunny", "affine_fixed", 40, 8, 1),
                                                         ("birdcage_occ", "interval", 24, 4, 2), ("fox", "affine_truncate", 16, 4, 1),
-                                                        ("fox", "slope_interval", 16, 4, 1)])
+                                                        ("fox", "slope_interval", 16, 4, 1), ("bunny", "slope_interval", 32, 8, 2)])
 def test_cast_rays_frustum_vs_oracle(name, mode, res, n_side, n_sub):
     """Larger images against the oracle.  A pixel is compared when no decision of its frustum chain was inside the 1e-5
     band in EITHER implementation (a flipped split changes the whole subtree of pixels)."""
