@@ -244,6 +244,24 @@ def sample_surface(func, params, lower, upper, n_samples, width, rngkey, n_node_
     return found
 
 
+def sample_surface_uniform(func, params, lower, upper, n_samples, width, rngkey, ctx=None):
+    """src/kd_tree.py:296-336: the tree-free baseline of sample_surface -- uniform draws in [lower, upper], keep |f| < width.
+    Point evaluations on the GPU, draws from a numpy Generator (jax.random streams are not reproducible without JAX)."""
+    rng = _rng(rngkey)
+    lower, upper = _vec3(lower, "lower"), _vec3(upper, "upper")
+    per_round = min(10 * n_samples, 100000)
+    found = np.zeros((n_samples, 3), np.float32)
+    n_found = 0
+    while n_found < n_samples:
+        pos = rng.uniform(lower, upper, (per_round, 3)).astype(np.float32)
+        import mlp
+        ok = np.abs(mlp.eval_points(params, pos, ctx=ctx)) < np.float32(width)
+        take = pos[ok][:n_samples - n_found]
+        found[n_found:n_found + take.shape[0]] = take
+        n_found += take.shape[0]
+    return found
+
+
 def bulk_properties(func, params, lower, upper, rngkey, n_expand=int(1e4), n_sample=int(1e6), ctx=None):
     """src/kd_tree.py:837-863 -> (mass, centroid (3,)) of {f < 0}: exact over the interior nodes, Monte Carlo over the
     unknown leaves (:804-835)."""

@@ -917,6 +917,10 @@ def test_sample_surface_and_bulk_properties_vs_oracle():
     assert np.all(np.abs(f) < width + 1e-5 * rays.point_scale(p, pts))
     same = np.all(pts == opts, axis=1)
     assert same.mean() > 0.99 or np.array_equal(pts[:100], opts[:100])
+    # the tree-free sibling (src/kd_tree.py:296-336): every sample inside the band and inside the domain
+    upts = kd_tree.sample_surface_uniform(func, p, LO, HI, 500, width, 7)
+    assert upts.shape == (500, 3) and upts.dtype == np.float32 and np.all(np.abs(upts) <= 1.0)
+    assert np.all(np.abs(net.eval_points(p, upts)) < width + 1e-5 * rays.point_scale(p, upts))
     mass, cen = kd_tree.bulk_properties(func, p, LO, HI, 11, n_expand=2000, n_sample=200000)
     omass, ocen = otree.bulk_properties(octx("affine_fixed"), p, LO, HI, np.random.default_rng(11), n_expand=2000, n_sample=200000)
     assert abs(mass - omass) <= 2e-4 * omass and np.all(np.abs(cen - ocen) <= 2e-4)
