@@ -384,7 +384,7 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(n_all, world, tile_stride),
             "ray_steps_per_s": ray_steps_all * args.steps / (total_ms * 1e-3),
             "e2e": {"value": n_all * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_all * 24,
-                    "d2h_bytes_per_step": n_all * 13, "timer": "wall clock around queries.cast_rays (+ all_gather for N>1)"},
+                    "d2h_bytes_per_step": n_all * 12, "timer": "wall clock around queries.cast_rays (+ all_gather for N>1)"},
             "gpu_launches": int(gpu_launches), "step_ms": [round(x, 2) for x in step_ms],
             "clocks": clk,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,

@@ -442,8 +442,9 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
                 const bool this_hit = (s0 != s1) || (v0 != v0) || (v1 != v1);   // sign(nan)=nan != anything
                 if (this_hit) hit_id = f + 1;
                 is_hit = is_hit || this_hit;
-                tie = tie || bound_near_tie(lo, up, 0.f, d[7], net.tie_rel) || fabsf(v0) <= kNearTieRel * d[5] ||
-                      fabsf(v1) <= kNearTieRel * d[6];
+                if (out_tie)      // the band bookkeeping is an extra of the parity tests: skipped when nobody asked for it
+                    tie = tie || bound_near_tie(lo, up, 0.f, d[7], net.tie_rel) || fabsf(v0) <= kNearTieRel * d[5] ||
+                          fabsf(v1) <= kNearTieRel * d[6];
             }
             __syncwarp();
             l0 = l1;

@@ -66,7 +66,7 @@ def _cast_rays_persistent(ctx, funcs_tuple, params_tuple, roots, dirs, opts, ret
     t = np.zeros(n, np.float32)
     hit = np.zeros(n, np.int32)
     cnt = np.zeros(n, np.int32)
-    tie = np.zeros(n, np.uint8)
+    tie = np.zeros(n, np.uint8) if return_near_tie else None      # the kernel skips the band bookkeeping when not asked
     n_evals = C.c_int64(0)
     _niq.check(_niq.lib().niq_cast_rays(ctx.handle, C.c_int32(nf), handles, cfgs, C.byref(o), C.c_int64(n),
                                         _niq.ptr(roots), _niq.ptr(dirs), _niq.ptr(t), _niq.ptr(hit), _niq.ptr(cnt),
