@@ -472,8 +472,13 @@ def extra_metrics(ctx):
                                                "near_tie": st["n_near_tie"], "ms": dt * 1e3}
     dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 7, n_subcell_depth=3), reps=2)
     ex["cfg2_bunny_hmc_depth7_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "leaves_per_s": 4096 / dt}
+    ctx.mc_points(reset=True)
     dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 9, n_subcell_depth=3), reps=1)
-    ex["cfg2_bunny_hmc_depth9_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "triangles_per_s": tri.shape[0] / dt}
+    ev, lat = ctx.mc_points(reset=True)
+    ex["cfg2_bunny_hmc_depth9_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "triangles_per_s": tri.shape[0] / dt,
+                                        "leaves": lat // 729 // 2, "leaves_per_s": lat / 729 / 2 / dt,
+                                        "lattice_points_evaluated_over_reference": ev / max(lat, 1),
+                                        "note": "points on a face shared by two leaves are evaluated once (values and triangles unchanged)"}
 
     # config 3: hammer x bunny under seeded rigid transforms, affine_truncate (n_keep 64, 'absolute'), eps 1e-3
     import mlp

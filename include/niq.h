@@ -120,6 +120,9 @@ int niq_ctx_kernel_timing(niq_ctx* ctx, int on);
  * the device counter on/off for subsequent launches; *macs (optional) returns the row-level multiply-adds counted
  * so far (padded rows / idle slots included); reset != 0 clears it.                                          */
 int niq_ctx_exec_macs(niq_ctx* ctx, int on, int64_t* macs, int reset);
+/* marching cubes accounting: lattice points actually evaluated / the (2^n+1)^3 per leaf the reference evaluates (points on
+ * a face shared by two leaves are evaluated once; the values -- hence the triangles -- are unchanged).  reset != 0 clears. */
+int niq_ctx_mc_points(niq_ctx* ctx, int64_t* evaluated, int64_t* lattice, int reset);
 /* device memory helpers so a host language can keep inputs resident (bench `value` leg)              */
 int niq_dev_alloc(niq_ctx* ctx, int64_t bytes, void** out);
 int niq_dev_free(niq_ctx* ctx, void* p);

@@ -28,7 +28,7 @@ TREE_INTERIOR, TREE_EXTERIOR = 1, 2
 SYMBOLS = (
     "niq_last_error", "niq_version", "niq_ctx_create", "niq_ctx_destroy", "niq_ctx_sync", "niq_ctx_device_info",
     "niq_ctx_launch_count", "niq_ctx_timer_start", "niq_ctx_timer_stop", "niq_ctx_kernel_ms",
-    "niq_ctx_kernel_timing", "niq_ctx_exec_macs", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
+    "niq_ctx_kernel_timing", "niq_ctx_exec_macs", "niq_ctx_mc_points", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
     "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
     "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_cast_rays_frustum", "niq_tree_build", "niq_tree_build_roots", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
@@ -168,6 +168,12 @@ class Context:
         out = C.c_int64()
         check(lib().niq_ctx_exec_macs(self.handle, C.c_int(1 if on else 0), C.byref(out), C.c_int(1 if reset else 0)))
         return out.value
+
+    def mc_points(self, reset=True):
+        """(lattice points evaluated by marching cubes so far, the reference's count for the same leaves)."""
+        ev, lat = C.c_int64(), C.c_int64()
+        check(lib().niq_ctx_mc_points(self.handle, C.byref(ev), C.byref(lat), C.c_int(1 if reset else 0)))
+        return ev.value, lat.value
 
     def fp32_peak_tflops(self):
         out = C.c_float()

@@ -70,6 +70,7 @@ struct niq_ctx {
     bool timer_armed = false, timer_started = false;   // niq_ctx_timer_start .. _stop bracket (see timer_touch / timer_mark)
     unsigned long long* d_exec = nullptr;   // executed-MAC counter of the engine kernels (zero-skipping accounting)
     bool count_exec = false;
+    long long mc_points_evaluated = 0, mc_points_lattice = 0;   // marching cubes: lattice points evaluated / the reference's count
 };
 
 struct DevBuf {   // stream-ordered temporary
@@ -194,6 +195,12 @@ static void timer_mark(niq_ctx* c) {
 }
 #define FINAL_SYNC(c) do { timer_mark(c); CU(cudaStreamSynchronize((c)->stream)); } while (0)
 
+extern "C" int niq_ctx_mc_points(niq_ctx* c, int64_t* evaluated, int64_t* lattice, int reset) {
+    if (!c || !evaluated || !lattice) return fail(NIQ_EINVAL, "bad argument");
+    *evaluated = c->mc_points_evaluated; *lattice = c->mc_points_lattice;
+    if (reset) c->mc_points_evaluated = c->mc_points_lattice = 0;
+    return NIQ_OK;
+}
 extern "C" int niq_ctx_timer_start(niq_ctx* c) {
     if (!c) return fail(NIQ_EINVAL, "ctx is NULL");
     c->timer_armed = true;
@@ -1309,20 +1316,53 @@ static int mc_device(niq_ctx* c, const niq_mlp* m, long long n, const float* lo,
     const long long pts_per_leaf = (long long)P * P * P;
     // leaves are processed in slabs so the lattice values stay bounded (256 MB)
     const long long slab = std::max<long long>(1, (64ll << 20) / pts_per_leaf);
+    const bool dedup = getenv("NIQ_MC_NO_DEDUP") == nullptr;       // development knob: A/B against one evaluation per leaf and point
     std::vector<std::pair<float*, long long>> parts;
     struct PartGuard { niq_ctx* c; std::vector<std::pair<float*, long long>>* p; ~PartGuard() { for (auto& q : *p) if (q.first) cudaFreeAsync(q.first, c->stream); } } pg{c, &parts};
     long long total = 0;
     for (long long s0 = 0; s0 < n; s0 += slab) {
         const long long L = std::min(slab, n - s0);
-        DevBuf vals(c), cnt(c), off(c);
-        TRY(vals.alloc((size_t)L * pts_per_leaf * 4));
+        DevBuf vals(c), cnt(c), off(c), table(c), nb(c), own_cnt(c), own_base(c);
         TRY(cnt.alloc(L * 4));
         TRY(off.alloc((L + 1) * 4));
         PointSource src{};
-        src.kind = 1; src.a = lo + 3 * s0; src.b = hi + 3 * s0; src.pts_per_side = P;
-        TRY(launch_eval_points(c, m, src, L * pts_per_leaf, vals.as<float>(), nullptr));
+        src.a = lo + 3 * s0; src.b = hi + 3 * s0; src.pts_per_side = P;
         McArgs a{};
-        a.leaf_lo = lo + 3 * s0; a.leaf_hi = hi + 3 * s0; a.vals = vals.as<float>(); a.n_leaves = L; a.n_side = side;
+        a.leaf_lo = lo + 3 * s0; a.leaf_hi = hi + 3 * s0; a.n_leaves = L; a.n_side = side;
+        long long n_pts = L * pts_per_leaf;
+        if (dedup && L > 1) {
+            // lattice points on a face shared with another leaf of the slab are evaluated once (k_mc_neighbours, mc_val)
+            long long T = 16;
+            while (T < 2 * L) T <<= 1;
+            TRY(table.alloc((size_t)T * 4));
+            TRY(nb.alloc((size_t)L * 12));
+            TRY(own_cnt.alloc((size_t)L * 4));
+            TRY(own_base.alloc((size_t)(L + 1) * 4));
+            CU(cudaMemsetAsync(table.p, 0, (size_t)T * 4, c->stream));
+            {
+                LaunchTimer lt(c, 1);
+                k_mc_hash_insert<<<(int)((L + 255) / 256), 256, 0, c->stream>>>(src.a, L, table.as<int>(), (unsigned)(T - 1));
+                CU(cudaGetLastError());
+            }
+            {
+                LaunchTimer lt(c, 1);
+                k_mc_neighbours<<<(int)((L + 255) / 256), 256, 0, c->stream>>>(src.a, src.b, L, table.as<int>(), (unsigned)(T - 1), P,
+                                                                               nb.as<int>(), own_cnt.as<int>());
+                CU(cudaGetLastError());
+            }
+            TRY(scan_exclusive(c, own_cnt.as<int>(), L, own_base.as<int>()));
+            int n_own = 0;
+            TRY(read_back(c, own_base.as<int>() + L, 4, &n_own));
+            n_pts = n_own;
+            src.kind = 4; src.own_base = own_base.as<int>(); src.own_nb = nb.as<int>(); src.n_leaves = L;
+            a.own_base = src.own_base; a.own_nb = src.own_nb;
+        } else {
+            src.kind = 1;
+        }
+        TRY(vals.alloc((size_t)n_pts * 4));
+        TRY(launch_eval_points(c, m, src, n_pts, vals.as<float>(), nullptr));
+        a.vals = vals.as<float>();
+        c->mc_points_evaluated += n_pts; c->mc_points_lattice += L * pts_per_leaf;
         {
             LaunchTimer lt(c, 1);
             k_mc_count<<<(int)L, kScanThreads, 0, c->stream>>>(a, cnt.as<int>());

@@ -33,6 +33,11 @@ struct PointSource {
     float sample_scale;       // kind 2: eps/sqrt(3) (intersection); < 0: use the node's full extent (closest point)
     const long long* top;     // kind 2: optional window (closest point)
     long long window;
+    // kind 4: the MC lattice of leaves WITHOUT the points a face neighbour already owns (k_mc_neighbours): leaf l owns the
+    // sub-lattice i_d >= has_neighbour(l, -d), own_base = exclusive scan of the owned counts (n_leaves + 1 entries)
+    const int* own_base;
+    const int* own_nb;        // (n_leaves, 3): the leaf sharing the low face in x / y / z, or -1
+    long long n_leaves;
 };
 
 __device__ __forceinline__ long long window_base(const long long* top, long long window) {
@@ -103,6 +108,35 @@ __device__ __forceinline__ float4 load_point(const PointSource& src, long long i
             } else {
                 const float s = (float)idx[d] / div;
                 xyz[d] = lo[d] * (1.f - s) + hi[d] * s;
+            }
+        }
+        return make_float4(xyz[0], xyz[1], xyz[2], 0.f);
+    } else if (src.kind == 4) {
+        // owned lattice point i -> (leaf, i0, i1, i2): binary search in the scan, then the leaf's owned sub-lattice
+        long long lo_l = 0, hi_l = src.n_leaves;                  // invariant: own_base[lo_l] <= i < own_base[hi_l]
+        while (hi_l - lo_l > 1) {
+            const long long mid = (lo_l + hi_l) >> 1;
+            if ((long long)src.own_base[mid] <= i) lo_l = mid; else hi_l = mid;
+        }
+        const long long leaf = lo_l;
+        const int P = src.pts_per_side;
+        int r = (int)(i - (long long)src.own_base[leaf]);
+        const int n0 = src.own_nb[3 * leaf] >= 0, n1 = src.own_nb[3 * leaf + 1] >= 0, n2 = src.own_nb[3 * leaf + 2] >= 0;
+        const int e1 = P - n1, e2 = P - n2;
+        const int i2 = r % e2 + n2; r /= e2;
+        const int i1 = r % e1 + n1;
+        const int i0 = r / e1 + n0;
+        const float* lo = src.a + 3 * leaf;
+        const float* hi = src.b + 3 * leaf;
+        const float div = (float)(P - 1);
+        const int idx[3] = {i0, i1, i2};
+        float xyz[3];
+        for (int d = 0; d < 3; ++d) {                             // the same formula as kind 1
+            if (idx[d] == P - 1) {
+                xyz[d] = hi[d];
+            } else {
+                const float sf = (float)idx[d] / div;
+                xyz[d] = lo[d] * (1.f - sf) + hi[d] * sf;
             }
         }
         return make_float4(xyz[0], xyz[1], xyz[2], 0.f);
@@ -1262,20 +1296,98 @@ __global__ void __launch_bounds__(kCpSmallThreads) k_cp_round_small(CpRound r, f
 __constant__ unsigned long long c_mc_case_words[256] = NIQ_MC_CASE_WORDS_INIT;
 
 struct McArgs {
-    const float* leaf_lo; const float* leaf_hi; const float* vals;   // vals: (L, P, P, P)
+    const float* leaf_lo; const float* leaf_hi; const float* vals;   // vals: (L, P, P, P), or the owned points only (own_base != 0)
     long long n_leaves;
     int n_side;            // 2^n_sub_depth subcells per axis
+    const int* own_base;   // shared-face dedup (see PointSource kind 4): exclusive scan of the owned counts, or nullptr
+    const int* own_nb;     // (L, 3) low-face neighbours or -1
 };
 
+// ---- shared lattice faces --------------------------------------------------------------------------------------------
+// Neighbouring leaves of a uniform-depth tree share the (2^n+1)^2 lattice points of their common face, which the reference
+// evaluates once per leaf.  A leaf whose low face in dimension d coincides EXACTLY with the high face of another leaf (same
+// float bounds in the other two dimensions, hi_nb[d] == lo[d]) reads those values from that leaf instead: the coordinates
+// the two leaves would compute are bit-identical (i_d = 0 gives lo[d], i_d = P-1 gives hi[d]; the other two coordinates come
+// from identical inputs), and a point evaluation does not depend on its batch, so every value -- hence every triangle -- is
+// unchanged.  8x8x8 of 9x9x9 points remain for a leaf with all three neighbours (-30 % evaluations).
+__device__ __forceinline__ unsigned mc_hash3(float x, float y, float z) {
+    unsigned h = __float_as_uint(x + 0.f) * 0x9E3779B1u;           // + 0.f: -0 and +0 hash alike
+    h = (h ^ (h >> 15)) + __float_as_uint(y + 0.f) * 0x85EBCA77u;
+    h = (h ^ (h >> 13)) + __float_as_uint(z + 0.f) * 0xC2B2AE3Du;
+    return h ^ (h >> 16);
+}
+__global__ void k_mc_hash_insert(const float* __restrict__ lo, long long n, int* __restrict__ table, unsigned mask) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x = lo[3 * i], y = lo[3 * i + 1], z = lo[3 * i + 2];
+    unsigned h = mc_hash3(x, y, z) & mask;
+    for (unsigned probe = 0; probe <= mask; ++probe) {
+        const int old = atomicCAS(table + h, 0, (int)i + 1);
+        if (old == 0) return;
+        const float* q = lo + 3 * (long long)(old - 1);
+        if (q[0] == x && q[1] == y && q[2] == z) return;          // a duplicate corner: the first leaf keeps the entry
+        h = (h + 1) & mask;
+    }
+}
+__global__ void k_mc_neighbours(const float* __restrict__ lo, const float* __restrict__ hi, long long n, const int* __restrict__ table,
+                                unsigned mask, int P, int* __restrict__ nb, int* __restrict__ count) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float l[3], u[3];
+    for (int d = 0; d < 3; ++d) { l[d] = lo[3 * i + d]; u[d] = hi[3 * i + d]; }
+    int cnt = 1;
+    for (int d = 0; d < 3; ++d) {
+        float key[3] = {l[0], l[1], l[2]};
+        key[d] = l[d] - (u[d] - l[d]);
+        int found = -1;
+        unsigned h = mc_hash3(key[0], key[1], key[2]) & mask;
+        for (unsigned probe = 0; probe <= mask; ++probe) {
+            const int e = table[h];
+            if (e == 0) break;
+            const float* q = lo + 3 * (long long)(e - 1);
+            if (q[0] == key[0] && q[1] == key[1] && q[2] == key[2]) { found = e - 1; break; }
+            h = (h + 1) & mask;
+        }
+        if (found >= 0) {
+            const float* qh = hi + 3 * (long long)found;
+            bool ok = found != (int)i && qh[d] == l[d];
+            for (int e = 0; e < 3; ++e)
+                if (e != d) ok = ok && qh[e] == u[e];
+            if (!ok) found = -1;
+        }
+        nb[3 * i + d] = found;
+        cnt *= P - (found >= 0 ? 1 : 0);
+    }
+    count[i] = cnt;
+}
+// lattice value (i0,i1,i2) of `leaf`: follow the low-face neighbours until the point is owned, then index the owner's sub-lattice
+__device__ __forceinline__ float mc_val(const McArgs& a, long long leaf, int i0, int i1, int i2) {
+    const int P = a.n_side + 1;
+    if (a.own_base == nullptr) return a.vals[leaf * (long long)(P * P * P) + (i0 * P + i1) * P + i2];
+    long long cur = leaf;
+    int idx[3] = {i0, i1, i2};
+    for (int it = 0; it < 3; ++it) {
+        bool moved = false;
+        for (int d = 0; d < 3; ++d) {
+            if (idx[d] == 0) {
+                const int n = a.own_nb[3 * cur + d];
+                if (n >= 0) { cur = n; idx[d] = P - 1; moved = true; }
+            }
+        }
+        if (!moved) break;
+    }
+    const int n0 = a.own_nb[3 * cur] >= 0, n1 = a.own_nb[3 * cur + 1] >= 0, n2 = a.own_nb[3 * cur + 2] >= 0;
+    return a.vals[(long long)a.own_base[cur] + ((idx[0] - n0) * (P - n1) + (idx[1] - n1)) * (P - n2) + (idx[2] - n2)];
+}
+
 __device__ __forceinline__ int mc_case(const McArgs& a, long long leaf, int s, float vv[8], int ijk[3]) {
-    const int n = a.n_side, P = n + 1;
+    const int n = a.n_side;
     ijk[2] = s % n; ijk[1] = (s / n) % n; ijk[0] = s / (n * n);
-    const float* v = a.vals + leaf * (long long)(P * P * P);
     int id = 0;
     for (int k = 0; k < 8; ++k) {
         const int ox = (NIQ_MC_VERT_MASK_X >> k) & 1, oy = (NIQ_MC_VERT_MASK_Y >> k) & 1,
                   oz = (NIQ_MC_VERT_MASK_Z >> k) & 1;
-        vv[k] = v[((ijk[0] + ox) * P + (ijk[1] + oy)) * P + (ijk[2] + oz)];
+        vv[k] = mc_val(a, leaf, ijk[0] + ox, ijk[1] + oy, ijk[2] + oz);
         id |= (vv[k] < 0.f) << k;
     }
     return id;

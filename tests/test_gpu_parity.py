@@ -927,6 +927,38 @@ def test_sample_surface_and_bulk_properties_vs_oracle():
     assert 0.01 < mass < 8.0 and np.all(np.abs(cen) < 1.0)
 
 
+def test_marching_cubes_shared_faces_evaluated_once(monkeypatch):
+    """Lattice points on a face shared by two leaves are evaluated once (k_mc_neighbours / mc_val): fewer evaluations, and
+    the triangle soup is BIT-identical to one evaluation per leaf and point (NIQ_MC_NO_DEDUP=1), for a uniform-depth tree,
+    for caller-supplied leaves of mixed sizes (no exact face match -> nothing shared) and across the golden case."""
+    import _niq
+    import extract_cell
+    import kd_tree
+    ctx = _niq.default_context()
+    p = sample_params("bunny")
+    func = make(p, "affine_fixed")
+    ctx.mc_points(reset=True)
+    tri = kd_tree.hierarchical_marching_cubes(func, p, LO, HI, 7, n_subcell_depth=3)
+    ev, lat = ctx.mc_points(reset=True)
+    assert lat == 4096 * 729 or lat % 729 == 0
+    assert 0.6 * lat < ev < 0.9 * lat, (ev, lat)
+    monkeypatch.setenv("NIQ_MC_NO_DEDUP", "1")
+    tri_ref = kd_tree.hierarchical_marching_cubes(func, p, LO, HI, 7, n_subcell_depth=3)
+    ev2, lat2 = ctx.mc_points(reset=True)
+    assert ev2 == lat2 == lat
+    monkeypatch.delenv("NIQ_MC_NO_DEDUP")
+    assert tri.shape == tri_ref.shape and tri.shape[0] > 50000
+    np.testing.assert_array_equal(tri, tri_ref)
+    # mixed leaf sizes / a duplicate leaf / non-dyadic bounds through the leaf-list entry point
+    lo = np.array([[-.25, -.25, -.25], [0.0, -.25, -.25], [0.25, -.25, -.25], [-.25, -.25, -.25], [0.1, 0.05, -0.3], [0.35, 0.05, -0.3]], np.float32)
+    hi = np.array([[0.0, 0.0, 0.0], [0.25, 0.0, 0.0], [0.75, 0.25, 0.25], [0.0, 0.0, 0.0], [0.35, 0.3, -0.05], [0.6, 0.3, -0.05]], np.float32)
+    a = extract_cell.extract_mesh_from_cells(func, p, lo, hi, 2)
+    monkeypatch.setenv("NIQ_MC_NO_DEDUP", "1")
+    b = extract_cell.extract_mesh_from_cells(func, p, lo, hi, 2)
+    monkeypatch.delenv("NIQ_MC_NO_DEDUP")
+    np.testing.assert_array_equal(a, b)
+
+
 # ---------------------------------------------------------------------------------------------------
 # the caller of cast_rays (SURVEY 8(f) row 4): render.render_image
 # ---------------------------------------------------------------------------------------------------
