@@ -119,12 +119,33 @@ def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_
     Leaf ORDER differs from the single-device call (canonicalise before comparing).  -> (lower, upper) (L,3)."""
     import torch
     import torch.distributed as dist
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    lo, hi = _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, rank, world, kw)
+    if world == 1:
+        return lo, hi
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    cnt = torch.tensor([lo.shape[0]], dtype=torch.int64, device=dev)
+    counts = [torch.zeros_like(cnt) for _ in range(world)]
+    dist.all_gather(counts, cnt, group=group)
+    counts = [int(c.item()) for c in counts]
+    cap = max(max(counts), 1)
+    pack = torch.zeros((cap, 6), dtype=torch.float32)
+    pack[:lo.shape[0], :3] = torch.from_numpy(lo)
+    pack[:lo.shape[0], 3:] = torch.from_numpy(hi)
+    parts = [torch.empty((cap, 6), dtype=torch.float32, device=dev) for _ in range(world)]
+    dist.all_gather(parts, pack.to(dev), group=group)
+    allp = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
+    return allp[:, :3].copy(), allp[:, 3:].copy()
+
+
+def _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, rank, world, kw):
+    """The UNKNOWN leaves at `split_depth` below this rank's share of the frontier (top levels replicated)."""
     injected = build_fn is not None
     if build_fn is None:
         import kd_tree
         build_fn = kd_tree.construct_uniform_unknown_levelset_tree
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
     if top_depth is None:
         top_depth = min(split_depth, int(np.ceil(np.log2(max(8 * world, 2)))) + 3)
     top = build_fn(func, params, lower, upper, split_depth=top_depth, **kw)
@@ -148,22 +169,31 @@ def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_
             lo, hi = tree.nodes(0)
         finally:
             tree.close()
+    return np.ascontiguousarray(lo, np.float32).reshape(-1, 3), np.ascontiguousarray(hi, np.float32).reshape(-1, 3)
+
+
+def hierarchical_marching_cubes_sharded(func, params, lower, upper, depth, n_subcell_depth=2, top_depth=None, build_fn=None,
+                                        mc_fn=None, group=None):
+    """hierarchical_marching_cubes (src/kd_tree.py:357-399) with the subtrees sharded: the top of the level-set tree is built
+    replicated, every rank refines its share of the frontier boxes to split depth 3*(depth - n_subcell_depth) and extracts
+    the triangles of ITS OWN leaves; one variable-length all_gather of 36 B/triangle returns the whole soup to every rank.
+    Triangle ORDER is rank-major (canonicalise before comparing with the single-device call).
+    `mc_fn(func, params, leaf_lower, leaf_upper, n_subcell_depth)` defaults to extract_cell.extract_mesh_from_cells."""
+    import torch.distributed as dist
+    if mc_fn is None:
+        import extract_cell
+        mc_fn = extract_cell.extract_mesh_from_cells
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    split_depth = 3 * (depth - n_subcell_depth)
+    lo, hi = _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, rank, world, {})
+    tri = mc_fn(func, params, lo, hi, n_subcell_depth) if lo.shape[0] > 0 else np.zeros((0, 3, 3), np.float32)
+    tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
     if world == 1:
-        return lo, hi
-    backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    cnt = torch.tensor([lo.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-    pack = torch.zeros((cap, 6), dtype=torch.float32)
-    pack[:lo.shape[0], :3] = torch.from_numpy(lo)
-    pack[:lo.shape[0], 3:] = torch.from_numpy(hi)
-    parts = [torch.empty((cap, 6), dtype=torch.float32, device=dev) for _ in range(world)]
-    dist.all_gather(parts, pack.to(dev), group=group)
-    allp = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
-    return allp[:, :3].copy(), allp[:, 3:].copy()
+        return tri.reshape(-1, 3, 3)
+    import torch
+    parts = _gather_rows(tri, world, rank, group, 9, torch.float32)
+    return np.concatenate(parts).reshape(-1, 3, 3)
 
 
 def _gather_rows(local, world, rank, group, width, dtype):

@@ -959,6 +959,20 @@ def test_marching_cubes_shared_faces_evaluated_once(monkeypatch):
     np.testing.assert_array_equal(a, b)
 
 
+def test_marching_cubes_sharded_entry_point_world1():
+    """sharding.hierarchical_marching_cubes_sharded on one device (top levels, then ONE multi-root build of the frontier,
+    marching cubes over its leaves): the same triangles as kd_tree.hierarchical_marching_cubes, in a different order."""
+    import kd_tree
+    import sharding
+    p = sample_params("bunny")
+    func = make(p, "affine_fixed")
+    tri = kd_tree.hierarchical_marching_cubes(func, p, LO, HI, 6, n_subcell_depth=3)
+    stri = sharding.hierarchical_marching_cubes_sharded(func, p, LO, HI, 6, n_subcell_depth=3, top_depth=5)
+    canon = lambda a: np.unique(a.reshape(-1, 9), axis=0)
+    assert stri.shape == tri.shape and tri.shape[0] > 10000
+    np.testing.assert_array_equal(canon(stri), canon(tri))
+
+
 # ---------------------------------------------------------------------------------------------------
 # the caller of cast_rays (SURVEY 8(f) row 4): render.render_image
 # ---------------------------------------------------------------------------------------------------

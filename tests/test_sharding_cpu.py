@@ -69,8 +69,13 @@ def _worker(rank, world, port, q):
     cam = (eye, look, up, left, 30., 30., 12, 12)
     fcast = lambda f, p, cam_, o, init, it: rays.cast_rays_frustum(f, p, cam_, o, init_ranges=init, iter_counts=it)
     fr = sharding.cast_rays_frustum_sharded((octx,), (params,), cam, fopts, cast_fn=fcast)
+    # hierarchical marching cubes: subtrees sharded, every rank extracts its own leaves, triangles gathered
+    from niq_oracle import mc
+    mcf = lambda f, p, lo_, hi_, n: mc.extract_mesh_from_leaves(p, lo_, hi_, n)
+    tris = sharding.hierarchical_marching_cubes_sharded(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), 4,
+                                                        n_subcell_depth=2, top_depth=3, build_fn=build, mc_fn=mcf)
     if rank == 0:
-        q.put((t, h, c, n_ev, lo, hi, cd, cl, fi, fl, fr))
+        q.put((t, h, c, n_ev, lo, hi, cd, cl, fi, fl, fr, tris))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,7 +89,7 @@ def test_sharded_rays_and_tree_world2_gloo():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    t, h, c, n_ev, lo, hi, cd, cl, fi, fl, fr = q.get(timeout=500)
+    t, h, c, n_ev, lo, hi, cd, cl, fi, fl, fr, tris = q.get(timeout=500)
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
@@ -120,3 +125,8 @@ def test_sharded_rays_and_tree_world2_gloo():
     np.testing.assert_array_equal(fr[1], rh)
     np.testing.assert_array_equal(fr[2], rc)
     assert fr[3] == rn and (rh != 0).any()
+    # marching cubes: the gathered soup equals the single-process soup as a set of triangles
+    ref_tris = tree.hierarchical_marching_cubes(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), 4, n_subcell_depth=2)
+    canon_t = lambda a: np.unique(np.asarray(a, np.float32).reshape(-1, 9), axis=0)
+    assert tris.shape == ref_tris.shape and tris.shape[0] > 100
+    np.testing.assert_array_equal(canon_t(tris), canon_t(ref_tris))
