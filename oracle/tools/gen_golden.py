@@ -283,13 +283,13 @@ def case_render(name, mode, res):
                 hit_ids=np.array(hit_ids, np.int32), n_eval=np.int64(n_eval), res=res)
 
 
-def case_frustum(names, mode, res, n_side, n_substeps=1):
+def case_frustum(names, mode, res, n_side, n_substeps=1, n_trunc=8):
     """queries.cast_rays_frustum (src/queries.py:178-587): out_t / out_hit_id / out_count as returned, (res_x, res_y)."""
     m = _ref_modules()
     jnp, queries, render = m["jnp"], m["queries"], m["render"]
     funcs, params = [], []
     for nm in names:
-        f, p = _load(m, nm, mode)
+        f, p = _load(m, nm, mode, **_mode_kwargs(mode, n_trunc))
         funcs.append(f)
         params.append(p)
     eye = jnp.array((2.0, 1.0, 2.0))
@@ -301,7 +301,7 @@ def case_frustum(names, mode, res, n_side, n_substeps=1):
     with np.errstate(all="ignore"):
         t, hit, cnt, n_evals = queries.cast_rays_frustum(tuple(funcs), tuple(params), cam, opts)
     return dict(eye=np.array(eye), look=np.array(look), up=np.array(up), left=np.array(left), res=res, n_side=n_side,
-                n_substeps=n_substeps, out_t=np.array(t, np.float32), out_hit_id=np.array(hit, np.int32),
+                n_substeps=n_substeps, n_trunc=n_trunc, out_t=np.array(t, np.float32), out_hit_id=np.array(hit, np.int32),
                 out_count=np.array(cnt, np.int32), n_evals=int(n_evals))
 
 
@@ -413,6 +413,8 @@ CASES["render_fox_fixed_r10"] = (case_render, ("fox", "affine_fixed", 10))      
 CASES["frust_fox_fixed_r12_s4"] = (case_frustum, (("fox",), "affine_fixed", 12, 4))
 CASES["frust_fox_bunny_interval_r10_s2_sub2"] = (case_frustum, (("fox", "bunny"), "interval", 10, 2, 2))
 CASES["frust_hammer_fixed_r9_s3_sub3"] = (case_frustum, (("hammer",), "affine_fixed", 9, 3, 3))
+CASES["frust_fox_slope_r10_s2"] = (case_frustum, (("fox",), "slope_interval", 10, 2))
+CASES["frust_fox_trunc_r8_s2"] = (case_frustum, (("fox",), "affine_truncate", 8, 2))
 CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))
 CASES["tree_fox_append_d9"] = (case_tree, ("fox", "affine_append", 4), dict(split_depth=9))
 CASES["rays_fox_fixed_r12"] = (case_cast_rays, (("fox",), "affine_fixed", 12))

@@ -324,6 +324,8 @@ FRUSTUM_CASES = {
     "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
     "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
     "frust_fox_bunny_interval_r10_s2_sub2": (("fox", "bunny"), "interval"),
+    "frust_fox_slope_r10_s2": (("fox",), "slope_interval"),
+    "frust_fox_trunc_r8_s2": (("fox",), "affine_truncate"),
 }
 
 
@@ -343,17 +345,17 @@ def test_cast_rays_frustum(case):
     g = golden(case)
     cam, opts = frustum_inputs(g)
     iters = []
-    t, hit, cnt, n_evals, tie = rays.cast_rays_frustum(tuple(net.AffineContext(mode) for _ in names), tuple(sample_params(n) for n in names),
+    t, hit, cnt, n_evals, tie = rays.cast_rays_frustum(tuple(ctx_for(mode, g.get("n_trunc", 8)) for _ in names), tuple(sample_params(n) for n in names),
                                                        cam, opts, return_near_tie=True, iter_counts=iters)
     ok = ~tie
     assert ok.mean() > 0.6 and t.shape == (int(g["res"]), int(g["res"]))
     np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
     np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
     np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
-    if mode == "affine_fixed":
-        assert (g["out_hit_id"] != 0).any()
-    else:                                                    # the loose interval bounds crawl: every frustum ends on the step limit
+    if mode == "interval":                                   # the loose interval bounds crawl: every frustum ends on the step limit
         assert (g["out_count"] > 100).all()
+    else:
+        assert (g["out_hit_id"] != 0).any()
     if not tie.any():
         assert n_evals == int(g["n_evals"])
     # host logic of the product (no GPU needed): initial tiles and the N_evals replay from per-iteration counts
