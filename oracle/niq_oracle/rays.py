@@ -245,10 +245,16 @@ def outward_normals(params_tuple, hit_pos, hit_ids, eps):
     return out
 
 
-def render_image(ctx_tuple, params_tuple, eye_pos, look_dir, up_dir, res, fov_deg, opts):
-    """render.py:94-150 with frustum=False, shading='normal', no tonemap."""
+def render_image(ctx_tuple, params_tuple, eye_pos, look_dir, up_dir, res, fov_deg, opts, frustum=False, left_dir=None):
+    """render.py:94-150 with shading='normal', no tonemap; frustum=True takes the cast_rays_frustum branch (:116-126), whose
+    (res_x, res_y) images are transposed into the ray order of generate_camera_rays."""
     roots, dirs = generate_camera_rays(eye_pos, look_dir, up_dir, res=res, fov_deg=fov_deg)
-    t, hit, cnt, n_eval = cast_rays(ctx_tuple, params_tuple, roots, dirs, opts)
+    if frustum:
+        cam = (eye_pos, look_dir, up_dir, left_dir, fov_deg, fov_deg, res, res)
+        t, hit, cnt, n_eval = cast_rays_frustum(ctx_tuple, params_tuple, cam, opts)
+        t, hit, cnt = t.transpose().flatten(), hit.transpose().flatten(), cnt.transpose().flatten()
+    else:
+        t, hit, cnt, n_eval = cast_rays(ctx_tuple, params_tuple, roots, dirs, opts)
     hit_pos = (roots + t[:, None] * dirs).astype(F32)
     nrm = outward_normals(params_tuple, hit_pos, hit, opts["hit_eps"])
     color = ((nrm + F32(1.)) / F32(2.)).astype(F32)

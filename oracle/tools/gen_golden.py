@@ -270,17 +270,19 @@ def case_pe(mode, n_trunc=8):
     return out
 
 
-def case_render(name, mode, res):
-    """render.render_image (src/render.py:94-150): frustum=False, shading='normal' -- image, depth, counts, hit ids."""
+def case_render(name, mode, res, frustum=False, n_side=16):
+    """render.render_image (src/render.py:94-150): shading='normal' -- image, depth, counts, hit ids; ray or frustum branch."""
     m = _ref_modules()
     jnp, render = m["jnp"], m["render"]
     func, params = _load(m, name, mode)
     eye = jnp.array((2., 1., 2.))
     look, up, left = render.look_at(eye)
     opts = m["queries"].get_default_cast_opts()
-    img, depth, counts, hit_ids, n_eval, _ = render.render_image(func, params, eye, look, up, left, res, 30., False, opts, shading="normal")
+    opts["n_side_init"] = n_side
+    with np.errstate(all="ignore"):
+        img, depth, counts, hit_ids, n_eval, _ = render.render_image(func, params, eye, look, up, left, res, 30., frustum, opts, shading="normal")
     return dict(img=np.array(img, np.float32), depth=np.array(depth, np.float32), counts=np.array(counts, np.int32),
-                hit_ids=np.array(hit_ids, np.int32), n_eval=np.int64(n_eval), res=res)
+                hit_ids=np.array(hit_ids, np.int32), n_eval=np.int64(n_eval), res=res, n_side=n_side)
 
 
 def case_frustum(names, mode, res, n_side, n_substeps=1, n_trunc=8):
@@ -410,6 +412,7 @@ CASES["tree_fox_slope_d12"] = (case_tree, ("fox", "slope_interval"), dict(split_
 for _mode in ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval"):   # sin + encode ops
     CASES[f"pe_{_mode}"] = (case_pe, (_mode,))
 CASES["render_fox_fixed_r10"] = (case_render, ("fox", "affine_fixed", 10))      # the caller of cast_rays
+CASES["render_frustum_fox_fixed_r14"] = (case_render, ("fox", "affine_fixed", 14, True, 2))
 CASES["frust_fox_fixed_r12_s4"] = (case_frustum, (("fox",), "affine_fixed", 12, 4))
 CASES["frust_fox_bunny_interval_r10_s2_sub2"] = (case_frustum, (("fox", "bunny"), "interval", 10, 2, 2))
 CASES["frust_hammer_fixed_r9_s3_sub3"] = (case_frustum, (("hammer",), "affine_fixed", 9, 3, 3))

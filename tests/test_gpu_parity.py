@@ -1156,6 +1156,25 @@ def test_cast_rays_frustum_tile_shares_equal_whole_image():
     assert sn == n_evals and (hit != 0).any()
 
 
+def test_render_image_frustum_branch_golden():
+    """render.render_image(frustum=True) against the unmodified reference (transposition into ray order, normals, shading)."""
+    import queries
+    import render
+    g = golden("render_frustum_fox_fixed_r14")
+    p = sample_params("fox")
+    func = make(p, "affine_fixed")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = int(g["n_side"])
+    img, depth, cnt, hit, n_eval, _ = render.render_image(func, p, eye, look, up, left, int(g["res"]), 30.0, True, opts)
+    np.testing.assert_array_equal(hit, g["hit_ids"])
+    np.testing.assert_array_equal(cnt, g["counts"])
+    assert n_eval == int(g["n_eval"])
+    np.testing.assert_allclose(depth, g["depth"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(img, g["img"], rtol=0, atol=2e-3)
+
+
 def test_cast_rays_frustum_uneven_tiles_non_square():
     """res_x != res_y and a tile count that divides neither (initial tiles of 3-4 x 2-3 pixels) against the oracle."""
     import queries

@@ -320,6 +320,23 @@ def test_render_image():
     assert np.all(img[g["hit_ids"] == 0] == 1.0)
 
 
+def test_render_image_frustum_branch():
+    """render_image(frustum=True) of the unmodified reference: the frustum images transposed into ray order, normals from
+    the generate_camera_rays directions (src/render.py:116-132)."""
+    g = golden("render_frustum_fox_fixed_r14")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = rays.look_at(eye)
+    opts = rays.get_default_cast_opts()
+    opts["n_side_init"] = int(g["n_side"])
+    img, depth, cnt, hit, n_eval = rays.render_image((net.AffineContext("affine_fixed"),), (sample_params("fox"),), eye, look, up,
+                                                     int(g["res"]), 30.0, opts, frustum=True, left_dir=left)
+    np.testing.assert_array_equal(hit, g["hit_ids"])
+    np.testing.assert_array_equal(cnt, g["counts"])
+    assert n_eval == int(g["n_eval"]) and (g["hit_ids"] != 0).sum() > 10
+    np.testing.assert_allclose(depth, g["depth"], rtol=RTOL, atol=0)
+    np.testing.assert_allclose(img, g["img"], rtol=0, atol=2e-3)
+
+
 FRUSTUM_CASES = {
     "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
     "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
