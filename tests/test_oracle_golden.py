@@ -395,3 +395,40 @@ def test_initial_frusta_uneven_tiles():
     np.testing.assert_array_equal(init[::16, 1], yt[:-1])
     np.testing.assert_array_equal(init[::16, 3], yt[1:])
     assert ((init[:, 2] - init[:, 0]) * (init[:, 3] - init[:, 1])).sum() == 50 * 37
+
+
+def test_mc_lattice_coordinates_on_shared_faces_are_bit_identical():
+    """The premise of the product's shared-face evaluation (csrc: k_mc_neighbours / mc_val): when the low face of a leaf
+    coincides exactly with the high face of another leaf (float-equal bounds), the lattice coordinates the reference's
+    linspace formula (src/extract_cell.py:372-381) gives the two leaves on that face are the same bits -- first sample = lo
+    exactly, last sample = hi itself, the other two axes from identical inputs -- so evaluating them once changes nothing.
+    Checked on the leaves of a real tree (dyadic bounds) and on leaves with non-dyadic bounds."""
+    from niq_oracle import mc
+    p = sample_params("fox")
+    r = tree.construct_uniform_unknown_levelset_tree(net.AffineContext("affine_fixed"), p, np.full(3, -1, np.float32),
+                                                     np.full(3, 1, np.float32), split_depth=9)
+    v = r["unknown_node_valid"]
+    lo, hi = r["unknown_node_lower"][v], r["unknown_node_upper"][v]
+    rng = np.random.default_rng(0)
+    base = rng.uniform(-1, 1, (40, 3)).astype(np.float32)
+    ext = rng.uniform(0.01, 0.3, (40, 3)).astype(np.float32)
+    lo2 = np.concatenate((base, base + np.array([1, 0, 0], np.float32) * ext))          # second half: x-neighbours of the first
+    hi2 = np.concatenate((base + ext, (base + np.array([1, 0, 0], np.float32) * ext) + ext)).astype(np.float32)
+    hi2[:40, 0] = lo2[40:, 0]                                                           # make the shared face exact
+    hi2[40:, 1:] = hi2[:40, 1:]
+    n_pairs = 0
+    for lo_, hi_ in ((lo, hi), (lo2.astype(np.float32), hi2)):
+        grid = mc.lattice_points(lo_, hi_, 3)                                           # (L, 9, 9, 9, 3)
+        key = {tuple(a.tolist()): i for i, a in enumerate(lo_)}
+        for i in range(lo_.shape[0]):
+            for d in range(3):
+                k = lo_[i].copy()
+                k[d] = lo_[i, d] - (hi_[i, d] - lo_[i, d])
+                j = key.get(tuple(k.tolist()))
+                if j is None or j == i or hi_[j, d] != lo_[i, d] or any(hi_[j, e] != hi_[i, e] for e in range(3) if e != d):
+                    continue
+                mine = np.take(grid[i], 0, axis=d)                                      # my low face
+                theirs = np.take(grid[j], 8, axis=d)                                    # their high face
+                assert np.array_equal(mine.view(np.uint32), theirs.view(np.uint32))
+                n_pairs += 1
+    assert n_pairs > 100
