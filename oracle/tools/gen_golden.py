@@ -285,7 +285,7 @@ def case_render(name, mode, res, frustum=False, n_side=16):
                 hit_ids=np.array(hit_ids, np.int32), n_eval=np.int64(n_eval), res=res, n_side=n_side)
 
 
-def case_frustum(names, mode, res, n_side, n_substeps=1, n_trunc=8):
+def case_frustum(names, mode, res, n_side, n_substeps=1, n_trunc=8, res_y=None):
     """queries.cast_rays_frustum (src/queries.py:178-587): out_t / out_hit_id / out_count as returned, (res_x, res_y)."""
     m = _ref_modules()
     jnp, queries, render = m["jnp"], m["queries"], m["render"]
@@ -299,11 +299,12 @@ def case_frustum(names, mode, res, n_side, n_substeps=1, n_trunc=8):
     opts = queries.get_default_cast_opts()
     opts["n_side_init"] = n_side
     opts["n_substeps"] = n_substeps
-    cam = (eye, look, up, left, 30., 30., res, res)
+    res_y = res if res_y is None else res_y
+    cam = (eye, look, up, left, 30., 30. if res_y == res else 22., res, res_y)          # a second fov for the non-square case
     with np.errstate(all="ignore"):
         t, hit, cnt, n_evals = queries.cast_rays_frustum(tuple(funcs), tuple(params), cam, opts)
     return dict(eye=np.array(eye), look=np.array(look), up=np.array(up), left=np.array(left), res=res, n_side=n_side,
-                n_substeps=n_substeps, n_trunc=n_trunc, out_t=np.array(t, np.float32), out_hit_id=np.array(hit, np.int32),
+                n_substeps=n_substeps, n_trunc=n_trunc, res_y=res_y, fov_y=np.float32(30. if res_y == res else 22.), out_t=np.array(t, np.float32), out_hit_id=np.array(hit, np.int32),
                 out_count=np.array(cnt, np.int32), n_evals=int(n_evals))
 
 
@@ -416,6 +417,7 @@ CASES["render_frustum_fox_fixed_r14"] = (case_render, ("fox", "affine_fixed", 14
 CASES["frust_fox_fixed_r12_s4"] = (case_frustum, (("fox",), "affine_fixed", 12, 4))
 CASES["frust_fox_bunny_interval_r10_s2_sub2"] = (case_frustum, (("fox", "bunny"), "interval", 10, 2, 2))
 CASES["frust_hammer_fixed_r9_s3_sub3"] = (case_frustum, (("hammer",), "affine_fixed", 9, 3, 3))
+CASES["frust_fox_fixed_r13x9_s3"] = (case_frustum, (("fox",), "affine_fixed", 13, 3), dict(res_y=9))   # res_x != res_y, fov_x != fov_y
 CASES["frust_fox_slope_r10_s2"] = (case_frustum, (("fox",), "slope_interval", 10, 2))
 CASES["frust_fox_trunc_r8_s2"] = (case_frustum, (("fox",), "affine_truncate", 8, 2))
 CASES["tree_fox_sdf_d12"] = (case_tree, ("fox", "sdf", 1.0), dict(split_depth=12, with_interior_nodes=True))

@@ -1019,6 +1019,7 @@ FRUSTUM_CASES = {
     "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
     "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
     "frust_fox_bunny_interval_r10_s2_sub2": (("fox", "bunny"), "interval"),
+    "frust_fox_fixed_r13x9_s3": (("fox",), "affine_fixed"),           # res_x != res_y and fov_x != fov_y
     "frust_fox_slope_r10_s2": (("fox",), "slope_interval"),          # persistent kernel over the 9-row slope tile
     "frust_fox_trunc_r8_s2": (("fox",), "affine_truncate"),          # host-level loop over the grow kernel
 }
@@ -1030,7 +1031,9 @@ def _frustum_inputs(g):
     opts["n_side_init"] = int(g["n_side"])
     opts["n_substeps"] = int(g["n_substeps"])
     res = int(g["res"])
-    return (g["eye"], g["look"], g["up"], g["left"], 30.0, 30.0, res, res), opts
+    res_y = int(g["res_y"]) if "res_y" in g else res
+    fov_y = float(g["fov_y"]) if "fov_y" in g else 30.0
+    return (g["eye"], g["look"], g["up"], g["left"], 30.0, fov_y, res, res_y), opts
 
 
 @pytest.mark.parametrize("case", sorted(FRUSTUM_CASES))

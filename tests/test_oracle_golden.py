@@ -341,6 +341,7 @@ FRUSTUM_CASES = {
     "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
     "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
     "frust_fox_bunny_interval_r10_s2_sub2": (("fox", "bunny"), "interval"),
+    "frust_fox_fixed_r13x9_s3": (("fox",), "affine_fixed"),           # res_x != res_y and fov_x != fov_y
     "frust_fox_slope_r10_s2": (("fox",), "slope_interval"),
     "frust_fox_trunc_r8_s2": (("fox",), "affine_truncate"),
 }
@@ -351,7 +352,9 @@ def frustum_inputs(g):
     opts["n_side_init"] = int(g["n_side"])
     opts["n_substeps"] = int(g["n_substeps"])
     res = int(g["res"])
-    return (g["eye"], g["look"], g["up"], g["left"], 30.0, 30.0, res, res), opts
+    res_y = int(g["res_y"]) if "res_y" in g else res
+    fov_y = float(g["fov_y"]) if "fov_y" in g else 30.0
+    return (g["eye"], g["look"], g["up"], g["left"], 30.0, fov_y, res, res_y), opts
 
 
 @pytest.mark.parametrize("case", sorted(FRUSTUM_CASES))
@@ -365,7 +368,7 @@ def test_cast_rays_frustum(case):
     t, hit, cnt, n_evals, tie = rays.cast_rays_frustum(tuple(ctx_for(mode, g.get("n_trunc", 8)) for _ in names), tuple(sample_params(n) for n in names),
                                                        cam, opts, return_near_tie=True, iter_counts=iters)
     ok = ~tie
-    assert ok.mean() > 0.6 and t.shape == (int(g["res"]), int(g["res"]))
+    assert ok.mean() > 0.6 and t.shape == g["out_t"].shape
     np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
     np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
     np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
@@ -378,9 +381,9 @@ def test_cast_rays_frustum(case):
     # host logic of the product (no GPU needed): initial tiles and the N_evals replay from per-iteration counts
     import queries
     n_side = int(g["n_side"])
-    init = queries._initial_frusta(int(g["res"]), int(g["res"]), n_side)
+    init = queries._initial_frusta(cam[6], cam[7], n_side)
     assert init.shape == (n_side * n_side, 4) and init.dtype == np.int32
-    assert ((init[:, 2] - init[:, 0]) * (init[:, 3] - init[:, 1])).sum() == int(g["res"]) ** 2
+    assert ((init[:, 2] - init[:, 0]) * (init[:, 3] - init[:, 1])).sum() == cam[6] * cam[7]
     assert queries._frustum_n_evals(n_side * n_side, [a for a, _ in iters], [b for _, b in iters]) == n_evals
 
 
