@@ -1019,7 +1019,6 @@ FRUSTUM_CASES = {
     "frust_fox_fixed_r12_s4": (("fox",), "affine_fixed"),
     "frust_hammer_fixed_r9_s3_sub3": (("hammer",), "affine_fixed"),
     "frust_fox_bunny_interval_r10_s2_sub2": (("fox", "bunny"), "interval"),
-    "frust_fox_fixed_r13x9_s3": (("fox",), "affine_fixed"),           # res_x != res_y and fov_x != fov_y
     "frust_fox_slope_r10_s2": (("fox",), "slope_interval"),          # persistent kernel over the 9-row slope tile
     "frust_fox_trunc_r8_s2": (("fox",), "affine_truncate"),          # host-level loop over the grow kernel
 }
@@ -1198,3 +1197,26 @@ def test_cast_rays_frustum_uneven_tiles_non_square():
     np.testing.assert_allclose(t[ok], ot[ok], rtol=RTOL, atol=0)
     if not (tie | otie).any():
         assert n_evals == on
+
+
+def test_cast_rays_frustum_non_square_two_fov_golden():
+    """res_x != res_y and fov_x != fov_y (13x9 pixels, 30 / 22 degrees) against the unmodified reference: pins which axis every
+    camera constant belongs to.  Kernel and host-level loop."""
+    import _niq
+    import queries
+    g = golden("frust_fox_fixed_r13x9_s3")
+    cam, opts = _frustum_inputs(g)
+    assert cam[6] == 13 and cam[7] == 9 and cam[5] == 22.0
+    p = sample_params("fox")
+    funcs = (make(p, "affine_fixed"),)
+    host_loop = lambda *a: queries._cast_rays_frustum_host_loop(_niq.default_context(), *a)
+    for impl in (queries.cast_rays_frustum, host_loop):
+        t, hit, cnt, n_evals, tie = impl(funcs, (p,), cam, opts, True)
+        assert t.shape == (13, 9)
+        ok = ~tie
+        assert ok.mean() > 0.6
+        np.testing.assert_array_equal(hit[ok], g["out_hit_id"][ok])
+        np.testing.assert_array_equal(cnt[ok], g["out_count"][ok])
+        np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
+        if not tie.any():
+            assert n_evals == int(g["n_evals"])
