@@ -7,6 +7,7 @@ The reference has no native boundary (its backend is XLA); the functions bound h
 jitted bodies of src/affine.py, src/queries.py and src/kd_tree.py -- see include/niq.h for the
 file:line each entry point stands in for.
 """
+import collections
 import ctypes as C
 import hashlib
 import os
@@ -116,13 +117,20 @@ class Context:
         self.handle = C.c_void_p()
         self.device = device
         check(lib().niq_ctx_create(C.c_int(device), C.byref(self.handle)))
-        self._mlp_cache = {}
+        self._mlp_cache = collections.OrderedDict()      # LRU: most recently used last
+        self._mlp_retired = collections.deque()          # evicted handles, closed a few evictions later
+
+    MLP_CACHE_SIZE = 64
+    MLP_RETIRE_DEPTH = 8
 
     def close(self):
         if self.handle:
             for m in self._mlp_cache.values():
                 m.close()
             self._mlp_cache.clear()
+            for m in self._mlp_retired:
+                m.close()
+            self._mlp_retired.clear()
             lib().niq_ctx_destroy(self.handle)
             self.handle = C.c_void_p()
 
@@ -210,12 +218,19 @@ class Context:
         so handles are cached by CONTENT hash, never by object identity."""
         key = params_digest(params)
         m = self._mlp_cache.get(key)
-        if m is None:
-            if len(self._mlp_cache) >= 64:
-                old = next(iter(self._mlp_cache))
-                self._mlp_cache.pop(old).close()
-            m = Mlp(self, params)
-            self._mlp_cache[key] = m
+        if m is not None:
+            self._mlp_cache.move_to_end(key)             # a hit refreshes the entry (true LRU)
+            return m
+        if len(self._mlp_cache) >= self.MLP_CACHE_SIZE:
+            # Evict the least recently used entry, but do not close it yet: a caller that fetched several handles for ONE
+            # query (find_any_intersection, cast_rays with two funcs) may still hold it.  It is closed MLP_RETIRE_DEPTH
+            # evictions later, far more lookups than any single call makes.
+            _, old = self._mlp_cache.popitem(last=False)
+            self._mlp_retired.append(old)
+            while len(self._mlp_retired) > self.MLP_RETIRE_DEPTH:
+                self._mlp_retired.popleft().close()
+        m = Mlp(self, params)
+        self._mlp_cache[key] = m
         return m
 
 

@@ -1,28 +1,14 @@
 // niq_api.cu -- the C ABI (include/niq.h): contexts, MLP packing, and the host-side drivers of the queries.
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo --fmad=false -shared -Xcompiler -fPIC
-#include <cuda_runtime.h>
-
-#include <algorithm>
-#include <cmath>
-#include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <string>
-#include <vector>
-
-#include "../../include/niq.h"
-#include "niq_grow.cuh"
-#include "niq_kernels.cuh"
-
-using namespace niq;
+// Build: see __graft_entry__.build (one translation unit per kernel family, linked into libniq.so).
+#define NIQ_HELPER_KERNELS
+#include "niq_internal.h"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_last_error;
 
-static int fail(int code, const char* fmt, ...) {
+int niq_fail(int code, const char* fmt, ...) {
     char buf[1024];
     va_list ap;
     va_start(ap, fmt);
@@ -32,79 +18,19 @@ static int fail(int code, const char* fmt, ...) {
     return code;
 }
 
-#define CU(expr)                                                                                    \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess)                                                                      \
-            return fail(e_ == cudaErrorMemoryAllocation ? NIQ_ENOMEM : NIQ_ECUDA, "%s failed: %s (%s:%d)", #expr, \
-                        cudaGetErrorString(e_), __FILE__, __LINE__);                                \
-    } while (0)
-#define TRY(expr)            \
-    do {                     \
-        int r_ = (expr);     \
-        if (r_ != NIQ_OK) return r_; \
-    } while (0)
-
 extern "C" const char* niq_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* niq_version(void) { return "niq-b200 0.1 (sm_100a)"; }
 
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-struct TimedLaunch { cudaEvent_t a, b; int family; };
-
-struct niq_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;          // side stream: the second shape of find_any_intersection runs beside the first
-    cudaEvent_t fork = nullptr, join = nullptr;
-    cudaDeviceProp prop{};
-    long long launches = 0;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    bool timing = false;
-    std::vector<TimedLaunch> pending;
-    std::vector<cudaEvent_t> event_pool;
-    double fam_ms[2] = {0, 0};
-    long long fam_launches[2] = {0, 0};
-    long long* pinned = nullptr;     // small pinned read-back area (64 x int64)
-    bool timer_armed = false, timer_started = false;   // niq_ctx_timer_start .. _stop bracket (see timer_touch / timer_mark)
-    unsigned long long* d_exec = nullptr;   // executed-MAC counter of the engine kernels (zero-skipping accounting)
-    bool count_exec = false;
-    long long mc_points_evaluated = 0, mc_points_lattice = 0;   // marching cubes: lattice points evaluated / the reference's count
-};
-
-struct DevBuf {   // stream-ordered temporary
-    niq_ctx* ctx; void* p = nullptr;
-    explicit DevBuf(niq_ctx* c) : ctx(c) {}
-    int alloc(size_t bytes) {
-        if (bytes == 0) bytes = 16;
-        cudaError_t e = cudaMallocAsync(&p, bytes, ctx->stream);
-        if (e != cudaSuccess) { p = nullptr; return fail(NIQ_ENOMEM, "cudaMallocAsync(%zu) failed: %s", bytes, cudaGetErrorString(e)); }
-        return NIQ_OK;
-    }
-    ~DevBuf() { if (p) cudaFreeAsync(p, ctx->stream); }
-    template <class T> T* as() { return reinterpret_cast<T*>(p); }
-    DevBuf(const DevBuf&) = delete;
-    DevBuf& operator=(const DevBuf&) = delete;
-};
-
-static cudaEvent_t get_event(niq_ctx* c) {
+cudaEvent_t niq_get_event(niq_ctx* c) {
     if (!c->event_pool.empty()) { cudaEvent_t e = c->event_pool.back(); c->event_pool.pop_back(); return e; }
     cudaEvent_t e = nullptr;
     cudaEventCreate(&e);
     return e;
 }
-struct LaunchTimer {   // brackets one kernel launch with events when timing is on
-    niq_ctx* c; int fam; cudaEvent_t a = nullptr, b = nullptr;
-    LaunchTimer(niq_ctx* ctx, int family) : c(ctx), fam(family) {
-        c->launches++;
-        if (c->timing && c->pending.size() < 8192) { a = get_event(c); b = get_event(c); cudaEventRecord(a, c->stream); }
-    }
-    ~LaunchTimer() {
-        if (a) { cudaEventRecord(b, c->stream); c->pending.push_back({a, b, fam}); }
-    }
-};
-static void resolve_timers(niq_ctx* c) {
+void niq_resolve_timers(niq_ctx* c) {
     for (auto& t : c->pending) {
         float ms = 0.f;
         if (cudaEventSynchronize(t.b) == cudaSuccess && cudaEventElapsedTime(&ms, t.a, t.b) == cudaSuccess) {
@@ -116,6 +42,8 @@ static void resolve_timers(niq_ctx* c) {
     }
     c->pending.clear();
 }
+#define resolve_timers niq_resolve_timers
+
 
 extern "C" int niq_ctx_create(int device, niq_ctx** out) {
     if (!out) return fail(NIQ_EINVAL, "niq_ctx_create: out is NULL");
@@ -127,10 +55,11 @@ extern "C" int niq_ctx_create(int device, niq_ctx** out) {
     if (device < 0 || device >= count) return fail(NIQ_EINVAL, "device %d out of range (have %d)", device, count);
     CU(cudaSetDevice(device));
     niq_ctx* c = new niq_ctx();
+    struct CtxGuard { niq_ctx* c; bool ok = false; ~CtxGuard() { if (!ok) niq_ctx_destroy(c); } } guard{c};   // no leak on any error path
     c->device = device;
     CU(cudaGetDeviceProperties(&c->prop, device));
-    if (c->prop.major < 9)
-        return fail(NIQ_ECUDA, "device compute capability %d.%d: kernels are built for sm_100a only", c->prop.major, c->prop.minor);
+    if (c->prop.major != 10)      // the library holds sm_100a code only: any other architecture would fail at the first launch
+        return fail(NIQ_ECUDA, "device compute capability %d.%d: kernels are built for sm_100a (B200) only", c->prop.major, c->prop.minor);
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     {   // stream-ordered temporaries (DevBuf) stay in the pool across synchronisations instead of going back to the OS
         cudaMemPool_t pool = nullptr;
@@ -147,13 +76,14 @@ extern "C" int niq_ctx_create(int device, niq_ctx** out) {
     CU(cudaMallocHost(&c->pinned, 64 * sizeof(long long)));
     CU(cudaMalloc(&c->d_exec, 8));
     CU(cudaMemset(c->d_exec, 0, 8));
+    guard.ok = true;
     *out = c;
     return NIQ_OK;
 }
 extern "C" int niq_ctx_destroy(niq_ctx* c) {
     if (!c) return NIQ_OK;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream) cudaStreamSynchronize(c->stream);
     resolve_timers(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     if (c->t0) cudaEventDestroy(c->t0);
@@ -187,13 +117,6 @@ extern "C" int niq_ctx_launch_count(niq_ctx* c, int64_t* out) {
 // niq_ctx_timer_start enqueues its work, t1 right after the last call has enqueued its last operation (BEFORE the
 // host waits for it), so the reading is the device time of the calls and does not include the wake-up latency of a
 // descheduled host thread (measured on the shared GPU box: up to a second of jitter on a 0.6 s step).
-static void timer_touch(niq_ctx* c) {
-    if (c->timer_armed && !c->timer_started) { cudaEventRecord(c->t0, c->stream); c->timer_started = true; }
-}
-static void timer_mark(niq_ctx* c) {
-    if (c->timer_armed && c->timer_started) cudaEventRecord(c->t1, c->stream);
-}
-#define FINAL_SYNC(c) do { timer_mark(c); CU(cudaStreamSynchronize((c)->stream)); } while (0)
 
 extern "C" int niq_ctx_mc_points(niq_ctx* c, int64_t* evaluated, int64_t* lattice, int reset) {
     if (!c || !evaluated || !lattice) return fail(NIQ_EINVAL, "bad argument");
@@ -318,45 +241,6 @@ extern "C" int niq_probe_ffma(niq_ctx* c, int blocks_per_sm, int threads, float*
 // ------------------------------------------------------------------------------------------------
 // MLP packing
 // ------------------------------------------------------------------------------------------------
-struct HostLayer { int in_dim, out_dim, in_pad, out_pad, act; bool dot; size_t w_off, b_off; };
-
-struct niq_mlp {
-    niq_ctx* ctx = nullptr;
-    std::vector<HostLayer> layers;
-    float* d_weights = nullptr;
-    float* d_bias = nullptr;
-    NetDev net{};
-    int wmax = 32;         // width class of the fixed-row engine
-    int maxw_pad = 8;      // widest padded row (grow engine)
-    int64_t macs = 0;
-    int total_floats = 0;  // packed weights of all layers
-    int sum_act_out = 0;   // sum of out_dim over activation layers (affine_all growth)
-    int max_act_out = 0;
-    int min_act_out = 1 << 30, n_act_layers = 0;
-};
-
-static int round_up(int x, int m) { return (x + m - 1) / m * m; }
-constexpr int kResidentPad = 512;   // floats after the resident weights: the pipelined loop over-reads one weight row
-
-// Decide where the weights of a launch live: resident in shared memory when everything fits beside the
-// activation buffers, otherwise streamed through the ring.  Returns the dynamic shared-memory size.
-template <class E>
-static size_t place_weights(niq_ctx* c, NetDev& net, int total_floats) {
-    net.exec_macs = c->count_exec ? c->d_exec : nullptr;
-    const size_t res = E::smem_bytes(total_floats + kResidentPad);
-    if (res <= c->prop.sharedMemPerBlockOptin) {
-        net.resident = 1;
-        net.w_region_floats = total_floats + kResidentPad;
-        return res;
-    }
-    net.resident = 0;
-    {   // development knob: head start (cycles) of warps 0-3 over warps 4-7 in the streamed ray kernel
-        const char* e = getenv("NIQ_DEPHASE");
-        net.dephase = e ? atoi(e) : 0;
-    }
-    return E::smem_bytes();
-}
-
 static bool invert3(const float* R, float* inv) {   // float32 Gauss-Jordan with partial pivoting
     float a[3][6];
     for (int i = 0; i < 3; ++i)
@@ -555,134 +439,6 @@ extern "C" int niq_mlp_macs(const niq_mlp* m, int64_t* macs) {
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
-template <class K>
-static int set_smem(K kernel, size_t bytes) {
-    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    return NIQ_OK;
-}
-static int grid_for(niq_ctx* c, long long n_pass) {
-    return (int)std::max<long long>(1, std::min<long long>(n_pass, c->prop.multiProcessorCount));
-}
-
-template <int WMAX>
-static int launch_classify_fixed_w(niq_ctx* c, NetDev net, int total_floats, const BoxSource& src, long long n, float offset,
-                                   int* label, float* lower, float* upper, unsigned char* tie) {
-    using E = Engine<WMAX, TileBox3>;
-    const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_classify_fixed<WMAX>, smem));
-    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
-    LaunchTimer lt(c, 0);
-    k_classify_fixed<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, src, n, offset, label, lower, upper, tie);
-    CU(cudaGetLastError());
-    return NIQ_OK;
-}
-template <int WMAX>
-static int launch_classify_slope_w(niq_ctx* c, NetDev net, int total_floats, const BoxSource& src, long long n, float offset,
-                                   int* label, float* lower, float* upper, unsigned char* tie) {
-    using E = Engine<WMAX, TileSlope3>;
-    const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_classify_slope<WMAX>, smem));
-    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
-    LaunchTimer lt(c, 0);
-    k_classify_slope<WMAX><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, src, n, offset, label, lower, upper, tie);
-    CU(cudaGetLastError());
-    return NIQ_OK;
-}
-static int launch_classify_slope(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
-                                 int* label, float* lower, float* upper, unsigned char* tie) {
-    if (n <= 0) return NIQ_OK;
-    switch (m->wmax) {
-        case 32: return launch_classify_slope_w<32>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-        case 64: return launch_classify_slope_w<64>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-        case 128: return launch_classify_slope_w<128>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-        default: return launch_classify_slope_w<256>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-    }
-}
-template <int WMAX>
-static int launch_eval_points_w(niq_ctx* c, NetDev net, int total_floats, const PointSource& src, long long n, float* f, float* scale) {
-    using E = Engine<WMAX, TilePts>;
-    const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_eval_points<WMAX>, smem));
-    const long long per = kWarps * E::WARP_ROWS;
-    LaunchTimer lt(c, 0);
-    k_eval_points<WMAX><<<grid_for(c, (n + per - 1) / per), kThreads, smem, c->stream>>>(net, src, n, f, scale);
-    CU(cudaGetLastError());
-    return NIQ_OK;
-}
-template <int WMAX, class Tile>
-static int launch_cast_rays_wt(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, long long n, int interval,
-                               const float* roots, const float* dirs, float* t, int* hit, int* cnt,
-                               unsigned char* tie, unsigned long long* queue) {
-    using E = Engine<WMAX, Tile>;
-    const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_cast_rays<WMAX, Tile>, smem));
-    const long long n_pass = (n + E::CTA_TILES - 1) / E::CTA_TILES;
-    LaunchTimer lt(c, 0);
-    k_cast_rays<WMAX, Tile><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
-    CU(cudaGetLastError());
-    return NIQ_OK;
-}
-template <int WMAX>
-static int launch_cast_rays_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, long long n, int interval,
-                              const float* roots, const float* dirs, float* t, int* hit, int* cnt,
-                              unsigned char* tie, unsigned long long* queue, bool slope = false) {
-    if (slope) return launch_cast_rays_wt<WMAX, TileRaySlope>(c, net, total_floats, o, n, 0, roots, dirs, t, hit, cnt, tie, queue);
-    return launch_cast_rays_wt<WMAX, TileRay>(c, net, total_floats, o, n, interval, roots, dirs, t, hit, cnt, tie, queue);
-}
-static int launch_classify_fixed(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
-                                 int* label, float* lower, float* upper, unsigned char* tie) {
-    if (n <= 0) return NIQ_OK;
-    switch (m->wmax) {
-        case 32: return launch_classify_fixed_w<32>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-        case 64: return launch_classify_fixed_w<64>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-        case 128: return launch_classify_fixed_w<128>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-        default: return launch_classify_fixed_w<256>(c, m->net, m->total_floats, src, n, offset, label, lower, upper, tie);
-    }
-}
-static int launch_eval_points(niq_ctx* c, const niq_mlp* m, const PointSource& src, long long n, float* f, float* scale) {
-    if (n <= 0) return NIQ_OK;
-    switch (m->wmax) {
-        case 32: return launch_eval_points_w<32>(c, m->net, m->total_floats, src, n, f, scale);
-        case 64: return launch_eval_points_w<64>(c, m->net, m->total_floats, src, n, f, scale);
-        case 128: return launch_eval_points_w<128>(c, m->net, m->total_floats, src, n, f, scale);
-        default: return launch_eval_points_w<256>(c, m->net, m->total_floats, src, n, f, scale);
-    }
-}
-
-static int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, BoxSource src, long long n,
-                                float offset, int* label, float* lower, float* upper, unsigned char* tie) {
-    if (n <= 0) return NIQ_OK;
-    if (m->maxw_pad > 128)
-        return fail(NIQ_EUNSUPPORTED, "affine_all / affine_truncate support hidden widths up to 128 (state matrix must fit shared memory)");
-    GrowArgs g{};
-    g.src = src; g.n = n; g.offset = offset;
-    g.truncate = cfg->mode == NIQ_MODE_AFFINE_TRUNCATE;
-    g.n_keep = g.truncate ? cfg->truncate_count : 0;
-    g.n_append = cfg->mode == NIQ_MODE_AFFINE_APPEND ? cfg->truncate_count : 0;
-    const int v = src.kind == 0 ? src.v : 3;
-    if (g.truncate && g.n_keep < 0) return fail(NIQ_EINVAL, "affine_truncate: truncate_count must be >= 0");
-    if (cfg->mode == NIQ_MODE_AFFINE_APPEND && (g.n_append < 1 || g.n_append > m->min_act_out))
-        return fail(NIQ_EINVAL, "affine_append: n_append must be in 1..%d (the narrowest activation layer; jax.lax.top_k needs k <= width)", m->min_act_out);
-    g.kcap = g.truncate ? std::max(v, std::min(g.n_keep, v + m->sum_act_out)) + m->max_act_out
-             : g.n_append > 0 ? v + g.n_append * m->n_act_layers : v + m->sum_act_out;
-    g.kcap = round_up(std::max(g.kcap, 4), 4);   // keeps the aff matrix 16-byte aligned behind mags/rank
-    g.W = round_up(m->maxw_pad, 8);
-    g.label = label; g.lower = lower; g.upper = upper; g.near_tie = tie;
-    const size_t floats = (size_t)22 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W * (g.truncate ? 2 : 1) + 16;
-    const size_t bytes = floats * sizeof(float);
-    if (bytes > c->prop.sharedMemPerBlockOptin)
-        return fail(NIQ_EUNSUPPORTED, "affine state of %zu bytes exceeds shared memory (%zu): network too wide/deep for this mode", bytes, (size_t)c->prop.sharedMemPerBlockOptin);
-    TRY(set_smem(k_classify_grow, bytes));
-    int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_classify_grow, 256, bytes);
-    per_sm = std::max(per_sm, 1);
-    const int grid = (int)std::min<long long>(n, (long long)c->prop.multiProcessorCount * per_sm);
-    LaunchTimer lt(c, 0);
-    k_classify_grow<<<grid, 256, bytes, c->stream>>>(m->net, g);
-    CU(cudaGetLastError());
-    return NIQ_OK;
-}
-
 static int check_cfg(const niq_mode_cfg* cfg) {
     if (!cfg) return fail(NIQ_EINVAL, "mode cfg is NULL");
     if (cfg->mode < NIQ_MODE_INTERVAL || cfg->mode > NIQ_MODE_SLOPE_INTERVAL) return fail(NIQ_EINVAL, "invalid mode");
@@ -923,12 +679,8 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
         TRY(queue.alloc(8));
         CU(cudaMemsetAsync(queue.p, 0, 8, c->stream));
         const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
-        switch (wmax) {
-            case 32: TRY(launch_cast_rays_w<32>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
-            case 64: TRY(launch_cast_rays_w<64>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
-            case 128: TRY(launch_cast_rays_w<128>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
-            default: TRY(launch_cast_rays_w<256>(c, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(), dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope)); break;
-        }
+        TRY(launch_cast_rays(c, wmax, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(),
+                             dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope));
     } else {
         return fail(NIQ_EUNSUPPORTED, "cast_rays in this mode runs through the host-level stepping loop of the Python layer");
     }
@@ -965,25 +717,6 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
 // ------------------------------------------------------------------------------------------------
 // cast_rays_frustum (src/queries.py:178-587)
 // ------------------------------------------------------------------------------------------------
-template <int WMAX, class Tile>
-static int launch_cast_frustum_wt(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, const FrustCam& cam, int interval,
-                                  const FrustQueue& q, long long n_pixels) {
-    using E = Engine<WMAX, Tile>;
-    const size_t smem = place_weights<E>(c, net, total_floats);
-    TRY(set_smem(k_cast_frustum<WMAX, Tile>, smem));
-    const long long n_pass = (n_pixels + E::CTA_TILES - 1) / E::CTA_TILES;
-    LaunchTimer lt(c, 0);
-    k_cast_frustum<WMAX, Tile><<<grid_for(c, n_pass), kThreads, smem, c->stream>>>(net, o, cam, interval, q);
-    CU(cudaGetLastError());
-    return NIQ_OK;
-}
-template <int WMAX>
-static int launch_cast_frustum_w(niq_ctx* c, NetDev net, int total_floats, const CastOpts& o, const FrustCam& cam, int interval,
-                                 const FrustQueue& q, long long n_pixels, bool slope) {
-    if (slope) return launch_cast_frustum_wt<WMAX, TileFrustumSlope>(c, net, total_floats, o, cam, 0, q, n_pixels);
-    return launch_cast_frustum_wt<WMAX, TileFrustum>(c, net, total_floats, o, cam, interval, q, n_pixels);
-}
-
 extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs,
                                      const niq_cast_opts* o, const niq_camera* cam, float refine_width_fac, int64_t n_init,
                                      const int32_t* init_ranges, float* t, int32_t* hit_id, int32_t* count, int64_t* n_evals,
@@ -1053,12 +786,7 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
         CU(cudaGetLastError());
     }
     const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
-    switch (wmax) {
-        case 32: TRY(launch_cast_frustum_w<32>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
-        case 64: TRY(launch_cast_frustum_w<64>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
-        case 128: TRY(launch_cast_frustum_w<128>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
-        default: TRY(launch_cast_frustum_w<256>(c, net, total_floats, co, fc, interval, q, n, slope)); break;
-    }
+    TRY(launch_cast_frustum(c, wmax, net, total_floats, co, fc, interval, q, n, slope));
     {
         LaunchTimer lt(c, 1);
         const int blocks = (int)std::min<long long>((n + 7) / 8, 8ll * c->prop.multiProcessorCount);
@@ -1100,15 +828,6 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
 // ------------------------------------------------------------------------------------------------
 // level-set tree
 // ------------------------------------------------------------------------------------------------
-struct NodeList { float* lo = nullptr; float* hi = nullptr; long long n = 0, cap = 0; };
-
-struct niq_tree {
-    niq_ctx* ctx = nullptr;
-    NodeList lists[3];     // 0 unknown leaves, 1 interior, 2 exterior
-    long long stats[4] = {0, 0, 0, 0};
-    std::vector<long long> levels;   // 4 per level: nodes entering, unknown, negative, positive
-};
-
 static int list_reserve(niq_ctx* c, NodeList& L, long long need) {
     if (need <= L.cap) return NIQ_OK;
     long long cap = std::max<long long>(need, std::max<long long>(2 * L.cap, 1024));
@@ -1157,6 +876,11 @@ extern "C" int niq_tree_build_roots(niq_ctx* c, const niq_mlp* m, const niq_mode
     niq_tree* T = new niq_tree();
     T->ctx = c;
     struct Guard { niq_tree* t; bool ok = false; ~Guard() { if (!ok) niq_tree_destroy(t); } } guard{T};
+    {   // interval / affine_fixed / slope_interval: the whole build is one cooperative launch (niq_tree.cuh)
+        bool handled = false;
+        TRY(tree_build_persistent(c, m, cfg, n_roots, lower, upper, split_depth, node_thresh, offset, flags, bps, T, &handled));
+        if (handled) { guard.ok = true; *out = T; return NIQ_OK; }
+    }
 
     NodeList cur, nxt;
     struct ListGuard { niq_ctx* c; NodeList* L; ~ListGuard() { if (L->lo) cudaFreeAsync(L->lo, c->stream); if (L->hi) cudaFreeAsync(L->hi, c->stream); } } g1{c, &cur}, g2{c, &nxt};
@@ -1242,6 +966,7 @@ extern "C" int niq_tree_build_roots(niq_ctx* c, const niq_mlp* m, const niq_mode
         std::swap(cur, nxt);
         TRY(next_bucket(cur.n, &bucket));
         if (quit_next) break;
+        if (cur.n == 0) break;      // nothing left to refine: no later level can add a node (the reference would idle through them)
     }
     // hand the final frontier to the tree object
     T->lists[0] = cur;
@@ -1501,6 +1226,9 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
         // shape B on the side stream, beside shape A (the frontier is small: each launch alone leaves most SMs idle)
         CU(cudaEventRecord(c->fork, c->stream));
         CU(cudaStreamWaitEvent(c->stream2, c->fork, 0));
+        // from here on stream2 may be running kernels on this round's buffers: whatever path leaves the scope, the main
+        // stream first waits for the side stream, so the stream-ordered frees of the DevBufs cannot overtake it
+        struct JoinGuard { niq_ctx* c; ~JoinGuard() { cudaEventRecord(c->join, c->stream2); cudaStreamWaitEvent(c->stream, c->join, 0); } } jg{c};
         int rB = NIQ_OK;
         {
             const bool timing = c->timing;

@@ -275,6 +275,7 @@ k_classify_slope(const __grid_constant__ NetDev net, const BoxSource src, long l
 // radius = sqrt(sum_v ||vec_v||^2).  vals / scale come from k_eval_points on the centres (PointSource kind 3).
 // lower / upper = f -+ lipschitz * radius (ours: the reference returns only the label).
 // ------------------------------------------------------------------------------------------------
+#ifdef NIQ_HELPER_KERNELS
 __global__ void k_sdf_labels(const BoxSource src, long long n, const float* __restrict__ vals,
                              const float* __restrict__ scale, float lipschitz, float offset, float tie_rel,
                              int* __restrict__ label, float* __restrict__ lower, float* __restrict__ upper,
@@ -314,6 +315,7 @@ __global__ void k_sdf_labels(const BoxSource src, long long n, const float* __re
     }
 }
 
+#endif  // NIQ_HELPER_KERNELS
 // ------------------------------------------------------------------------------------------------
 // point evaluation: n points -> f (and the |.|-scale of the last dot product)
 // ------------------------------------------------------------------------------------------------
@@ -550,6 +552,7 @@ struct FrustQueue {
     unsigned int* hist_term; unsigned int* hist_ref; int n_bins;
 };
 
+#ifdef NIQ_HELPER_KERNELS
 __global__ void k_frustum_init(FrustQueue q, const int* __restrict__ ranges, long long n_init, float init_step) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < n_init) {
@@ -562,6 +565,7 @@ __global__ void k_frustum_init(FrustQueue q, const int* __restrict__ ranges, lon
     if (i == 0) { q.ctrl[0] = 0ull; q.ctrl[1] = (unsigned long long)n_init; q.ctrl[2] = (unsigned long long)n_init; q.ctrl[3] = 0ull; q.ctrl[4] = 0ull; }
 }
 
+#endif  // NIQ_HELPER_KERNELS
 // render.camera_ray (src/render.py:17-24): normalize(look + left*(tx*tan_x) + up*(ty*tan_y))
 __device__ __forceinline__ void frustum_cam_ray(const FrustCam& cam, float tx, float ty, float r[3]) {
     const float a = tx * cam.tan_x, b = ty * cam.tan_y;
@@ -804,6 +808,7 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
     eng.drain();
 }
 
+#ifdef NIQ_HELPER_KERNELS
 // a finished frustum paints its pixels: out[x * res_y + y] (the reference's (res_x, res_y) images)
 __global__ void k_frustum_fill(const FrustFin* __restrict__ fin, const unsigned long long* __restrict__ ctrl, int res_y,
                                float* __restrict__ out_t, int* __restrict__ out_hit, int* __restrict__ out_count,
@@ -834,6 +839,7 @@ __global__ void k_iter_hist(const int* __restrict__ count, long long n, int n_su
     }
 }
 
+#endif  // NIQ_HELPER_KERNELS
 // ------------------------------------------------------------------------------------------------
 // HBM-bound helpers: exclusive scan, tree split, compaction
 // ------------------------------------------------------------------------------------------------
@@ -868,6 +874,7 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
     return base + x - v;
 }
 
+#ifdef NIQ_HELPER_KERNELS
 // phase 1: per-tile sums
 __global__ void __launch_bounds__(kScanThreads) k_scan_tile_sums(const int* __restrict__ in, long long n,
                                                                   int* __restrict__ tile_sums) {
@@ -920,6 +927,7 @@ __global__ void k_tree_flags(const int* __restrict__ label, long long n, int* __
     if (b != 0u && (threadIdx.x & 31) == 0 && n_tie) atomicAdd(n_tie, (unsigned long long)__popc(b));
 }
 
+#endif  // NIQ_HELPER_KERNELS
 __device__ __forceinline__ int argmax3_first(float a, float b, float c) {
     int d = 0;
     float m = a;
@@ -928,6 +936,7 @@ __device__ __forceinline__ int argmax3_first(float a, float b, float c) {
     return d;
 }
 
+#ifdef NIQ_HELPER_KERNELS
 // Tree split in the reference's order (src/kd_tree.py:61-96): per batch of `bsz` nodes the children are
 // written as [A-children of the batch..., B-children of the batch...].  scan = exclusive scan of the
 // UNKNOWN flags (n+1 entries).  do_split = 0 copies the unknown nodes themselves (last round).
@@ -989,6 +998,7 @@ __global__ void k_split_interleaved(const float* __restrict__ lo, const float* _
     if (qid) { out_qid[oa] = qid[i]; out_qid[ob] = qid[i]; }
 }
 
+#endif  // NIQ_HELPER_KERNELS
 // ------------------------------------------------------------------------------------------------
 // find_any_intersection: per-node verdict (reference src/kd_tree.py:449-518)
 // ------------------------------------------------------------------------------------------------
@@ -1003,6 +1013,7 @@ __device__ __forceinline__ void sample_point7(const float* lo, const float* hi, 
     if (k >= 4) p[k - 4] = p[k - 4] + (s_or_neg >= 0.f ? s_or_neg : hi[k - 4] - lo[k - 4]) * -1.f;
 }
 
+#ifdef NIQ_HELPER_KERNELS
 __global__ void k_isect_logic(const float* __restrict__ lo, const float* __restrict__ hi, long long n,
                               const int* __restrict__ labA, const int* __restrict__ labB,
                               const float* __restrict__ valsA, const float* __restrict__ valsB, float eps_w,
@@ -1053,6 +1064,7 @@ __global__ void k_isect_logic(const float* __restrict__ lo, const float* __restr
     }
 }
 
+#endif  // NIQ_HELPER_KERNELS
 // ------------------------------------------------------------------------------------------------
 // closest_point: one round over the popped window (reference src/kd_tree.py:679-760)
 // ------------------------------------------------------------------------------------------------
@@ -1070,6 +1082,7 @@ struct CpRound {
     long long* stats;               // [1] node visits
 };
 
+#ifdef NIQ_HELPER_KERNELS
 __global__ void k_cp_eval(CpRound r) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= r.window) return;
@@ -1290,9 +1303,11 @@ __global__ void __launch_bounds__(kCpSmallThreads) k_cp_round_small(CpRound r, f
     }
 }
 
+#endif  // NIQ_HELPER_KERNELS
 // ------------------------------------------------------------------------------------------------
 // marching cubes over leaves (reference src/extract_cell.py:314-421, src/kd_tree.py:338-355)
 // ------------------------------------------------------------------------------------------------
+#ifdef NIQ_HELPER_KERNELS
 __constant__ unsigned long long c_mc_case_words[256] = NIQ_MC_CASE_WORDS_INIT;
 
 struct McArgs {
@@ -1481,5 +1496,7 @@ __global__ void __launch_bounds__(256) k_ffma_peak(float* out, int iters, float 
     const float s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7)) + ((y0 + y1) + (y2 + y3)) + ((y4 + y5) + (y6 + y7));
     if (s == 12345.678f) out[0] = s;
 }
+
+#endif  // NIQ_HELPER_KERNELS
 
 }  // namespace niq

@@ -30,7 +30,9 @@ def rank_pixels(res_x, res_y, tile, rank, world, tile_stride=1):
 
 def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y, tile=16, cast_fn=None, group=None):
     """cast_rays over the full image with the rays partitioned across the ranks of `group`; every rank
-    returns the full (out_t, out_hit_id, out_count, N_evals) like the single-device call.
+    returns the full (out_t, out_hit_id, out_count, N_evals) like the single-device call.  N_evals is the
+    reference's count for the WHOLE image (src/queries.py:137,164-173: padded lanes per iteration), replayed from the
+    gathered per-ray step counts -- not the sum of the per-shard counts, whose bucket padding differs.
     `cast_fn` defaults to queries.cast_rays (tests inject a CPU stand-in to exercise the plumbing)."""
     import torch
     import torch.distributed as dist
@@ -46,7 +48,7 @@ def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y
     if world == 1:
         out_t = np.zeros(n, np.float32); out_h = np.zeros(n, np.int32); out_c = np.zeros(n, np.int32)
         out_t[mine], out_h[mine], out_c[mine] = t, hit, cnt
-        return out_t, out_h, out_c, n_evals
+        return out_t, out_h, out_c, replay_n_evals(out_c, opts)
     # one gather of (idx, t, hit, count), padded to the largest shard
     backend = dist.get_backend(group)
     dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
@@ -60,8 +62,6 @@ def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y
     out = torch.empty((world, cap, 3), dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(out.view(-1, 3), pack, group=group) if backend == "nccl" else \
         dist.all_gather(list(out.unbind(0)), pack, group=group)
-    ev = torch.tensor([n_evals], dtype=torch.int64, device=dev)
-    dist.all_reduce(ev, group=group)
     out = out.cpu().numpy()
     out_t = np.zeros(n, np.float32); out_h = np.zeros(n, np.int32); out_c = np.zeros(n, np.int32)
     for r in range(world):
@@ -69,7 +69,31 @@ def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y
         out_t[idx] = out[r, :sizes[r], 0].view(np.float32)
         out_h[idx] = out[r, :sizes[r], 1]
         out_c[idx] = out[r, :sizes[r], 2]
-    return out_t, out_h, out_c, int(ev.item())
+    return out_t, out_h, out_c, replay_n_evals(out_c, opts)
+
+
+def replay_n_evals(count, opts):
+    """N_evals of src/queries.py:137,164-173 from the per-ray step counts of the whole image: every iteration evaluates
+    the current padded array (n_substeps lanes each), which shrinks to the next bucket size whenever the live rays fit
+    (src/bucketing.py:7-14,35-36).  The same replay niq_cast_rays does for one device."""
+    from bucketing import get_next_bucket_size
+    n_sub = int(opts['n_substeps'])
+    n_bins = int(opts['n_max_step']) // n_sub + 3
+    it = np.minimum((np.asarray(count, np.int64) + n_sub - 1) // n_sub, n_bins - 1)
+    hist = np.bincount(it, minlength=n_bins)
+    cur = valid = int(it.shape[0])
+    evals = 0
+    for k in range(1, n_bins):
+        if valid <= 0:
+            break
+        evals += cur * n_sub
+        valid -= int(hist[k])
+        if valid <= 0:
+            break
+        nb = get_next_bucket_size(valid)
+        if nb < cur:
+            cur = nb
+    return evals
 
 
 def cast_rays_frustum_sharded(funcs_tuple, params_tuple, cam_params, opts, cast_fn=None, group=None):

@@ -287,6 +287,7 @@ def closest_point(ctx, params, lower, upper, query_points, eps=0.001, batch_proc
     n_visits = 0
     max_top = top
     n_tie = 0
+    tie_query = np.zeros((Q,), bool)          # ours: queries that visited a near-tie box (diagnostic, results unaffected)
 
     def grow(a, n_new):
         g = np.zeros((n_new,) + a.shape[1:], a.dtype)
@@ -319,7 +320,9 @@ def closest_point(ctx, params, lower, upper, query_points, eps=0.001, batch_proc
         pts = (center[:, None, :] + ext[:, None, :] * _SAMPLE_OFFSETS[None, :, :]).astype(F32)
 
         lab, lo_b, up_b, sc_b = net.classify_box(params, ctx, lo, hi, return_scale=True)
-        n_tie += int((net.bound_near_tie(lo_b, up_b, 0.0, sc_b, rel=net.tie_rel(params)) & valid).sum())
+        tie_b = net.bound_near_tie(lo_b, up_b, 0.0, sc_b, rel=net.tie_rel(params)) & valid
+        n_tie += int(tie_b.sum())
+        tie_query[b_id[tie_b]] = True
         is_outside = (lab == net.SIGN_NEGATIVE) | (lab == net.SIGN_POSITIVE)
         vals = net.eval_points(params, pts.reshape(-1, 3)).reshape(-1, 7)
         spans = ~_all_same_sign(vals) & valid
@@ -343,7 +346,7 @@ def closest_point(ctx, params, lower, upper, query_points, eps=0.001, batch_proc
         n_rounds += 1
 
     if stats is not None:
-        stats.update(n_rounds=n_rounds, n_visits=n_visits, max_stack=max_top, n_near_tie=n_tie)
+        stats.update(n_rounds=n_rounds, n_visits=n_visits, max_stack=max_top, n_near_tie=n_tie, tie_query=tie_query)
     return min_dist, min_loc
 
 

@@ -98,11 +98,11 @@ def test_sharded_rays_and_tree_world2_gloo():
     eye = np.array((2., 1., 2.), np.float32)
     look, up, _ = rays.look_at(eye)
     roots, dirs = rays.generate_camera_rays(eye, look, up, res=24, fov_deg=30., res_y=16)
-    rt, rh, rc, _ = rays.cast_rays((octx,), (params,), roots, dirs, rays.get_default_cast_opts())
+    rt, rh, rc, rn_ev = rays.cast_rays((octx,), (params,), roots, dirs, rays.get_default_cast_opts())
     np.testing.assert_array_equal(t, rt)          # same oracle arithmetic per ray -> bit-identical after the gather
     np.testing.assert_array_equal(h, rh)
     np.testing.assert_array_equal(c, rc)
-    assert n_ev > 0
+    assert n_ev == rn_ev                          # the WHOLE image's padded-lane count, replayed from the gathered step counts
     ref = tree.construct_uniform_unknown_levelset_tree(octx, params, np.full(3, -1, np.float32), np.full(3, 1, np.float32), split_depth=9)
     v = ref["unknown_node_valid"]
     canon = lambda a, b: np.unique(np.concatenate((a, b), axis=1), axis=0)
