@@ -8,18 +8,23 @@ Headline workload (BASELINE.json configs[4], the one its metric "rays/sec (1080p
 random-init 3->256x8->1 ReLU MLP (glorot-normal A, b~N(0,1e-2^2), NumPy seed 0), 1920x1080 pinhole rays
 (eye (2,1,2), look-at origin, fov 30), queries.cast_rays, affine_fixed, default opts.  With this network every
 ray takes exactly n_max_step = 512 steps and none hits, so the full image is 1.06e9 ray-steps
-= 4.9 EFLOP; a "step" of this bench is therefore a STATED SUB-SAMPLE: every `tile_stride`-th 16x16 pixel
-tile of the image, dealt round-robin over the ranks (per-ray work is uniform, so rays/s of the sub-sample is
-rays/s of the image).  Per-GPU work is fixed as N grows ("weak").  One JSON line on stdout from rank 0.
+= 4.9 EFLOP (a minute per pass on one B200); a "step" of this bench is therefore a STATED, FIXED SUB-SAMPLE of the
+image: `--tiles-total` (296) 16x16 pixel tiles spread evenly over it = 75,776 rays x 512 steps, dealt round-robin to
+the N ranks -- the total work does not change with N ("strong" scaling).  One JSON line on stdout from rank 0.
 
 value   = rays/s, whole job, ray buffers already resident in HBM, CUDA-event timed on the context stream.
-e2e     = rays/s through the public Python API (queries.cast_rays, NumPy host buffers from pinned memory,
-          H2D + D2H inside the timed region), + for N > 1 the NCCL all_gather of the results.
-roofline= FP32-FMA bound (NOT hbm / tensor: 2.3 GFLOP per 24 B ray; tensor cores would break the 1e-5
-          parity bar): algorithmic flops (10*M per ray-step) / kernel time vs the FFMA peak
-          measured on this GPU by a register-only FFMA kernel.
-cpu_baseline / --impl reference = the CPU oracle (NumPy restatement of the reference; JAX is not installable
-          here, so the reference itself cannot run) on the host cores over a bounded sample.
+e2e     = rays/s through the public Python API (queries.cast_rays at N = 1, sharding.cast_rays_sharded at N > 1): host
+          buffers in and out, H2D + D2H inside the timed region, for N > 1 plus the NCCL all_gather of the device-resident
+          (t, hit, count) image (12 B/ray).
+roofline= FP32-FMA bound (NOT hbm / tensor: 2.3 GFLOP per 24 B ray; tensor cores would break the 1e-5 parity bar):
+          executed and algorithmic flops (10*M per ray-step) / kernel time vs the FFMA peak measured on
+          this GPU by a register-only FFMA kernel.
+tree    = the second half of BASELINE's metric, kd-tree boxes/s: the config's own depth-14 tree (full, latency-bound, does
+          not shard) and bunny split_depth 21 (1.79 M boxes) with the subtrees sharded over the N ranks (strong scaling).
+configs = BASELINE configs 1-4 on the reference's sample inputs (N = 1 only), each with its own roofline and a CPU baseline
+          timed in the same run.
+cpu_baseline / --impl reference = the CPU oracle (NumPy restatement of the reference; JAX is not installable here, so the
+          reference itself cannot run) on the host cores over a bounded sample of the same workload.
 """
 import argparse
 import json
@@ -142,24 +147,43 @@ def cpu_workers():
     return max(1, min(n, 64))
 
 
-def sample_rays(roots, dirs, n, seed=0):
-    """A bounded sample of the workload's rays: whole 16x16 tiles, seeded."""
+TILES_TOTAL = 296          # 4 x 74: at N = 8 every GPU still gets 37 tiles = 4 full waves of 148 CTAs x 16 rays
+
+
+def chosen_tiles(n_total):
+    """The stated sub-sample: n_total tiles spread evenly over the row-major tile grid of the image."""
     import sharding
     ntx, nty = sharding.tile_ids(RES_X, RES_Y, TILE)
-    rng = np.random.default_rng(seed)
-    tiles = rng.choice(ntx * nty, size=max(1, n // (TILE * TILE)), replace=False)
-    idx = []
-    for tl in tiles:
-        ty, tx = divmod(int(tl), ntx)
-        yy, xx = np.meshgrid(np.arange(ty * TILE, min((ty + 1) * TILE, RES_Y)), np.arange(tx * TILE, min((tx + 1) * TILE, RES_X)), indexing="ij")
-        idx.append((yy * RES_X + xx).reshape(-1))
-    idx = np.concatenate(idx)[:n]
-    return roots[idx], dirs[idx]
+    stride = max(1, (ntx * nty) // n_total)
+    return np.arange(0, ntx * nty, stride)[:n_total], ntx
+
+
+def pixels_of_tiles(tiles, ntx):
+    ty, tx = np.divmod(np.asarray(tiles, np.int64), ntx)
+    oy, ox = np.meshgrid(np.arange(TILE), np.arange(TILE), indexing="ij")
+    py = (ty[:, None, None] * TILE + oy[None]).reshape(len(tiles), -1)
+    px = (tx[:, None, None] * TILE + ox[None]).reshape(len(tiles), -1)
+    ok = (py < RES_Y) & (px < RES_X)
+    return (py * RES_X + px)[ok].astype(np.int64)
+
+
+def workload_config(n_tiles, world):
+    tiles, ntx = chosen_tiles(n_tiles)
+    return {
+        "workload": "BASELINE configs[4]: random-init 3->256x8->1 ReLU MLP (NumPy seed 0), 1920x1080 camera rays, "
+                    "queries.cast_rays affine_fixed, default opts (n_max_step 512: every ray runs all 512 steps, no hits)",
+        "rays_per_step": int(pixels_of_tiles(tiles, ntx).shape[0]), "ray_steps_per_ray": 512, "image": [RES_X, RES_Y], "tile": TILE,
+        "tiles_per_step": int(len(tiles)),
+        "sub_sample": "a fixed set of 16x16 tiles spread evenly over the image (every 27th tile of the row-major tile grid), dealt "
+                      "round-robin to the ranks; the full image is 2,073,600 rays = 4.9 EFLOP (bench.py --full-image casts it once)",
+        "parallelism": f"ray tiles x{world}", "l2": "256 MiB device buffer rewritten between timed steps (untimed)",
+    }
 
 
 def run_reference(args):
     """--impl reference: the CPU oracle port (the reference is pure Python on JAX, which is not installable in
-    this image, so there is nothing to build into oracle/_ref) on all host cores."""
+    this image, so there is nothing to build into oracle/_ref) on all host cores.  Same workload / config
+    as the GPU arm; each step is a bounded sample of that workload's rays (whole tiles of the same tile set)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -171,8 +195,10 @@ def run_reference(args):
     roots, dirs = rays.generate_camera_rays(eye, look, up, res=RES_X, fov_deg=30., res_y=RES_Y)
     opts = rays.get_default_cast_opts()
     nw = cpu_workers()
+    tiles, ntx = chosen_tiles(args.tiles_total)
     n_sample = int(os.environ.get("NIQ_BENCH_CPU_RAYS", 32 * nw))     # rays per step: a few seconds of CPU work
-    r, d = sample_rays(roots, dirs, n_sample)
+    idx = pixels_of_tiles(tiles[:max(1, n_sample // (TILE * TILE))], ntx)[:n_sample]
+    r, d = roots[idx], dirs[idx]
     n_sample = r.shape[0]
     with mp.get_context("fork").Pool(nw) as pool:
         for _ in range(args.warmup):
@@ -183,12 +209,13 @@ def run_reference(args):
             total += dt
             steps += st
     value = n_sample * args.steps / total
-    sample = f"{n_sample} rays (whole 16x16 tiles, seed 0) x all 512 steps per step, rays split over {nw} processes"
+    sample = (f"{n_sample} rays per step (the first whole 16x16 tiles of the GPU arm's tile set) x all 512 steps, rays split over "
+              f"{nw} processes x 1 BLAS thread")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(n_sample, 1, None),
+        "config": workload_config(args.tiles_total, args.gpus),
         "cpu_baseline": {"value": value, "unit": "rays/s", "cores": nw, "kind": "port", "sample": sample,
                          "ray_steps_per_s": steps / total},
         "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -197,20 +224,20 @@ def run_reference(args):
     print(json.dumps(out), flush=True)
 
 
-def workload_config(rays_per_step, world, tile_stride):
-    return {
-        "workload": "BASELINE configs[4]: random-init 3->256x8->1 ReLU MLP (NumPy seed 0), 1920x1080 camera rays, "
-                    "queries.cast_rays affine_fixed, default opts (n_max_step 512: every ray runs all 512 steps, no hits)",
-        "rays_per_step": int(rays_per_step), "ray_steps_per_ray": 512, "image": [RES_X, RES_Y], "tile": TILE,
-        "tile_stride": tile_stride, "sub_sample": "every tile_stride-th 16x16 tile of the image, dealt round-robin to ranks; "
-                                                  "the full image is 2,073,600 rays = 4.9 EFLOP",
-        "parallelism": f"ray tiles x{world}", "l2": "256 MiB device buffer rewritten between timed steps (untimed)",
-    }
-
-
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
+
+def dram_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, as extracted from the committed ncu --set full
+    capture by tools/ncu_traffic.py (profiles/r2_dram_traffic.json); None when no capture of that kernel is on record."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")) as f:
+            rec = json.load(f).get(kernel)
+        return rec
+    except (OSError, ValueError):
+        return None
+
 
 def run_ours(args):
     import torch
@@ -228,6 +255,7 @@ def run_ours(args):
 
     import _niq
     import implicit_mlp_utils
+    import kd_tree
     import queries
     import sharding
 
@@ -239,22 +267,18 @@ def run_ours(args):
     roots, dirs = camera_rays()
     opts = queries.get_default_cast_opts()
 
-    ntx, nty = sharding.tile_ids(RES_X, RES_Y, TILE)
-    tiles_per_rank = args.tiles
-    tile_stride = max(1, (ntx * nty) // (tiles_per_rank * world))
-    mine = sharding.rank_pixels(RES_X, RES_Y, TILE, rank, world, tile_stride)[:tiles_per_rank * TILE * TILE]
+    # ---- the fixed tile set, dealt round-robin: total work is the same for every N (strong scaling) ----
+    tiles, ntx = chosen_tiles(args.tiles_total)
+    pix_of = lambda r, w: pixels_of_tiles(tiles[r::w], ntx)
+    mine = pix_of(rank, world)
     n = int(mine.shape[0])
-    r_h = torch.from_numpy(roots[mine]).pin_memory()
-    d_h = torch.from_numpy(dirs[mine]).pin_memory()
+    n_all = int(pixels_of_tiles(tiles, ntx).shape[0])
     dev = torch.device("cuda", local)
-    r_d, d_d = r_h.to(dev), d_h.to(dev)
+    r_d, d_d = torch.from_numpy(roots[mine]).to(dev), torch.from_numpy(dirs[mine]).to(dev)
     t_d = torch.zeros(n, dtype=torch.float32, device=dev)
     h_d = torch.zeros(n, dtype=torch.int32, device=dev)
     c_d = torch.zeros(n, dtype=torch.int32, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    cap = tiles_per_rank * TILE * TILE            # shards differ in size (partial border tiles): the gather is padded to cap
-    gathered = torch.empty((world, cap, 3), dtype=torch.int32, device=dev) if world > 1 else None
-    pack_h = torch.zeros((cap, 3), dtype=torch.int32).pin_memory() if world > 1 else None
 
     def barrier():
         torch.cuda.synchronize()
@@ -267,12 +291,11 @@ def run_ours(args):
                                  c_d.data_ptr(), opts, want_n_evals=False, ctx=ctx)
 
     def e2e_step():
-        out = queries.cast_rays((func,), (params,), r_h.numpy(), d_h.numpy(), opts, ctx=ctx)
-        if world > 1:        # the one collective of the path: gather (t, hit, count) = 12 B/ray over NVLink
-            pack_h[:n] = torch.from_numpy(np.stack((out[0].view(np.int32), out[1], out[2]), axis=1))
-            dist.all_gather_into_tensor(gathered.view(-1, 3), pack_h.to(dev, non_blocking=True))
-            torch.cuda.synchronize()
-        return out
+        # the call a user makes: host arrays in, host arrays out (N > 1: the image's rays dealt over the ranks, results
+        # gathered over NVLink from the device buffers, every rank ends up with the whole result on the host)
+        if world == 1:
+            return queries.cast_rays((func,), (params,), roots[mine], dirs[mine], opts, ctx=ctx)
+        return sharding.cast_rays_sharded((func,), (params,), roots, dirs, opts, RES_X, RES_Y, TILE, pixels_of_rank=pix_of)
 
     # ---- warm-up ----
     for _ in range(max(args.warmup, 3)):
@@ -304,46 +327,79 @@ def run_ours(args):
     total_ms = float(sum(step_ms))
     ray_steps = int(c_d.sum().item())
 
-    # ---- e2e through the public API (host buffers) ----
+    # ---- e2e through the public API (host buffers); a few steps are enough for a stable mean ----
+    e2e_steps = max(1, min(args.steps, 5))
     e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
 
-    # ---- second half of BASELINE's metric: kd-tree boxes/s on the same network (configs[4]: depth-14 level-set tree).
-    # The tree of this network is full (nothing is pruned: 32,767 box classifications).  N = 1: the whole tree;
-    # N > 1: top levels replicated, subtrees dealt round-robin (sharding.tree_sharded) = strong scaling of one tree.
-    import kd_tree
+    # ---- kd-tree boxes/s (second half of BASELINE's metric) ----
     lo3, hi3 = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
-    TREE_DEPTH = 14
-
-    def tree_step():
-        if world == 1:
+    tree = {}
+    if rank == 0:
+        # (a) the config's own tree: depth 14 of the 8x256 net = a FULL tree (nothing pruned, 32,767 boxes), 15 dependent
+        # levels whose cost is the latency of one pass through the net: does not shard (replicas only), reported at N = 1 size
+        def d14():
             st = {}
-            out = kd_tree.construct_uniform_unknown_levelset_tree(func, params, lo3, hi3, split_depth=TREE_DEPTH, stats=st, ctx=ctx)
+            out = kd_tree.construct_uniform_unknown_levelset_tree(func, params, lo3, hi3, split_depth=14, stats=st, ctx=ctx)
             return int(out["unknown_node_valid"].sum()), st["n_evals"]
-        lo_l, hi_l = sharding.tree_sharded(func, params, lo3, hi3, TREE_DEPTH, ctx=ctx)
-        return int(lo_l.shape[0]), None
-
-    tree_step()
-    barrier()
-    tree_reps = 5
-    t0 = time.perf_counter()
-    for _ in range(tree_reps):
-        n_leaves, n_tree_evals = tree_step()
-    barrier()
-    tree_s = (time.perf_counter() - t0) / tree_reps
-    tree_dev_ms = None
-    if world == 1:
+        d14()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            n_leaves, n_boxes = d14()
+        d14_s = (time.perf_counter() - t0) / 5
         ctx.timer_start()
-        tr = kd_tree.build_tree(func, params, lo3, hi3, split_depth=TREE_DEPTH, ctx=ctx)
-        tree_dev_ms = ctx.timer_stop()
+        tr = kd_tree.build_tree(func, params, lo3, hi3, split_depth=14, ctx=ctx)
+        d14_dev_ms = ctx.timer_stop()
         tr.close()
+        tree["cfg5_depth14"] = {"value": n_boxes / d14_s, "unit": "boxes/s", "boxes": n_boxes, "leaves": n_leaves, "ms": d14_s * 1e3,
+                                "device_ms": d14_dev_ms, "boxes_per_s_device": n_boxes / (d14_dev_ms * 1e-3),
+                                "tflops_algorithmic_device": 10 * M * n_boxes / (d14_dev_ms * 1e-3) / 1e12,
+                                "scaling": "replicas only (15 dependent levels, each one pass through the net: latency-bound, rank 0 alone)",
+                                "kernel": "k_tree_persistent<256, TileBox3> (one cooperative launch per build)",
+                                "timer": "ms: wall clock through kd_tree.construct_uniform_unknown_levelset_tree incl. the leaf download; device_ms: CUDA events"}
+    barrier()
+    # (b) a tree that can scale: bunny.npz (8x64 ELU), split_depth 21 = 1.79 M boxes, 380 K leaves; N > 1: top levels replicated,
+    # subtrees dealt round-robin, leaves all-gathered from the device buffers (sharding.tree_sharded)
+    bunny = sample_mlp("bunny")
+    fb = implicit_mlp_utils.generate_implicit_from_params(bunny, "affine_fixed")
+    Mb = ctx.mlp(bunny).macs
 
-    # ---- optional: the WHOLE 1920x1080 image once (this rank's share of it for N > 1), to check the sub-sample's rate ----
+    def d21_device():            # until every rank holds all leaves in HBM
+        if world == 1:
+            tr = kd_tree.build_tree(fb, bunny, lo3, hi3, split_depth=21, ctx=ctx)
+            st, nl = tr.stats(), tr.count(0)
+            tr.close()
+            return nl, st["n_evals"]
+        out, counts = sharding.tree_sharded(fb, bunny, lo3, hi3, 21, to_host=False, ctx=ctx)
+        return int(sum(counts)), None
+
+    def d21_host():              # the public call: all leaves on the host of every rank
+        if world == 1:
+            out = kd_tree.construct_uniform_unknown_levelset_tree(fb, bunny, lo3, hi3, split_depth=21, ctx=ctx)
+            return int(out["unknown_node_valid"].sum())
+        return int(sharding.tree_sharded(fb, bunny, lo3, hi3, 21, ctx=ctx)[0].shape[0])
+
+    d21_device(); d21_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        n_leaves21, n_boxes21 = d21_device()
+    barrier()
+    d21_s = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    for _ in range(3):
+        d21_host()
+    barrier()
+    d21_host_s = (time.perf_counter() - t0) / 3
+    BOXES21 = 1786421 if n_boxes21 is None else n_boxes21      # boxes of the single-device tree (the sharded build classifies the
+                                                               # replicated top levels on every rank: not counted twice)
+
+    # ---- optional: the WHOLE 1920x1080 image once (this rank's share of it for N > 1) ----
     full_image = None
     if args.full_image:
         mine_full = sharding.rank_pixels(RES_X, RES_Y, TILE, rank, world, 1)
@@ -364,31 +420,39 @@ def run_ours(args):
         del rf, df, tf_, hf, cf
 
     if world > 1:
-        red = torch.tensor([total_ms, e2e_s, kernel_ms], dtype=torch.float64, device=dev)
+        red = torch.tensor([total_ms, e2e_s, kernel_ms, d21_s, d21_host_s], dtype=torch.float64, device=dev)
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kernel_ms = (float(x) for x in red.tolist())
+        total_ms, e2e_s, kernel_ms, d21_s, d21_host_s = (float(x) for x in red.tolist())
         rs = torch.tensor([ray_steps, n], dtype=torch.int64, device=dev)
         dist.all_reduce(rs)
-        ray_steps_all, n_all = (int(x) for x in rs.tolist())
+        ray_steps_all, n_sum = (int(x) for x in rs.tolist())
+        assert n_sum == n_all
     else:
-        ray_steps_all, n_all = ray_steps, n
+        ray_steps_all = ray_steps
 
     if rank == 0:
         value = n_all * args.steps / (total_ms * 1e-3)
         k_s = kernel_ms / max(kernel_launches, 1) * 1e-3                  # this rank's kernel, average launch duration
         algorithmic = flop_per_ray_step * ray_steps / k_s / 1e12         # reference formulation: every column of every layer
         achieved = 2.0 * exec_macs / max(kernel_launches, 1) / k_s / 1e12   # FMAs the kernel actually issued (device counter)
+        traffic = dram_traffic("k_cast_rays<256>")
         out = {
             "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(n_all, world, tile_stride),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(args.tiles_total, world),
             "ray_steps_per_s": ray_steps_all * args.steps / (total_ms * 1e-3),
-            "e2e": {"value": n_all * args.steps / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_all * 24,
-                    "d2h_bytes_per_step": n_all * 12, "timer": "wall clock around queries.cast_rays (+ all_gather for N>1)"},
+            "full_image_extrapolated_s": RES_X * RES_Y / value,
+            "e2e": {"value": n_all / e2e_s, "unit": "rays/s", "h2d_bytes_per_step": n_all * 24,
+                    "d2h_bytes_per_step": n_all * 12 * (world if world > 1 else 1), "steps": e2e_steps,
+                    "timer": "wall clock around queries.cast_rays (N = 1) / sharding.cast_rays_sharded (N > 1: + one NCCL all_gather of "
+                             "the device-resident results, every rank reads the whole image back)"},
             "gpu_launches": int(gpu_launches), "step_ms": [round(x, 2) for x in step_ms],
             "clocks": clk,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops,
-                         "traffic": 2.14e6, "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch from the ncu --set full capture of the same kernel at 18 tiles (profiles/r1_final_cast_rays256_ncu_full_summary.txt): 2.14 MB read (the weights once), 0 written; not memory-bound",
+                         "traffic": None if traffic is None else traffic["bytes_per_launch"],
+                         "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum per launch, read from profiles/r2_dram_traffic.json "
+                                         "(tools/ncu_traffic.py over the committed ncu --set full capture); null = no capture on record. "
+                                         "The kernel is not memory-bound: the weights are read once per CTA",
                          "achieved_algorithmic": algorithmic, "frac_algorithmic": algorithmic / peak_tflops,
                          "executed_over_algorithmic_flops": achieved / algorithmic,
                          "note": "achieved = EXECUTED FP32 FMA flops (device counter: columns that are exactly zero after a relu layer are skipped, "
@@ -399,130 +463,220 @@ def run_ours(args):
                          "kernel_ms_per_launch": kernel_ms / max(kernel_launches, 1),
                          "hbm_note": "not HBM-bound: 37 B per ray moved for 2.35 GFLOP"},
         }
-        full_tree_boxes = 2 ** (TREE_DEPTH + 1) - 1
-        out["tree"] = {"metric": "kd-tree boxes/s (construct_uniform_unknown_levelset_tree, same 8x256 ReLU MLP, affine_fixed, split_depth 14, domain [-1,1]^3)",
-                       "value": full_tree_boxes / tree_s, "unit": "boxes/s", "boxes": full_tree_boxes, "leaves": n_leaves,
-                       "ms": tree_s * 1e3, "scaling": "strong" if world > 1 else None,
-                       "timer": "wall clock through the public API incl. the leaf download (e2e); 15 levels, each a classify launch + scan/split",
-                       "device_ms": tree_dev_ms,
-                       "note": "full tree of the random-init net (no pruning): latency-bound (levels 0-7 hold <= 128 boxes); bunny depth-21 (1.79 M boxes) is in --extra"}
+        tree["bunny_depth21"] = {"value": BOXES21 / d21_s, "unit": "boxes/s", "boxes": BOXES21, "leaves": n_leaves21, "ms": d21_s * 1e3,
+                                 "scaling": "strong", "e2e": {"value": BOXES21 / d21_host_s, "unit": "boxes/s", "ms": d21_host_s * 1e3,
+                                                              "d2h_bytes": n_leaves21 * 24},
+                                 "tflops_algorithmic": 10 * Mb * BOXES21 / d21_s / 1e12,
+                                 "parallelism": "single cooperative kernel" if world == 1 else f"top levels replicated, subtrees dealt round-robin x{world}, "
+                                                "leaves all-gathered from device buffers (one NCCL all_gather_into_tensor of 24 B/leaf)",
+                                 "timer": "wall clock, max over ranks: value = until the leaves are in HBM (of every rank for N > 1); e2e = until every rank "
+                                          "holds them on the host (sharding.tree_sharded / kd_tree.construct_uniform_unknown_levelset_tree)"}
+        out["tree"] = {"metric": "kd-tree boxes/s (construct_uniform_unknown_levelset_tree, affine_fixed, domain [-1,1]^3)", **tree}
         # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores ----
         if world == 1 and not args.no_cpu:
             import multiprocessing as mp
             nw = cpu_workers()
-            n_s = 64 * nw
-            r, d = sample_rays(roots, dirs, n_s)
+            idx = pixels_of_tiles(tiles[:max(1, (64 * nw) // (TILE * TILE))], ntx)[:64 * nw]
+            r, d = roots[idx], dirs[idx]
             with mp.get_context("fork").Pool(nw) as pool:
                 cpu_cast_rays(params, r[:nw], d[:nw], opts, pool, nw)
                 dt, st = cpu_cast_rays(params, r, d, opts, pool, nw)
             out["cpu_baseline"] = {"value": r.shape[0] / dt, "unit": "rays/s", "cores": nw, "kind": "port",
-                                   "sample": f"{r.shape[0]} rays (whole 16x16 tiles, seed 0) x all 512 steps, {nw} processes x 1 BLAS thread",
+                                   "sample": f"{r.shape[0]} rays (the first whole 16x16 tiles of the step's tile set) x all 512 steps, {nw} processes x 1 BLAS thread",
                                    "ray_steps_per_s": st / dt}
         if full_image is not None:
             out["full_image"] = full_image
-        if args.extra:
-            out["extra"] = extra_metrics(ctx)
+        if world == 1 and not args.no_configs:
+            out["configs"] = config_metrics(ctx, peak_tflops, cpu=not args.no_cpu)
         print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
 
-def extra_metrics(ctx):
-    """Secondary numbers on the reference's sample inputs (BASELINE configs[0..3]); each timed once after a warm-up."""
+def sample_mlp(name):
+    with np.load(os.path.join(ROOT, "tests", "golden", "mlps.npz")) as d:
+        return {k.split("/", 1)[1]: d[k] for k in d.files if k.startswith(name + "/")}
+
+
+def cfg3_transforms(n, seed=0):
+    """rotation about z by U[0,2pi), translation U[-1.5,1.5]^3, np.random.default_rng(0)."""
+    rng = np.random.default_rng(seed)
+    Rs, ts = [], []
+    for _ in range(n):
+        th = rng.uniform(0, 2 * np.pi)
+        Rs.append(np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32))
+        ts.append(rng.uniform(-1.5, 1.5, 3).astype(np.float32))
+    return np.stack(Rs), np.stack(ts)
+
+
+# ---- CPU legs of the configs block: the oracle on bounded samples, one process each (1 BLAS thread) ----
+
+def _cpu_cfg(task):
+    from threadpoolctl import threadpool_limits
+    from niq_oracle import mc, net, rays, tree
+    lo, hi = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
+    kind = task[0]
+    with threadpool_limits(limits=1):
+        t0 = time.perf_counter()
+        if kind == "cfg1":
+            _, p, roots, dirs = task
+            out = rays.cast_rays((net.AffineContext("affine_fixed"),), (p,), roots, dirs, rays.get_default_cast_opts())
+            units = {"rays": int(roots.shape[0]), "ray_steps": int(out[2].sum())}
+        elif kind == "cfg2_tree":
+            _, p, depth = task
+            st = {}
+            tree.construct_uniform_unknown_levelset_tree(net.AffineContext("affine_fixed"), p, lo, hi, split_depth=depth, stats=st)
+            units = {"boxes": int(st["n_evals"])}
+        elif kind == "cfg2_mc":
+            _, p, llo, lhi = task
+            tri = mc.extract_mesh_from_leaves(p, llo, lhi, 3)
+            units = {"leaves": int(llo.shape[0]), "triangles": int(np.asarray(tri).reshape(-1, 9).shape[0])}
+        elif kind == "cfg3":
+            _, pA, pB, R, t = task
+            c = net.AffineContext("affine_truncate", truncate_count=64)
+            nodes = 0
+            for i in range(R.shape[0]):
+                st = {}
+                tree.find_any_intersection((c, c), (pA, net.prepend_op(pB, net.spatial_transformation(R[i], t[i]))), lo, hi, 1e-3, stats=st)
+                nodes += st["n_nodes"]
+            units = {"queries": int(R.shape[0]), "nodes": int(nodes)}
+        else:
+            _, p, q = task
+            st = {}
+            tree.closest_point(net.AffineContext("affine_fixed"), p, lo, hi, q, eps=1e-3, batch_process_size=2048, stats=st)
+            units = {"queries": int(q.shape[0]), "visits": int(st["n_visits"])}
+        return kind, time.perf_counter() - t0, units
+
+
+def config_metrics(ctx, peak_tflops, cpu=True):
+    """BASELINE configs 1-4 on the reference's sample inputs: absolute numbers, fraction of the measured FFMA peak
+    (algorithmic flops of SURVEY.md 8(d); executed flops from the device counter where the engine runs), and the CPU oracle
+    timed in the same run on a bounded sample (one process per leg, 1 BLAS thread)."""
     import implicit_mlp_utils
     import kd_tree
+    import mlp
     import queries
     import render
-    with np.load(os.path.join(ROOT, "tests", "golden", "mlps.npz")) as d:
-        mlps = {nm: {k.split("/", 1)[1]: d[k] for k in d.files if k.startswith(nm + "/")} for nm in ("fox", "bunny", "hammer", "birdcage_occ")}
+    mlps = {nm: sample_mlp(nm) for nm in ("fox", "bunny", "hammer", "birdcage_occ")}
     lo, hi = np.full(3, -1, np.float32), np.full(3, 1, np.float32)
-    ex = {}
+    cfg = {}
 
     def timed(fn, reps=3):
         fn()
-        best = 1e30
+        best, dev_best, macs = 1e30, 1e30, 0
         for _ in range(reps):
+            ctx.exec_macs(on=True, reset=True)
+            ctx.timer_start()
             t0 = time.perf_counter()
             r = fn()
-            best = min(best, time.perf_counter() - t0)
-        return best, r
+            dt = time.perf_counter() - t0
+            dms = ctx.timer_stop()
+            macs = ctx.exec_macs(on=False, reset=True)
+            if dt < best:
+                best, dev_best = dt, dms
+        return best, dev_best, macs, r
 
+    def roof(flop_alg, macs, seconds):
+        ex = 2.0 * macs / seconds / 1e12 if macs else None
+        alg = flop_alg / seconds / 1e12
+        return {"bound": "fp32", "unit": "TFLOP/s", "peak": peak_tflops, "achieved_algorithmic": alg, "frac_algorithmic": alg / peak_tflops,
+                "achieved": ex, "frac": None if ex is None else ex / peak_tflops}
+
+    # ---- config 1: fox 512x512 cast_rays, affine_fixed ----
     p = mlps["fox"]
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
+    Mf = ctx.mlp(p).macs
     eye = np.array((2., 1., 2.), np.float32)
     look, up, _ = render.look_at(eye)
     roots, dirs = render.generate_camera_rays(eye, look, up, res=512, fov_deg=30.)
-    dt, r = timed(lambda: queries.cast_rays((f,), (p,), roots, dirs, queries.get_default_cast_opts(), ctx=ctx))
-    ex["cfg1_fox_512x512_cast_rays"] = {"rays_per_s": roots.shape[0] / dt, "ray_steps_per_s": int(r[2].sum()) / dt, "ms": dt * 1e3,
-                                        "hits": int((r[1] > 0).sum()), "tflops_algorithmic": 10 * 7296 * int(r[2].sum()) / dt / 1e12}
-    # the frustum variant of the same image (src/queries.py:178-587): frusta of pixels marched together, then split
-    look, up, left = render.look_at(eye)
-    for res in (512, 1024):
-        cam = (eye, look, up, left, 30., 30., res, res)
-        dt, r = timed(lambda: queries.cast_rays_frustum((f,), (p,), cam, queries.get_default_cast_opts(), ctx=ctx))
-        ex[f"cfg1_fox_{res}x{res}_cast_rays_frustum"] = {"pixels_per_s": res * res / dt, "ms": dt * 1e3, "hits": int((r[1] > 0).sum()),
-                                                        "n_evals_reference_count": int(r[3])}
+    o = queries.get_default_cast_opts()
+    dt, dms, macs, r = timed(lambda: queries.cast_rays((f,), (p,), roots, dirs, o, ctx=ctx))
+    steps1 = int(r[2].sum())
+    cfg["cfg1_fox_512x512_cast_rays"] = {"rays_per_s": roots.shape[0] / dt, "ray_steps_per_s": steps1 / dt, "ms": dt * 1e3, "device_ms": dms,
+                                         "hits": int((r[1] > 0).sum()), "ray_steps": steps1, "roofline": roof(10 * Mf * steps1, macs, dms * 1e-3),
+                                         "kernel": "k_cast_rays<32>"}
+    # ---- config 2: bunny tree depth 12 / 21, hierarchical marching cubes depth 7 (n_subcell_depth 3) ----
     p = mlps["bunny"]
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
+    Mb = ctx.mlp(p).macs
     for depth in (12, 21):
         st = {}
-        dt, r = timed(lambda: kd_tree.construct_uniform_unknown_levelset_tree(f, p, lo, hi, split_depth=depth, stats=st))
-        ex[f"cfg2_bunny_tree_depth{depth}"] = {"boxes_per_s": st["n_evals"] / dt, "boxes": st["n_evals"], "leaves": int(r["unknown_node_valid"].sum()),
-                                               "near_tie": st["n_near_tie"], "ms": dt * 1e3}
-    dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 7, n_subcell_depth=3), reps=2)
-    ex["cfg2_bunny_hmc_depth7_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "leaves_per_s": 4096 / dt}
+        dt, dms, macs, r = timed(lambda: kd_tree.construct_uniform_unknown_levelset_tree(f, p, lo, hi, split_depth=depth, stats=st, ctx=ctx))
+        cfg[f"cfg2_bunny_tree_depth{depth}"] = {"boxes_per_s": st["n_evals"] / dt, "boxes": st["n_evals"], "leaves": int(r["unknown_node_valid"].sum()),
+                                                "near_tie": st["n_near_tie"], "ms": dt * 1e3, "device_ms": dms,
+                                                "roofline": roof(10 * Mb * st["n_evals"], macs, dms * 1e-3), "kernel": "k_tree_persistent<64, TileBox3>"}
     ctx.mc_points(reset=True)
-    dt, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 9, n_subcell_depth=3), reps=1)
+    dt, dms, macs, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(f, p, lo, hi, 7, n_subcell_depth=3, ctx=ctx), reps=2)
     ev, lat = ctx.mc_points(reset=True)
-    ex["cfg2_bunny_hmc_depth9_sub3"] = {"triangles": int(tri.shape[0]), "ms": dt * 1e3, "triangles_per_s": tri.shape[0] / dt,
-                                        "leaves": lat // 729 // 2, "leaves_per_s": lat / 729 / 2 / dt,
-                                        "lattice_points_evaluated_over_reference": ev / max(lat, 1),
-                                        "note": "points on a face shared by two leaves are evaluated once (values and triangles unchanged)"}
-
-    # config 3: hammer x bunny under seeded rigid transforms, affine_truncate (n_keep 64, 'absolute'), eps 1e-3
-    import mlp
+    cfg["cfg2_bunny_hmc_depth7_sub3"] = {"triangles": int(tri.shape[0]), "leaves": 4096, "ms": dt * 1e3, "device_ms": dms, "leaves_per_s": 4096 / dt,
+                                         "triangles_per_s": tri.shape[0] / dt, "lattice_points_evaluated_over_reference": ev / max(lat, 1),
+                                         "roofline": roof(2 * Mb * 729 * 4096 + 10 * Mb * 8191, macs, dms * 1e-3),
+                                         "kernel": "k_tree_persistent<64> + k_eval_points<64> + k_mc_count / k_mc_write",
+                                         "hbm_pass": "k_mc_write: 36 B per triangle written, lattice values re-read from L2"}
+    # ---- config 3: hammer x bunny under 64 seeded rigid transforms, affine_truncate (n_keep 64, 'absolute'), eps 1e-3 ----
     pA = mlps["hammer"]
     pB = mlp.prepend_op(mlps["bunny"], mlp.spatial_transformation())
     kw = dict(affine_n_truncate=64, affine_truncate_policy="absolute")
     fA = implicit_mlp_utils.generate_implicit_from_params(pA, "affine_truncate", **kw)
     fB = implicit_mlp_utils.generate_implicit_from_params(pB, "affine_truncate", **kw)
-    rng = np.random.default_rng(0)
-    n_q, n_found, n_nodes, n_rounds, t_tot, t_max = 24, 0, 0, 0, 0.0, 0.0
-    # warm-up on a disjoint pair (the longest kind of query: ~19 rounds), so that no timed query pays first-use allocations
-    pB["0000.spatial_transformation.R"] = np.eye(3, dtype=np.float32)
-    pB["0000.spatial_transformation.t"] = np.array((1.45, 0., 0.), np.float32)
-    kd_tree.find_any_intersection((fA, fB), (pA, pB), lo, hi, 1e-3, ctx=ctx)
-    for i in range(n_q + 1):
-        th = rng.uniform(0, 2 * np.pi)
-        pB["0000.spatial_transformation.R"] = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
-        pB["0000.spatial_transformation.t"] = rng.uniform(-1.5, 1.5, 3).astype(np.float32)
+    R, t = cfg3_transforms(64)
+
+    def one(i, st=None):
+        pB["0000.spatial_transformation.R"], pB["0000.spatial_transformation.t"] = R[i], t[i]
+        return kd_tree.find_any_intersection((fA, fB), (pA, pB), lo, hi, 1e-3, stats=st, ctx=ctx)[0]
+    one(0); one(1)
+    n_found = n_nodes = n_rounds = 0
+    lat = []
+    for i in range(64):
         st = {}
         t0 = time.perf_counter()
-        found = kd_tree.find_any_intersection((fA, fB), (pA, pB), lo, hi, 1e-3, stats=st, ctx=ctx)[0]
-        d = time.perf_counter() - t0
-        if i == 0:
-            continue                      # warm-up
-        n_found += bool(found); n_nodes += st["n_nodes"]; n_rounds += st["n_rounds"]; t_tot += d; t_max = max(t_max, d)
-    ex["cfg3_hammer_x_bunny_intersection_truncate64"] = {"queries": n_q, "found": n_found, "queries_per_s": n_q / t_tot, "nodes_per_s": n_nodes / t_tot,
-                                                        "nodes": n_nodes, "rounds": n_rounds, "mean_ms": 1e3 * t_tot / n_q, "max_ms": 1e3 * t_max}
-
-    # config 4: birdcage_occ closest_point, affine_fixed, eps 1e-3.  The reference's default global LIFO window
-    # (batch_process_size 2048) couples the queries and is sequential by construction (SURVEY.md F6); the window >= stack
-    # regime is the same algorithm run level-synchronously per query (shardable).  Both on stated sub-samples of the 1 M queries.
+        n_found += bool(one(i, st))
+        lat.append(time.perf_counter() - t0)
+        n_nodes += st["n_nodes"]; n_rounds += st["n_rounds"]
+    tot = float(np.sum(lat))
+    FLOP_NODE3 = 2 * 3.80e6 + 14 * 2 * ctx.mlp(pA).macs             # SURVEY.md 8(d): 2 truncate-64 classifies + 14 point evaluations
+    cfg["cfg3_hammer_x_bunny_intersection_truncate64"] = {"queries": 64, "found": n_found, "queries_per_s": 64 / tot, "nodes_per_s": n_nodes / tot,
+                                                         "nodes": n_nodes, "rounds": n_rounds, "mean_ms": 1e3 * tot / 64, "max_ms": 1e3 * max(lat),
+                                                         "median_ms": 1e3 * float(np.median(lat)),
+                                                         "roofline": roof(FLOP_NODE3 * n_nodes, 0, tot), "kernel": "k_classify_grow + k_eval_points<64> + k_isect_logic"}
+    # ---- config 4: birdcage_occ closest_point, affine_fixed, eps 1e-3, Q = 256 of the 1 M seeded queries ----
     p = mlps["birdcage_occ"]
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
+    Mc = ctx.mlp(p).macs
     q_all = np.random.default_rng(0).uniform(-1, 1, (1000000, 3)).astype(np.float32)
     for tag, nq, B in (("window2048", 256, 2048), ("window_ge_stack", 4096, 2 ** 26)):
         st = {}
-        kd_tree.closest_point(f, p, lo, hi, q_all[:64], eps=1e-3, batch_process_size=B, ctx=ctx)
-        t0 = time.perf_counter()
-        dist_q, _ = kd_tree.closest_point(f, p, lo, hi, q_all[:nq], eps=1e-3, batch_process_size=B, stats=st, ctx=ctx)
-        d = time.perf_counter() - t0
-        ex[f"cfg4_birdcage_closest_point_{tag}"] = {"queries": nq, "batch_process_size": B, "queries_per_s": nq / d, "node_visits_per_s": st["n_visits"] / d,
-                                                   "visits_per_query": st["n_visits"] / nq, "rounds": st["n_rounds"], "max_stack": st["max_stack"], "ms": d * 1e3,
-                                                   "finite": int(np.isfinite(dist_q).sum())}
-    return ex
+        dt, dms, macs, _ = timed(lambda: kd_tree.closest_point(f, p, lo, hi, q_all[:nq], eps=1e-3, batch_process_size=B, stats=st, ctx=ctx), reps=1)
+        cfg[f"cfg4_birdcage_closest_point_{tag}"] = {"queries": nq, "batch_process_size": B, "queries_per_s": nq / dt, "node_visits_per_s": st["n_visits"] / dt,
+                                                    "visits_per_query": st["n_visits"] / nq, "rounds": st["n_rounds"], "max_stack": st["max_stack"], "ms": dt * 1e3,
+                                                    "device_ms": dms, "roofline": roof((10 + 14) * Mc * st["n_visits"], macs, dt),
+                                                    "kernel": "k_classify_fixed<64> + k_eval_points<64> + k_cp_round_small (CUDA graph)" if B <= 2048 else "k_classify_fixed<64> + k_eval_points<64> + k_cp_*"}
+    # ---- the CPU oracle beside each config, bounded samples, in parallel processes ----
+    if cpu:
+        import multiprocessing as mp
+        from niq_oracle import net
+        sub = (np.arange(512)[::16][:, None] * 512 + np.arange(512)[::16][None, :]).reshape(-1)          # 32 x 32 rays of the 512^2 image
+        top = kd_tree.construct_uniform_unknown_levelset_tree(implicit_mlp_utils.generate_implicit_from_params(mlps["bunny"], "affine_fixed"),
+                                                              mlps["bunny"], lo, hi, split_depth=12, ctx=ctx)
+        v = top["unknown_node_valid"]
+        llo, lhi = top["unknown_node_lower"][v][::64], top["unknown_node_upper"][v][::64]                 # 64 of the 4,096 leaves
+        tasks = [("cfg1", mlps["fox"], roots[sub], dirs[sub]), ("cfg2_tree", mlps["bunny"], 12), ("cfg2_mc", mlps["bunny"], llo, lhi),
+                 ("cfg3", mlps["hammer"], mlps["bunny"], R[:3], t[:3]), ("cfg4", mlps["birdcage_occ"], q_all[:4])]
+        with mp.get_context("fork").Pool(min(len(tasks), cpu_workers())) as pool:
+            res = {k: (dt, u) for k, dt, u in pool.map(_cpu_cfg, tasks, chunksize=1)}
+        def base(kind, key, unit, sample):
+            dt, u = res[kind]
+            return {"value": u[key] / dt, "unit": unit, "cores": 1, "kind": "port", "sample": sample, "seconds": dt}
+        cfg["cfg1_fox_512x512_cast_rays"]["cpu_baseline"] = base("cfg1", "ray_steps", "ray-steps/s", "32 x 32 rays (every 16th pixel of the 512^2 image), oracle cast_rays")
+        cfg["cfg2_bunny_tree_depth12"]["cpu_baseline"] = base("cfg2_tree", "boxes", "boxes/s", "the whole depth-12 tree (8,191 boxes), oracle")
+        cfg["cfg2_bunny_tree_depth21"]["cpu_baseline"] = dict(cfg["cfg2_bunny_tree_depth12"]["cpu_baseline"], sample="as depth 12 (per-box cost does not depend on depth)")
+        cfg["cfg2_bunny_hmc_depth7_sub3"]["cpu_baseline"] = base("cfg2_mc", "leaves", "leaves/s", "64 of the 4,096 leaves (every 64th), oracle extraction with n_subcell_depth 3")
+        cfg["cfg3_hammer_x_bunny_intersection_truncate64"]["cpu_baseline"] = base("cfg3", "nodes", "nodes/s", "the first 3 of the 64 transforms, oracle find_any_intersection")
+        c4 = base("cfg4", "visits", "node visits/s", "the first 4 queries at batch_process_size 2048, oracle closest_point")
+        cfg["cfg4_birdcage_closest_point_window2048"]["cpu_baseline"] = c4
+        cfg["cfg4_birdcage_closest_point_window_ge_stack"]["cpu_baseline"] = dict(c4, sample=c4["sample"] + " (per-visit cost is the same)")
+    return cfg
 
 
 def main():
@@ -534,9 +688,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--tiles", type=int, default=74, help="16x16 ray tiles per GPU per step")
-    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--extra", action="store_true", help="also time the sample-input configs (secondary numbers)")
+    ap.add_argument("--tiles-total", type=int, default=TILES_TOTAL, help="16x16 ray tiles per step, whole job (fixed for every N)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline legs")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs block (BASELINE configs 1-4)")
     ap.add_argument("--full-image", action="store_true", help="additionally cast the whole 1920x1080 image once (about a minute on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":

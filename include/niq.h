@@ -132,8 +132,10 @@ int niq_dev_download(niq_ctx* ctx, void* dst, const void* src, int64_t bytes);
 int niq_measure_fp32_peak(niq_ctx* ctx, float* tflops);
 
 /* ---- MLP handle: replaces src/mlp.py:96-144 (op-list interpreter) + :173-185 (load) ---------- */
-/* Supported op sequences: (dense | spatial) each optionally followed by ONE of relu/elu, with an optional
- * trailing squeeze_last (requires out_dim 1).  Input dimension 3.  Weights are copied and packed once.  */
+/* Supported op sequences: an optional spatial_transformation, an optional pow2_frequency_encode on the 3-D input, then
+ * dense ops each optionally followed by ONE of relu / elu / sin, with an optional trailing squeeze_last (requires
+ * out_dim 1; no activation after the last dense).  Input dimension 3, hidden widths <= 256.  Weights are copied and
+ * packed once.                                                                                              */
 int niq_mlp_create(niq_ctx* ctx, int32_t n_ops, const niq_op_desc* ops, niq_mlp** out);
 int niq_mlp_destroy(niq_mlp* mlp);
 /* MACs of one row through the net (sum of in*out over dense/spatial layers) -- SURVEY.md 8(d) "M"     */
@@ -239,6 +241,19 @@ int niq_mc_tables(int32_t* tri_table, int32_t* edge_verts, uint8_t* vert_coords)
 int niq_find_any_intersection(niq_ctx* ctx, const niq_mlp* mlpA, const niq_mode_cfg* cfgA,
                               const niq_mlp* mlpB, const niq_mode_cfg* cfgB, const float lower[3],
                               const float upper[3], float eps, int32_t* found, float loc[3], int64_t stats[3]);
+
+/* A BATCH of pairwise queries that differ only in the rigid transforms of the two shapes (the reference's GUI re-runs the
+ * query whenever a gizmo moves, src/main_intersection.py:171-183; SURVEY.md 8(d) config 3 is a list of such transforms):
+ * xfA / xfB: HOST (n_queries, 12) float32 = R (3x3 row-major) then t (3) per query -- the values the reference would store in
+ * params["0000.spatial_transformation.R" / ".t"] -- or NULL to use the handle's own first op.  A handle that receives
+ * transforms must have been created from params whose FIRST op is a spatial_transformation.  All queries run in ONE persistent
+ * cooperative kernel (every round processes the frontiers of all live queries); each query's verdict, location and
+ * statistics equal those of its own niq_find_any_intersection call.  found (n) i32, loc (n,3) f32 (-777 when not found),
+ * stats (n,3) i64 optional.  affine_truncate / affine_all / affine_append; other modes -> NIQ_EUNSUPPORTED.             */
+int niq_find_any_intersection_batch(niq_ctx* ctx, const niq_mlp* mlpA, const niq_mode_cfg* cfgA,
+                                    const niq_mlp* mlpB, const niq_mode_cfg* cfgB, int64_t n_queries,
+                                    const float* xfA, const float* xfB, const float lower[3], const float upper[3],
+                                    float eps, int32_t* found, float* loc, int64_t* stats);
 
 /* ---- closest_point: src/kd_tree.py:659-802 ------------------------------------------------------- */
 /* query_points (q,3) -> dist (q) (inf if no surface found), loc (q,3) (contract only where dist is finite).

@@ -34,6 +34,7 @@ SYMBOLS = (
     "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_cast_rays_frustum", "niq_tree_build", "niq_tree_build_roots", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
     "niq_mesh_count", "niq_mesh_copy", "niq_mesh_destroy", "niq_mc_tables", "niq_find_any_intersection",
+    "niq_find_any_intersection_batch",
     "niq_closest_point",
 )
 

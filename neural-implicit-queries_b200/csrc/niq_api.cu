@@ -241,27 +241,6 @@ extern "C" int niq_probe_ffma(niq_ctx* c, int blocks_per_sm, int threads, float*
 // ------------------------------------------------------------------------------------------------
 // MLP packing
 // ------------------------------------------------------------------------------------------------
-static bool invert3(const float* R, float* inv) {   // float32 Gauss-Jordan with partial pivoting
-    float a[3][6];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) { a[i][j] = R[3 * i + j]; a[i][3 + j] = i == j ? 1.f : 0.f; }
-    for (int col = 0; col < 3; ++col) {
-        int piv = col;
-        for (int r = col + 1; r < 3; ++r) if (std::fabs(a[r][col]) > std::fabs(a[piv][col])) piv = r;
-        if (a[piv][col] == 0.f) return false;
-        if (piv != col) for (int j = 0; j < 6; ++j) std::swap(a[piv][j], a[col][j]);
-        const float d = a[col][col];
-        for (int j = 0; j < 6; ++j) a[col][j] = a[col][j] / d;
-        for (int r = 0; r < 3; ++r) {
-            if (r == col) continue;
-            const float f = a[r][col];
-            for (int j = 0; j < 6; ++j) a[r][j] = a[r][j] - f * a[col][j];
-        }
-    }
-    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) inv[3 * i + j] = a[i][3 + j];
-    return true;
-}
-
 extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops, niq_mlp** out) {
     if (!c || !ops || !out || n_ops <= 0) return fail(NIQ_EINVAL, "niq_mlp_create: bad argument");
     CU(cudaSetDevice(c->device));
@@ -681,8 +660,18 @@ extern "C" int niq_cast_rays(niq_ctx* c, int32_t n_funcs, const niq_mlp* const* 
         const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
         TRY(launch_cast_rays(c, wmax, net, total_floats, co, n, interval, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(),
                              dtie.as<unsigned char>(), queue.as<unsigned long long>(), slope));
+    } else if (cfgs[0].mode == NIQ_MODE_AFFINE_TRUNCATE || cfgs[0].mode == NIQ_MODE_AFFINE_ALL || cfgs[0].mode == NIQ_MODE_AFFINE_APPEND) {
+        // growing-form modes: one CTA marches one ray, rays come from an atomic queue (niq_rays_grow.cuh)
+        NetDev net{};
+        int wmax = 32, total_floats = 0;
+        TRY(concat_nets(n_funcs, mlps, net, wmax, total_floats));
+        DevBuf queue(c);
+        TRY(queue.alloc(8));
+        CU(cudaMemsetAsync(queue.p, 0, 8, c->stream));
+        TRY(launch_cast_rays_grow(c, n_funcs, mlps, cfgs, net, co, n, dr.as<float>(), dd.as<float>(), dt.as<float>(), dh.as<int>(), dc.as<int>(),
+                                  dtie.as<unsigned char>(), queue.as<unsigned long long>()));
     } else {
-        return fail(NIQ_EUNSUPPORTED, "cast_rays in this mode runs through the host-level stepping loop of the Python layer");
+        return fail(NIQ_EUNSUPPORTED, "cast_rays in sdf mode runs through the host-level stepping loop of the Python layer");
     }
 
     // N_evals of the reference (src/queries.py:137,164-173): lanes evaluated per iteration incl. bucket padding
@@ -1195,6 +1184,15 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
     TRY(check_cfg(cfgA)); TRY(check_cfg(cfgB));
     CU(cudaSetDevice(c->device));
     timer_touch(c);
+    {   // affine_truncate / affine_all / affine_append: the whole search is one persistent cooperative kernel (niq_isect.cuh)
+        bool handled = false;
+        int64_t st3[3] = {0, 0, 0};
+        TRY(isect_grow_batch(c, mA, cfgA, mB, cfgB, 1, nullptr, nullptr, lower, upper, eps, found, loc, st3, &handled));
+        if (handled) {
+            if (stats) { stats[0] = st3[0]; stats[1] = st3[1]; stats[2] = st3[2]; }
+            return NIQ_OK;
+        }
+    }
     const float eps_w = eps / sqrtf(3.0f);                 // reference src/kd_tree.py:446
     NodeList cur, nxt;
     struct ListGuard { niq_ctx* c; NodeList* L; ~ListGuard() { if (L->lo) cudaFreeAsync(L->lo, c->stream); if (L->hi) cudaFreeAsync(L->hi, c->stream); } } g1{c, &cur}, g2{c, &nxt};
@@ -1274,6 +1272,24 @@ extern "C" int niq_find_any_intersection(niq_ctx* c, const niq_mlp* mA, const ni
     }
     if (stats) { stats[0] = n_nodes; stats[1] = n_rounds; stats[2] = n_tie; }
     FINAL_SYNC(c);
+    return NIQ_OK;
+}
+
+extern "C" int niq_find_any_intersection_batch(niq_ctx* c, const niq_mlp* mA, const niq_mode_cfg* cfgA, const niq_mlp* mB,
+                                               const niq_mode_cfg* cfgB, int64_t n_queries, const float* xfA, const float* xfB,
+                                               const float lower[3], const float upper[3], float eps, int32_t* found, float* loc,
+                                               int64_t* stats) {
+    if (!c || !mA || !mB || !lower || !upper || n_queries < 0 || (n_queries > 0 && (!found || !loc)))
+        return fail(NIQ_EINVAL, "niq_find_any_intersection_batch: bad argument");
+    TRY(check_cfg(cfgA)); TRY(check_cfg(cfgB));
+    if (n_queries == 0) return NIQ_OK;
+    CU(cudaSetDevice(c->device));
+    timer_touch(c);
+    bool handled = false;
+    TRY(isect_grow_batch(c, mA, cfgA, mB, cfgB, n_queries, xfA, xfB, lower, upper, eps, found, loc, stats, &handled));
+    if (!handled)
+        return fail(NIQ_EUNSUPPORTED, "niq_find_any_intersection_batch runs the growing-form modes (affine_truncate / affine_all / "
+                                      "affine_append); other modes: one niq_find_any_intersection call per query");
     return NIQ_OK;
 }
 

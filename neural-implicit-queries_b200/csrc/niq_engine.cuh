@@ -319,7 +319,12 @@ struct Engine {
     static constexpr int ROWS = RT * NT;                       // rows carried by one thread
     static constexpr int SLOTS = G::TPW * NT;                  // tiles per warp
     static constexpr int WARP_ROWS = SLOTS * RT;               // rows in one warp's activation buffer
-    static constexpr int WARP_FLOATS = WARP_ROWS * G::S;
+    // A slot's rows are RT * S floats apart from the next slot's.  When that is a multiple of 32 floats (RT = 8: the point tile)
+    // the TPW slots a warp reads together would sit in the SAME shared-memory banks (a 4-way conflict on every activation
+    // LDS.128 of the 64-wide nets, measured: profiles/r2_hmc_kernels_ncu_full_summary.txt); one float4 of skew per slot
+    // spreads them over distinct bank groups.
+    static constexpr int TS = RT * G::S + (((RT * G::S) % 32 == 0 && G::TPW > 1) ? 4 : 0);   // slot stride in floats
+    static constexpr int WARP_FLOATS = SLOTS * TS;
     static constexpr int CTA_TILES = kWarps * SLOTS;
     static constexpr int LIST_WORDS = WMAX + 16;               // per-warp live-row list (+ over-read tail)
     static constexpr int SEG_WORDS = 4 * (kMaxSegs + 1);
@@ -336,7 +341,7 @@ struct Engine {
     uint64_t* full;        // [kStages] mbarriers: chunk landed in the stage
     int* done;             // [kStages] warps that have finished reading the stage's current chunk
     float* stage;          // [kStages][kChunkFloats]
-    float* act;            // this warp's [WARP_ROWS][S]
+    float* act;            // this warp's [SLOTS] x ([RT][S] rows + skew)
     float* fin;            // this warp's [SLOTS][8] final scalars / scratch
     uint32_t* lst;         // this warp's [LIST_WORDS]: byte offset (inside its chunk) of the weight row of every live k
     int* seg;              // this warp's [kMaxSegs][4]: start, n8, count-before, count of every chunk of the consuming layer
@@ -395,8 +400,9 @@ struct Engine {
 
     // activation row pointer of slot (n, t) row r
     __device__ __forceinline__ float* row_ptr(int n, int tt, int r) const {
-        return act + ((n * G::TPW + tt) * RT + r) * G::S;
+        return act + (n * G::TPW + tt) * TS + r * G::S;
     }
+    __device__ __forceinline__ float* slot_ptr(int slot) const { return act + slot * TS; }
 
     // Streamed weights: the chunk sequence 0,1,2,... (cyclic over the launch's chunk table) flows through a ring of
     // kStages shared-memory stages.  Chunk q lands in stage q % kStages by one TMA bulk copy that completes on
@@ -453,7 +459,7 @@ struct Engine {
         for (int n = 0; n < NT; ++n)
 #pragma unroll
             for (int r = 0; r < RT; ++r)
-                a[n * RT + r] = *reinterpret_cast<const float4*>(p + (n * G::TPW * RT + r) * G::S);
+                a[n * RT + r] = *reinterpret_cast<const float4*>(p + n * G::TPW * TS + r * G::S);
     }
 
     // One k-step of the outer product on packed column pairs: acc[r][p] holds columns (2p, 2p+1) of the thread's 8.
@@ -725,8 +731,9 @@ struct Engine {
                 const int4 sg = *reinterpret_cast<const int4*>(seg + 4 * i);      // start, n4, cb0, cnt
                 if (q < sg.y - sg.w) {
                     const int pos = sg.x + sg.w + q;
-#pragma unroll 5
-                    for (int r = 0; r < WARP_ROWS; ++r) act[r * G::S + pos] = 0.f;
+                    for (int sl = 0; sl < SLOTS; ++sl)
+#pragma unroll
+                        for (int r = 0; r < RT; ++r) act[sl * TS + r * G::S + pos] = 0.f;
                     lst[pos] = 0u;
                 }
             }
@@ -871,7 +878,7 @@ struct Engine {
                 for (int n = 0; n < NT; ++n)
 #pragma unroll
                     for (int r = 0; r < RT; ++r) {
-                        const float a = a_base[(n * G::TPW * RT + r) * G::S + a0 + j];
+                        const float a = a_base[n * G::TPW * TS + r * G::S + a0 + j];
                         const int i = n * RT + r;
                         if (Tile::is_err(r)) out[i] = fmaf(a, wja, out[i]);
                         else out[i] = fmaf(a, wj, out[i]);

@@ -36,62 +36,56 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant__ NetDev net, const GrowArgs g) {
-    extern __shared__ __align__(16) float sm[];
+struct GrowCfg {          // what the growing-form propagation needs to know about the mode
+    int truncate, n_keep, n_append, kcap, W;
+};
+struct GrowState {        // shared-memory carve-up of one CTA (see grow_carve); aff / tmp swap on every truncation
+    float *base, *base2, *err, *err2, *alpha, *delta, *red, *mags;
+    int* rank;
+    float *aff, *tmp;
+};
+__host__ __device__ inline size_t grow_state_floats(const GrowCfg& g) {
+    return (size_t)22 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W * (g.truncate ? 2 : 1) + 16;
+}
+__device__ __forceinline__ void grow_carve(float* sm, const GrowCfg& g, GrowState& s) {
     const int W = g.W;
-    float* base = sm;                 // [W]
-    float* base2 = base + W;          // [W]
-    float* err = base2 + W;           // [W]
-    float* err2 = err + W;            // [W]
-    float* alpha = err2 + W;          // [W]
-    float* delta = alpha + W;         // [W]
-    float* red = delta + W;           // [16][W] partial sums (two vectors x 8 parts)
-    float* mags = red + 16 * W;       // [kcap]
-    int* rank = reinterpret_cast<int*>(mags + g.kcap);   // [kcap]
-    float* aff = reinterpret_cast<float*>(rank + g.kcap); // [kcap][W]
-    float* tmp = aff + (size_t)g.kcap * W;               // [kcap][W] (truncate only): the truncated state is built here, then the two swap
+    s.base = sm;                  // [W]
+    s.base2 = s.base + W;         // [W]
+    s.err = s.base2 + W;          // [W]
+    s.err2 = s.err + W;           // [W]
+    s.alpha = s.err2 + W;         // [W]
+    s.delta = s.alpha + W;        // [W]
+    s.red = s.delta + W;          // [16][W] partial sums (two vectors x 8 parts)
+    s.mags = s.red + 16 * W;      // [kcap]
+    s.rank = reinterpret_cast<int*>(s.mags + g.kcap);     // [kcap]
+    s.aff = reinterpret_cast<float*>(s.rank + g.kcap);    // [kcap][W]
+    s.tmp = s.aff + (size_t)g.kcap * W;                   // [kcap][W] (truncate only): the truncated state is built here, then the two swap
+}
+
+// Bound propagation of ONE general box through layers [l0, l1) of `net` by the whole CTA (256 threads).
+// Precondition: the caller wrote the input form -- base[0..3] = centre (4th entry 0), aff rows [0, k) = the box vectors
+// (4 floats each), err[0..3] = 0 (reference src/affine.py:109-117, non-interval modes) -- and synchronised the CTA.
+// A0 / b0 (optional): weights / bias that replace those of layer l0 (a per-query spatial_transformation, see
+// niq_find_any_intersection_batch).  On return every thread holds lower / upper / scale (= sum_j |base_j A_j| + |b| of the
+// last dot product, the near-tie yardstick).
+__device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, const float* A0, const float* b0, const GrowCfg& g,
+                                             GrowState& st, int k, float& lower, float& upper, float& scale) {
     __shared__ float s_fin[3];
     __shared__ float s_rest;
-
+    const int W = g.W;
+    float* base = st.base; float* base2 = st.base2; float* err = st.err; float* err2 = st.err2;
+    float* alpha = st.alpha; float* delta = st.delta; float* red = st.red; float* mags = st.mags; int* rank = st.rank;
+    float* aff = st.aff; float* tmp = st.tmp;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-    for (long long box = blockIdx.x; box < g.n; box += gridDim.x) {
-        // ---- input form (reference src/affine.py:109-117, non-interval modes): aff = vecs, err = 0 ----
-        int k;
-        {
-            __syncthreads();
-            if (tid == 0) {
-                if (g.src.kind == 0) {
-                    const float* c = g.src.a + 3 * box;
-                    base[0] = c[0]; base[1] = c[1]; base[2] = c[2]; base[3] = 0.f;
-                    for (int r = 0; r < g.src.v; ++r) {
-                        const float* p = g.src.b + (box * g.src.v + r) * 3;
-                        aff[r * W + 0] = p[0]; aff[r * W + 1] = p[1]; aff[r * W + 2] = p[2]; aff[r * W + 3] = 0.f;
-                    }
-                } else {
-                    float4 rows[5];
-                    BoxSource s = g.src;
-                    s.interval = 0;
-                    load_box_rows(s, box, rows);
-                    base[0] = rows[0].x; base[1] = rows[0].y; base[2] = rows[0].z; base[3] = 0.f;
-                    for (int r = 0; r < 3; ++r) {
-                        aff[r * W + 0] = rows[1 + r].x; aff[r * W + 1] = rows[1 + r].y;
-                        aff[r * W + 2] = rows[1 + r].z; aff[r * W + 3] = 0.f;
-                    }
-                }
-                err[0] = err[1] = err[2] = err[3] = 0.f;
-            }
-            k = g.src.kind == 0 ? g.src.v : 3;
-            __syncthreads();
-        }
-
+    {
         float* b_cur = base;
         float* b_nxt = base2;
         float* e_cur = err;
         float* e_nxt = err2;
-        for (int l = 0; l < net.n_layers; ++l) {
+        for (int l = l0; l < l1; ++l) {
             const LayerDev& L = net.layers[l];
-            const float* A = net.chunks[L.chunk_begin].src;
+            const float* A = (l == l0 && A0 != nullptr) ? A0 : net.chunks[L.chunk_begin].src;
+            const float* bias = (l == l0 && b0 != nullptr) ? b0 : L.bias;
             if (!L.last_of_net) {
                 const int K = L.in_pad, N = L.out_pad;
                 const int Np2 = next_pow2(N);
@@ -164,7 +158,7 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                 if (tid < N) {
                     float sb = 0.f, se = 0.f;
                     for (int p = 0; p < parts; ++p) { sb += red[p * W + tid]; se += red[(8 + p) * W + tid]; }
-                    b_nxt[tid] = sb + __ldg(L.bias + tid);
+                    b_nxt[tid] = sb + __ldg(bias + tid);
                     e_nxt[tid] = se;
                 }
                 { float* t2 = e_cur; e_cur = e_nxt; e_nxt = t2; t2 = b_cur; b_cur = b_nxt; b_nxt = t2; }
@@ -334,24 +328,130 @@ __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant_
                     }
                     s = warp_sum(s); sa = warp_sum(sa); se = warp_sum(se);
                     if (lane == 0) {
-                        s_fin[0] = s + __ldg(L.bias);
-                        s_fin[2] = sa + fabsf(__ldg(L.bias));
+                        s_fin[0] = s + __ldg(bias);
+                        s_fin[2] = sa + fabsf(__ldg(bias));
                         s_fin[1] = se;
                     }
                 }
                 __syncthreads();
-                if (tid == 0) {
+                {
                     float rad = 0.f;
                     for (int w = 0; w < 8; ++w) rad += red[w];
                     rad += s_fin[1];
-                    const float lo = s_fin[0] - rad, up = s_fin[0] + rad;
-                    if (g.lower) g.lower[box] = lo;
-                    if (g.upper) g.upper[box] = up;
-                    if (g.label) g.label[box] = label_of(lo, up, g.offset);
-                    if (g.near_tie) g.near_tie[box] = bound_near_tie(lo, up, g.offset, s_fin[2], net.tie_rel) ? 1 : 0;
+                    lower = s_fin[0] - rad; upper = s_fin[0] + rad; scale = s_fin[2];
                 }
                 __syncthreads();
             }
+        }
+    }
+    st.aff = aff; st.tmp = tmp;        // a truncation swapped the two buffers
+}
+
+// f(x) of up to 8 points by the whole CTA (256 threads): warp p evaluates point p, whose activations live in row p of the
+// two ping-pong buffers hA / hB ([8][W] floats of shared memory, rows private to their warp).  Precondition: hA[p*W + 0..3] =
+// (x, y, z, 0) written and visible to warp p.  The arithmetic is that of the engine's point rows (niq_engine.cuh, reference
+// src/mlp.py:253-347): a hidden neuron accumulates fma(h_k, A_kc, acc) for ascending k from 0, then + bias, then the
+// activation; the final dot product is split over `cg_lanes` (= width class / 8) lanes -- lane cg takes k = cg, cg + CG, ...
+// -- and combined by an xor butterfly, like Engine::dot_layer.  Returns f and scale = sum_k |h_k w_k| + |b| of point `warp`
+// in every lane of that warp.
+__device__ __forceinline__ void cta_points8(const NetDev& net, int l0, int l1, const float* A0, const float* b0, int cg_lanes,
+                                            float* hA, float* hB, int W, float& f, float& scale) {
+    const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
+    float* hin = hA + p * W;
+    float* hout = hB + p * W;
+    f = 0.f; scale = 0.f;
+    for (int l = l0; l < l1; ++l) {
+        const LayerDev& L = net.layers[l];
+        const float* A = (l == l0 && A0 != nullptr) ? A0 : net.chunks[L.chunk_begin].src;
+        const float* bias = (l == l0 && b0 != nullptr) ? b0 : L.bias;
+        const int K = L.in_pad;
+        if (!L.last_of_net) {
+            const int N = L.out_pad;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const float* wp = A + lane;
+#pragma unroll 4
+            for (int k = 0; k < K; ++k) {
+                const float a = hin[k];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (lane + 32 * i < N) acc[i] = fmaf(a, __ldg(wp + (size_t)k * N + 32 * i), acc[i]);
+            }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c = lane + 32 * i;
+                if (c < N) {
+                    float x = acc[i] + __ldg(bias + c);
+                    if (L.act == ACT_RELU) x = fmaxf(x, 0.f);
+                    else if (L.act == ACT_ELU) x = elu_pt(x);
+                    else if (L.act == ACT_SIN) x = sinf(x);
+                    hout[c] = x;
+                }
+            }
+            __syncwarp();
+            float* t2 = hin; hin = hout; hout = t2;
+        } else {
+            float out = 0.f, ps = 0.f;
+            if (lane < cg_lanes) {
+                for (int j = lane; j < K; j += cg_lanes) {
+                    const float a = hin[j], w = __ldg(A + j);
+                    out = fmaf(a, w, out);
+                    ps = fmaf(fabsf(a), fabsf(w), ps);
+                }
+            }
+            for (int off = 1; off < cg_lanes; off <<= 1) {
+                out += __shfl_xor_sync(0xffffffffu, out, off);
+                ps += __shfl_xor_sync(0xffffffffu, ps, off);
+            }
+            const float b = __ldg(bias);
+            out += b; ps += fabsf(b);
+            f = __shfl_sync(0xffffffffu, out, 0);
+            scale = __shfl_sync(0xffffffffu, ps, 0);
+            __syncwarp();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant__ NetDev net, const GrowArgs g) {
+    extern __shared__ __align__(16) float sm[];
+    GrowCfg cfg{g.truncate, g.n_keep, g.n_append, g.kcap, g.W};
+    GrowState st;
+    grow_carve(sm, cfg, st);
+    const int tid = threadIdx.x;
+    for (long long box = blockIdx.x; box < g.n; box += gridDim.x) {
+        // ---- input form (reference src/affine.py:109-117, non-interval modes): aff = vecs, err = 0 ----
+        __syncthreads();
+        if (tid == 0) {
+            float* base = st.base; float* aff = st.aff; float* err = st.err;
+            const int W = g.W;
+            if (g.src.kind == 0) {
+                const float* c = g.src.a + 3 * box;
+                base[0] = c[0]; base[1] = c[1]; base[2] = c[2]; base[3] = 0.f;
+                for (int r = 0; r < g.src.v; ++r) {
+                    const float* p = g.src.b + (box * g.src.v + r) * 3;
+                    aff[r * W + 0] = p[0]; aff[r * W + 1] = p[1]; aff[r * W + 2] = p[2]; aff[r * W + 3] = 0.f;
+                }
+            } else {
+                float4 rows[5];
+                BoxSource s = g.src;
+                s.interval = 0;
+                load_box_rows(s, box, rows);
+                base[0] = rows[0].x; base[1] = rows[0].y; base[2] = rows[0].z; base[3] = 0.f;
+                for (int r = 0; r < 3; ++r) {
+                    aff[r * W + 0] = rows[1 + r].x; aff[r * W + 1] = rows[1 + r].y;
+                    aff[r * W + 2] = rows[1 + r].z; aff[r * W + 3] = 0.f;
+                }
+            }
+            err[0] = err[1] = err[2] = err[3] = 0.f;
+        }
+        __syncthreads();
+        float lo, up, sc;
+        grow_forward(net, 0, net.n_layers, nullptr, nullptr, cfg, st, g.src.kind == 0 ? g.src.v : 3, lo, up, sc);
+        if (tid == 0) {
+            if (g.lower) g.lower[box] = lo;
+            if (g.upper) g.upper[box] = up;
+            if (g.label) g.label[box] = label_of(lo, up, g.offset);
+            if (g.near_tie) g.near_tie[box] = bound_near_tie(lo, up, g.offset, sc, net.tie_rel) ? 1 : 0;
         }
     }
 }

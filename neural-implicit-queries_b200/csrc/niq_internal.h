@@ -150,6 +150,28 @@ static void timer_mark(niq_ctx* c) {
 }
 #define FINAL_SYNC(c) do { timer_mark(c); CU(cudaStreamSynchronize((c)->stream)); } while (0)
 
+static bool invert3(const float* R, float* inv) {   // float32 Gauss-Jordan with partial pivoting
+    float a[3][6];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) { a[i][j] = R[3 * i + j]; a[i][3 + j] = i == j ? 1.f : 0.f; }
+    for (int col = 0; col < 3; ++col) {
+        int piv = col;
+        for (int r = col + 1; r < 3; ++r) if (std::fabs(a[r][col]) > std::fabs(a[piv][col])) piv = r;
+        if (a[piv][col] == 0.f) return false;
+        if (piv != col) for (int j = 0; j < 6; ++j) std::swap(a[piv][j], a[col][j]);
+        const float d = a[col][col];
+        for (int j = 0; j < 6; ++j) a[col][j] = a[col][j] / d;
+        for (int r = 0; r < 3; ++r) {
+            if (r == col) continue;
+            const float f = a[r][col];
+            for (int j = 0; j < 6; ++j) a[r][j] = a[r][j] - f * a[col][j];
+        }
+    }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) inv[3 * i + j] = a[i][3 + j];
+    return true;
+}
+
+
 // launchers, one translation unit per kernel family (compiled in parallel; see __graft_entry__.build)
 int launch_classify_fixed(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
                           int* label, float* lower, float* upper, unsigned char* tie);
@@ -167,3 +189,12 @@ int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, 
 int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, long long n_roots, const float* lower,
                           const float* upper, int split_depth, long long node_thresh, float offset, int flags, int bps,
                           niq_tree* T, bool* handled);
+// find_any_intersection for the growing-form modes as one persistent cooperative kernel (niq_isect.cuh), for a batch of n_q
+// queries that differ in the rigid transforms prepended to the two shapes (xfA / xfB: HOST (n_q, 12) = R (3x3) + t (3) per
+// query, or NULL: the handle's own first layer).  *handled = false when a mode is not a growing-form mode.
+int isect_grow_batch(niq_ctx* c, const niq_mlp* mA, const niq_mode_cfg* cfgA, const niq_mlp* mB, const niq_mode_cfg* cfgB,
+                     long long n_q, const float* xfA, const float* xfB, const float lower[3], const float upper[3], float eps,
+                     int32_t* found, float* loc, int64_t* stats, bool* handled);
+int launch_cast_rays_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs, const NetDev& net,
+                          const CastOpts& o, long long n, const float* roots, const float* dirs, float* t, int* hit, int* cnt,
+                          unsigned char* tie, unsigned long long* queue);

@@ -198,7 +198,7 @@ k_classify_fixed(const __grid_constant__ NetDev net, const BoxSource src, long l
             float4 rows[5];
             if (i < n) load_box_rows(src, i, rows);
             else for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-            float* dst = eng.act + eng.lane * 5 * E::G::S;
+            float* dst = eng.slot_ptr(eng.lane);
             for (int r = 0; r < 5; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
         }
         __syncwarp();
@@ -245,7 +245,7 @@ k_classify_slope(const __grid_constant__ NetDev net, const BoxSource src, long l
             float4 rows[5];
             for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n) { BoxSource s2 = src; s2.interval = 0; load_box_rows(s2, i, rows); }   // [centre, vec x3, 0]
-            float* dst = eng.act + eng.lane * 7 * E::G::S;
+            float* dst = eng.slot_ptr(eng.lane);
             for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
             for (int r = 4; r < 7; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -335,7 +335,7 @@ k_eval_points(const __grid_constant__ NetDev net, const PointSource src, long lo
             const long long i = p0 + r;
             float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (i < n) x = load_point(src, i);
-            *reinterpret_cast<float4*>(eng.act + r * E::G::S) = x;
+            *reinterpret_cast<float4*>(eng.slot_ptr(r >> 3) + (r & 7) * E::G::S) = x;
         }
         __syncwarp();
         float out[E::ROWS], ps[E::ROWS];
@@ -449,7 +449,7 @@ k_cast_rays(const __grid_constant__ NetDev net, const CastOpts o, long long n, i
                 }
                 rows[3] = make_float4(psx, psy, psz, 0.f);
                 rows[4] = make_float4(rx + te * dx, ry + te * dy, rz + te * dz, 0.f);
-                float* dst = eng.act + lane * 5 * E::G::S;
+                float* dst = eng.slot_ptr(lane);
                 for (int r = 0; r < 5; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
             }
             __syncwarp();
@@ -690,7 +690,7 @@ k_cast_frustum(const __grid_constant__ NetDev net, const CastOpts o, const __gri
                 }
                 rows[RT - 2] = make_float4(cam.root[0] + t * mid[0], cam.root[1] + t * mid[1], cam.root[2] + t * mid[2], 0.f);
                 rows[RT - 1] = make_float4(cam.root[0] + te * mid[0], cam.root[1] + te * mid[1], cam.root[2] + te * mid[2], 0.f);
-                float* dst = eng.act + lane * RT * E::G::S;
+                float* dst = eng.slot_ptr(lane);
 #pragma unroll
                 for (int r = 0; r < RT; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
             }

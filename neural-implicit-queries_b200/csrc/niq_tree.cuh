@@ -32,7 +32,8 @@ struct TreeCtl {                         // device control block; written by CTA
     long long status;                    // 0 finished, 1 frontier buffers too small, 2 interior list, 3 exterior list
     long long need;                      // status != 0: nodes the too-small buffer must hold
     long long n_evals, max_frontier;
-    unsigned long long n_tie;
+    unsigned long long n_tie;            // near-tie boxes of the finished levels
+    unsigned long long n_tie_level;      // ... of the level in flight (folded in by CTA 0 once the level is known to fit)
     unsigned int bar_count, bar_gen;     // grid barrier
 };
 
@@ -111,6 +112,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
     long long n_fin[2] = {a.ctl->n_fin[0], a.ctl->n_fin[1]};
     long long n_evals = a.ctl->n_evals, max_frontier = a.ctl->max_frontier;
     long long status = 0, need = 0;
+    unsigned long long n_tie = a.ctl->n_tie;                          // meaningful in CTA 0, thread 0
     const long long T = a.n_tiles_max;
 
     while (level < a.n_splits) {
@@ -140,7 +142,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
                     src.interval = Tile::rule == 2 ? 0 : a.interval;
                     load_box_rows(src, i, rows);
                 }
-                float* dst = eng.act + lane * RT * E::G::S;
+                float* dst = eng.slot_ptr(lane);
                 if (Tile::rule == 2) {       // slope_interval: [primal, centre x3, width x3 = 0]
 #pragma unroll
                     for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
@@ -194,7 +196,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
                     if (b_unk) atomicAdd(cnt + tile, __popc(b_unk));
                     if (b_neg && a.want_neg) atomicAdd(cnt + T + tile, __popc(b_neg));
                     if (b_pos && a.want_pos) atomicAdd(cnt + 2 * T + tile, __popc(b_pos));
-                    if (b_tie) atomicAdd(&a.ctl->n_tie, (unsigned long long)__popc(b_tie));
+                    if (b_tie) atomicAdd(&a.ctl->n_tie_level, (unsigned long long)__popc(b_tie));
                 }
             }
             __syncwarp();
@@ -219,6 +221,10 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         if (n_out > a.cap) { status = 1; need = n_out; }
         else if (a.want_neg && n_fin[0] + tot[1] > a.fin_cap[0]) { status = 2; need = n_fin[0] + tot[1]; }
         else if (a.want_pos && n_fin[1] + tot[2] > a.fin_cap[1]) { status = 3; need = n_fin[1] + tot[2]; }
+        if (blockIdx.x == 0 && tid == 0) {      // every add of this level happened before the barrier; the next ones come after the next
+            if (status == 0) n_tie += a.ctl->n_tie_level;
+            a.ctl->n_tie_level = 0ull;
+        }
         if (status != 0) {
             // stop with the frontier intact; the counters of this level are stale for the relaunch, which redoes the level
             for (long long t = (long long)blockIdx.x * kThreads + tid; t < 3 * T; t += (long long)gridDim.x * kThreads) cnt[t] = 0;
@@ -357,7 +363,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
     if (blockIdx.x == 0 && tid == 0) {
         TreeCtl* c = a.ctl;
         c->n_cur = N; c->which = which; c->bucket = bucket; c->n_fin[0] = n_fin[0]; c->n_fin[1] = n_fin[1];
-        c->status = status; c->need = need; c->n_evals = n_evals; c->max_frontier = max_frontier;
+        c->status = status; c->need = need; c->n_evals = n_evals; c->max_frontier = max_frontier; c->n_tie = n_tie;
         c->level = level;                        // = levels processed so far
     }
     eng.drain();

@@ -104,11 +104,12 @@ int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg,
     const long long n_splits = split_depth < 0 ? (1ll << 40) : (long long)split_depth + 1;
     // Frontier capacity: the full tree at split_depth, or twice the terminate threshold (a level that enters with fewer
     // nodes than the threshold at most doubles), whichever is smaller -- bounded at first and grown on demand.
-    const long long kCapFirst = 4ll << 20;
+    long long kCapFirst = 4ll << 20;
+    if (const char* e = getenv("NIQ_TREE_CAP")) kCapFirst = std::max(1ll, atoll(e));       // test knob: force the growth path
     long long want = kCapFirst;
     if (split_depth >= 0 && split_depth < 40) want = std::min(want, n_roots << std::min(split_depth, 40));
     if (node_thresh < (1ll << 40)) want = std::min(want, std::max(2 * node_thresh, n_roots));
-    want = std::max<long long>(std::max(want, n_roots), 4096);
+    want = std::max<long long>(std::max(want, n_roots), getenv("NIQ_TREE_CAP") ? 1 : 4096);
 
     TreeBufs b(c);
     TRY(resize_frontier(c, b, want, 0, 0));
@@ -116,7 +117,7 @@ int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg,
     CU(cudaMemcpyAsync(b.hi[0], upper, (size_t)n_roots * 12, cudaMemcpyHostToDevice, c->stream));
     const bool want_fin[2] = {(flags & NIQ_TREE_INTERIOR) != 0, (flags & NIQ_TREE_EXTERIOR) != 0};
     for (int k = 0; k < 2; ++k)
-        if (want_fin[k]) TRY(resize_fin(c, b, k, std::max<long long>(want, 1 << 16), 0));
+        if (want_fin[k]) TRY(resize_fin(c, b, k, std::max<long long>(want, getenv("NIQ_TREE_CAP") ? 1 : (1 << 16)), 0));
     TRY(alloc_async(c, &b.levels, (size_t)4 * kTreeMaxLevels));
     CU(cudaMemsetAsync(b.levels, 0, (size_t)4 * kTreeMaxLevels * sizeof(long long), c->stream));
     TRY(alloc_async(c, &b.ctl, 1));

@@ -181,6 +181,59 @@ def find_any_intersection(func_tuple, params_tuple, lower, upper, eps, viz_nodes
     return False, 0, 0, np.array((-777., -777., -777.), np.float32)
 
 
+def find_any_intersection_batch(func_tuple, params_tuple, lower, upper, eps, R_B=None, t_B=None, R_A=None, t_A=None, stats=None,
+                                ctx=None):
+    """Ours: a BATCH of find_any_intersection queries that differ in the rigid transforms of the shapes -- the values the
+    reference's GUI writes into params["0000.spatial_transformation.R" / ".t"] before every call
+    (src/main_intersection.py:171-183).  R_* (n,3,3), t_* (n,3); a shape that receives transforms must have a
+    spatial_transformation as its first op (mlp.prepend_op).  The growing-form modes run all queries in ONE persistent kernel
+    (niq_find_any_intersection_batch); other modes run one call per query.  -> (found (n,) bool, loc (n,3) f32); query i
+    equals find_any_intersection with R[i], t[i] stored in the params."""
+    if len(func_tuple) != 2 or len(params_tuple) != 2:
+        raise ValueError("intersection supports pairwise only as written")
+    ctx = ctx or _niq.default_context()
+    lower, upper = _vec3(lower, "lower"), _vec3(upper, "upper")
+
+    def pack(R, t):
+        if R is None and t is None:
+            return None
+        R = np.ascontiguousarray(R, np.float32).reshape(-1, 9)
+        t = np.ascontiguousarray(t, np.float32).reshape(-1, 3)
+        if R.shape[0] != t.shape[0]:
+            raise ValueError("R and t must hold one transform per query")
+        return np.ascontiguousarray(np.concatenate((R, t), axis=1))
+    xA, xB = pack(R_A, t_A), pack(R_B, t_B)
+    if xA is None and xB is None:
+        raise ValueError("give the transforms of at least one shape")
+    n = (xA if xA is not None else xB).shape[0]
+    if xA is not None and xB is not None and xA.shape[0] != xB.shape[0]:
+        raise ValueError("both shapes need the same number of transforms")
+    modes = {f.ctx.mode for f in func_tuple}
+    found = np.zeros(n, np.int32)
+    loc = np.full((n, 3), -777., np.float32)
+    st = np.zeros((n, 3), np.int64)
+    if modes <= {"affine_truncate", "affine_all", "affine_append"}:
+        mA, mB = ctx.mlp(params_tuple[0]), ctx.mlp(params_tuple[1])
+        cA, cB = _niq.mode_cfg(func_tuple[0].ctx), _niq.mode_cfg(func_tuple[1].ctx)
+        _niq.check(_niq.lib().niq_find_any_intersection_batch(ctx.handle, mA.handle, C.byref(cA), mB.handle, C.byref(cB), C.c_int64(n),
+                                                              _niq.ptr(xA), _niq.ptr(xB), _niq.ptr(lower), _niq.ptr(upper),
+                                                              C.c_float(eps), _niq.ptr(found), _niq.ptr(loc), _niq.ptr(st)))
+    else:
+        pA, pB = dict(params_tuple[0]), dict(params_tuple[1])
+        for i in range(n):
+            for p, x in ((pA, xA), (pB, xB)):
+                if x is not None:
+                    p["0000.spatial_transformation.R"] = x[i, :9].reshape(3, 3)
+                    p["0000.spatial_transformation.t"] = x[i, 9:]
+            s1 = {}
+            f, _, _, l = find_any_intersection(func_tuple, (pA, pB), lower, upper, eps, stats=s1, ctx=ctx)
+            found[i], loc[i] = int(bool(f)), l
+            st[i] = (s1["n_nodes"], s1["n_rounds"], s1["n_near_tie"])
+    if stats is not None:
+        stats.update(n_nodes=st[:, 0].copy(), n_rounds=st[:, 1].copy(), n_near_tie=st[:, 2].copy())
+    return found.astype(bool), loc
+
+
 def closest_point(func, params, lower, upper, query_points, eps=0.001, batch_process_size=2048, stats=None, ctx=None):
     """src/kd_tree.py:765-802 -> (query_min_dist (Q,), query_min_loc (Q,3)).  Results depend on
     `batch_process_size` exactly as in the reference (global LIFO window)."""

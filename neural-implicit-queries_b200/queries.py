@@ -3,14 +3,21 @@
 
 interval / affine_fixed / slope_interval: ONE persistent CUDA kernel (csrc/niq_kernels.cuh k_cast_rays) marches every ray
 to termination with an in-kernel work queue -- no per-iteration host round trip, no bucket padding.
-affine_all / affine_truncate: the reference's host-level iteration (one pass per step, order-preserving
-compaction) with the bound / point evaluations on the GPU (one CTA per ray segment, niq_grow.cuh)."""
+affine_all / affine_truncate / affine_append: the same, one CTA per ray in flight (csrc/niq_rays_grow.cuh k_cast_rays_grow).
+sdf (and NIQ_RAYS_HOST_LOOP=1, the A/B switch of the tests): the reference's host-level iteration (one pass per step,
+order-preserving compaction) with the bound / point evaluations batched on the GPU."""
 import ctypes as C
+import os
 
 import numpy as np
 
 import _niq
 from bucketing import fits_in_smaller_bucket, get_next_bucket_size
+
+
+# every mode of the reference's factory except 'sdf' marches its rays in ONE persistent kernel (k_cast_rays for the fixed-row modes,
+# k_cast_rays_grow for the growing affine forms); NIQ_RAYS_HOST_LOOP=1 (A/B tests) forces the host-level iteration below
+_PERSISTENT_RAY_MODES = {"interval", "affine_fixed", "slope_interval", "affine_truncate", "affine_all", "affine_append"}
 
 
 def get_default_cast_opts():
@@ -51,7 +58,7 @@ def cast_rays(funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie=Fals
     if roots.ndim != 2 or roots.shape[1] != 3 or roots.shape != dirs.shape:
         raise ValueError("roots and dirs must both have shape (N,3)")
     modes = {f.ctx.mode for f in funcs_tuple}
-    if len(modes) == 1 and modes <= {"interval", "affine_fixed", "slope_interval"}:
+    if len(modes) == 1 and modes <= _PERSISTENT_RAY_MODES and not os.environ.get("NIQ_RAYS_HOST_LOOP"):
         return _cast_rays_persistent(ctx, funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie)
     return _cast_rays_host_loop(ctx, funcs_tuple, params_tuple, roots, dirs, opts, return_near_tie)
 

@@ -28,14 +28,18 @@ def rank_pixels(res_x, res_y, tile, rank, world, tile_stride=1):
     return (py * res_x + px)[ok].astype(np.int64)
 
 
-def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y, tile=16, cast_fn=None, group=None):
+def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y, tile=16, cast_fn=None, group=None,
+                      pixels_of_rank=None):
     """cast_rays over the full image with the rays partitioned across the ranks of `group`; every rank
     returns the full (out_t, out_hit_id, out_count, N_evals) like the single-device call.  N_evals is the
     reference's count for the WHOLE image (src/queries.py:137,164-173: padded lanes per iteration), replayed from the
     gathered per-ray step counts -- not the sum of the per-shard counts, whose bucket padding differs.
-    `cast_fn` defaults to queries.cast_rays (tests inject a CPU stand-in to exercise the plumbing)."""
+    `cast_fn` defaults to queries.cast_rays (tests inject a CPU stand-in to exercise the plumbing).
+    `pixels_of_rank(r, world)` (optional) -> the flat pixel indices rank r casts (default: all tiles of the image dealt
+    round-robin); pixels nobody casts stay zero (bench.py casts a stated sub-sample of the tiles)."""
     import torch
     import torch.distributed as dist
+    device_path = cast_fn is None         # the product path keeps the results on the device until after the gather
     if cast_fn is None:
         import queries
         cast_fn = queries.cast_rays
@@ -43,32 +47,53 @@ def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     n = roots.shape[0]
     assert n == res_x * res_y, "rays must be the full image in generate_camera_rays order"
-    mine = rank_pixels(res_x, res_y, tile, rank, world)
-    t, hit, cnt, n_evals = cast_fn(funcs_tuple, params_tuple, roots[mine], dirs[mine], opts)[:4]
+    if pixels_of_rank is None:
+        pixels_of_rank = lambda r, w: rank_pixels(res_x, res_y, tile, r, w)
+    mine = pixels_of_rank(rank, world)
     if world == 1:
+        t, hit, cnt, _ = cast_fn(funcs_tuple, params_tuple, roots[mine], dirs[mine], opts)[:4]
         out_t = np.zeros(n, np.float32); out_h = np.zeros(n, np.int32); out_c = np.zeros(n, np.int32)
         out_t[mine], out_h[mine], out_c[mine] = t, hit, cnt
         return out_t, out_h, out_c, replay_n_evals(out_c, opts)
-    # one gather of (idx, t, hit, count), padded to the largest shard
     backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    sizes = [len(rank_pixels(res_x, res_y, tile, r, world)) for r in range(world)]
+    shards = [pixels_of_rank(r, world) for r in range(world)]
+    sizes = [len(x) for x in shards]
     cap = max(sizes)
-    pack = torch.zeros((cap, 3), dtype=torch.int32)
-    pack[:len(mine), 0] = torch.from_numpy(t.view(np.int32))
-    pack[:len(mine), 1] = torch.from_numpy(hit)
-    pack[:len(mine), 2] = torch.from_numpy(cnt)
-    pack = pack.to(dev)
-    out = torch.empty((world, cap, 3), dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(out.view(-1, 3), pack, group=group) if backend == "nccl" else \
-        dist.all_gather(list(out.unbind(0)), pack, group=group)
-    out = out.cpu().numpy()
+    if backend == "nccl" and device_path:
+        # results stay on the device: the persistent kernel writes (t, hit_id, count) into the rows of ONE packed buffer,
+        # which is all-gathered over NVLink as it is (12 B/ray, one NCCL call), then read back once
+        import _niq
+        dev = torch.device("cuda", torch.cuda.current_device())
+        r_d = torch.from_numpy(np.ascontiguousarray(roots[mine])).to(dev)
+        d_d = torch.from_numpy(np.ascontiguousarray(dirs[mine])).to(dev)
+        pack = torch.zeros((3, cap), dtype=torch.int32, device=dev)
+        torch.cuda.current_stream().synchronize()              # the library runs on its own stream
+        queries.cast_rays_device(funcs_tuple, params_tuple, len(mine), r_d.data_ptr(), d_d.data_ptr(), pack[0].data_ptr(),
+                                 pack[1].data_ptr(), pack[2].data_ptr(), opts, want_n_evals=False,
+                                 ctx=_niq.default_context(torch.cuda.current_device()))
+        out = torch.empty((world, 3, cap), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(out, pack, group=group)
+        out = out.cpu().numpy()
+    else:
+        t, hit, cnt, _ = cast_fn(funcs_tuple, params_tuple, roots[mine], dirs[mine], opts)[:4]
+        dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+        pack = torch.zeros((3, cap), dtype=torch.int32)
+        pack[0, :len(mine)] = torch.from_numpy(t.view(np.int32))
+        pack[1, :len(mine)] = torch.from_numpy(hit)
+        pack[2, :len(mine)] = torch.from_numpy(cnt)
+        pack = pack.to(dev)
+        out = torch.empty((world, 3, cap), dtype=torch.int32, device=dev)
+        if backend == "nccl":
+            dist.all_gather_into_tensor(out, pack, group=group)
+        else:
+            dist.all_gather(list(out.unbind(0)), pack, group=group)
+        out = out.cpu().numpy()
     out_t = np.zeros(n, np.float32); out_h = np.zeros(n, np.int32); out_c = np.zeros(n, np.int32)
     for r in range(world):
-        idx = rank_pixels(res_x, res_y, tile, r, world)
-        out_t[idx] = out[r, :sizes[r], 0].view(np.float32)
-        out_h[idx] = out[r, :sizes[r], 1]
-        out_c[idx] = out[r, :sizes[r], 2]
+        idx = shards[r]
+        out_t[idx] = out[r, 0, :sizes[r]].view(np.float32)
+        out_h[idx] = out[r, 1, :sizes[r]]
+        out_c[idx] = out[r, 2, :sizes[r]]
     return out_t, out_h, out_c, replay_n_evals(out_c, opts)
 
 
@@ -136,32 +161,77 @@ def deal_boxes(n_boxes, rank, world):
     return np.arange(rank, n_boxes, world, dtype=np.int64)
 
 
-def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_fn=None, group=None, **kw):
+def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_fn=None, group=None, to_host=True, **kw):
     """construct_uniform_unknown_levelset_tree with subtrees sharded across ranks: the top `top_depth`
     levels are built on every rank (replicated, tiny), the surviving frontier is dealt round-robin, each rank
     refines its own boxes to `split_depth`, and the UNKNOWN leaves are all-gathered (24 B/leaf).
-    Leaf ORDER differs from the single-device call (canonicalise before comparing).  -> (lower, upper) (L,3)."""
+    Leaf ORDER differs from the single-device call (canonicalise before comparing).  -> (lower, upper) (L,3).
+    to_host=False (NCCL only): return (gathered device tensor (world, 2, cap, 3), per-rank counts) without the read-back."""
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    backend = dist.get_backend(group) if world > 1 else None
+    if world > 1 and backend == "nccl" and build_fn is None:
+        return _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, rank, world, group, kw, to_host)
     lo, hi = _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, rank, world, kw)
     if world == 1:
         return lo, hi
-    backend = dist.get_backend(group)
-    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
-    cnt = torch.tensor([lo.shape[0]], dtype=torch.int64, device=dev)
-    counts = [torch.zeros_like(cnt) for _ in range(world)]
-    dist.all_gather(counts, cnt, group=group)
-    counts = [int(c.item()) for c in counts]
-    cap = max(max(counts), 1)
-    pack = torch.zeros((cap, 6), dtype=torch.float32)
-    pack[:lo.shape[0], :3] = torch.from_numpy(lo)
-    pack[:lo.shape[0], 3:] = torch.from_numpy(hi)
-    parts = [torch.empty((cap, 6), dtype=torch.float32, device=dev) for _ in range(world)]
-    dist.all_gather(parts, pack.to(dev), group=group)
-    allp = np.concatenate([p.cpu().numpy()[:c] for p, c in zip(parts, counts)])
+    parts = _gather_rows(np.concatenate((lo, hi), axis=1), world, rank, group, 6, torch.float32)
+    allp = np.concatenate(parts)
     return allp[:, :3].copy(), allp[:, 3:].copy()
+
+
+def _top_frontier(func, params, lower, upper, split_depth, top_depth, world, kw):
+    import kd_tree
+    if top_depth is None:
+        top_depth = min(split_depth, int(np.ceil(np.log2(max(8 * world, 2)))) + 3)
+    top = kd_tree.construct_uniform_unknown_levelset_tree(func, params, lower, upper, split_depth=top_depth, **kw)
+    v = top['unknown_node_valid']
+    return top['unknown_node_lower'][v], top['unknown_node_upper'][v], top_depth
+
+
+def _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, rank, world, group, kw, to_host=True):
+    """NCCL path: this rank's leaves never visit the host before the gather -- the tree's device-resident leaf list is copied
+    into a padded device buffer (niq_tree_copy, device to device), ONE all_gather_into_tensor moves 24 B/leaf over NVLink
+    (after an 8-byte all_gather of the counts), and the gathered leaves are read back once."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    import _niq
+    import kd_tree
+    dev = torch.device("cuda", torch.cuda.current_device())
+    flo, fhi, top_depth = _top_frontier(func, params, lower, upper, split_depth, top_depth, world, kw)
+    mine = deal_boxes(flo.shape[0], rank, world)
+    tkw = {k: v for k, v in kw.items() if k in ("offset", "batch_process_size", "ctx")}
+    tree = None
+    n_mine = 0
+    if len(mine):
+        tree = kd_tree.build_tree(func, params, flo[mine], fhi[mine], split_depth=split_depth - top_depth, **tkw)
+        n_mine = tree.count(0)
+    try:
+        cnt = torch.tensor([n_mine], dtype=torch.int64, device=dev)
+        counts = torch.empty(world, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(counts, cnt, group=group)
+        counts = counts.cpu().tolist()
+        cap = max(max(counts), 1)
+        pack = torch.zeros((2, cap, 3), dtype=torch.float32, device=dev)
+        torch.cuda.current_stream().synchronize()
+        if n_mine:
+            _niq.check(_niq.lib().niq_tree_copy(tree.handle, C.c_int(0), C.c_void_p(pack[0].data_ptr()), C.c_void_p(pack[1].data_ptr()),
+                                                C.c_int64(cap), C.c_int(_niq.MEM_DEVICE)))
+        out = torch.empty((world, 2, cap, 3), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(out, pack, group=group)
+        if not to_host:
+            torch.cuda.current_stream().synchronize()
+            return out, counts
+        out = out.cpu().numpy()
+    finally:
+        if tree is not None:
+            tree.close()
+    lo = np.concatenate([out[r, 0, :counts[r]] for r in range(world)])
+    hi = np.concatenate([out[r, 1, :counts[r]] for r in range(world)])
+    return lo, hi
 
 
 def _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, rank, world, kw):
@@ -221,8 +291,8 @@ def hierarchical_marching_cubes_sharded(func, params, lower, upper, depth, n_sub
 
 
 def _gather_rows(local, world, rank, group, width, dtype):
-    """all_gather of per-rank (n_r, width) float32 blocks of different lengths -> list of arrays (one collective of
-    counts, one padded all_gather)."""
+    """all_gather of per-rank (n_r, width) blocks of different lengths -> list of arrays: an 8-byte all_gather of the
+    counts, then ONE padded all_gather of the rows (NCCL: all_gather_into_tensor on device buffers)."""
     import torch
     import torch.distributed as dist
     backend = dist.get_backend(group)
@@ -234,9 +304,14 @@ def _gather_rows(local, world, rank, group, width, dtype):
     cap = max(max(counts), 1)
     pack = torch.zeros((cap, width), dtype=dtype)
     pack[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local))
-    parts = [torch.empty((cap, width), dtype=dtype, device=dev) for _ in range(world)]
-    dist.all_gather(parts, pack.to(dev), group=group)
-    return [p.cpu().numpy()[:c] for p, c in zip(parts, counts)]
+    pack = pack.to(dev)
+    out = torch.empty((world, cap, width), dtype=dtype, device=dev)
+    if backend == "nccl":
+        dist.all_gather_into_tensor(out, pack, group=group)
+    else:
+        dist.all_gather(list(out.unbind(0)), pack, group=group)
+    out = out.cpu().numpy()
+    return [out[r, :c] for r, c in enumerate(counts)]
 
 
 def closest_point_sharded(func, params, lower, upper, query_points, eps=0.001, batch_process_size=2 ** 26, cp_fn=None,

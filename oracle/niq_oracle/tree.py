@@ -319,12 +319,21 @@ def closest_point(ctx, params, lower, upper, query_points, eps=0.001, batch_proc
         is_small = width < eps_cube_width
         pts = (center[:, None, :] + ext[:, None, :] * _SAMPLE_OFFSETS[None, :, :]).astype(F32)
 
-        lab, lo_b, up_b, sc_b = net.classify_box(params, ctx, lo, hi, return_scale=True)
-        tie_b = net.bound_near_tie(lo_b, up_b, 0.0, sc_b, rel=net.tie_rel(params)) & valid
+        # The reference pushes all B lanes through the net; every use of a lane's label / sample values is masked by `valid`
+        # (= the first n_valid lanes), so only those are evaluated here (B = 2^21 would otherwise cost 2 M boxes per round)
+        n_valid = int(valid.sum())
+        lab = np.zeros((B,), np.int32)
+        vals = np.ones((B, 7), F32)
+        lab_v, lo_b, up_b, sc_b = net.classify_box(params, ctx, lo[:n_valid], hi[:n_valid], return_scale=True)
+        lab[:n_valid] = lab_v
+        tie_b = np.zeros((B,), bool)
+        tie_b[:n_valid] = net.bound_near_tie(lo_b, up_b, 0.0, sc_b, rel=net.tie_rel(params))
         n_tie += int(tie_b.sum())
         tie_query[b_id[tie_b]] = True
         is_outside = (lab == net.SIGN_NEGATIVE) | (lab == net.SIGN_POSITIVE)
-        vals = net.eval_points(params, pts.reshape(-1, 3)).reshape(-1, 7)
+        for s0 in range(0, n_valid, 1 << 16):
+            s1 = min(s0 + (1 << 16), n_valid)
+            vals[s0:s1] = net.eval_points(params, pts[s0:s1].reshape(-1, 3)).reshape(-1, 7)
         spans = ~_all_same_sign(vals) & valid
         this_dist = np.where(spans, max_dist_in_node, F32(np.inf)).astype(F32)
         needs = valid & ~is_outside & ~is_small & (d_center < q_min)

@@ -8,7 +8,7 @@ whose bound lies within 1e-5 (relative) of the level set -- counted; values with
 import numpy as np
 import pytest
 
-from conftest import golden, sample_params
+from conftest import golden, parity_report, sample_params
 from niq_oracle import net, rays, tree as otree
 
 pytestmark = pytest.mark.gpu
@@ -532,6 +532,32 @@ def test_cast_rays_vs_oracle(name, mode, res):
         assert n_evals == on_evals
 
 
+@pytest.mark.parametrize("mode,n_trunc,n_sub", [("affine_truncate", 8, 1), ("affine_all", 8, 1), ("affine_append", 4, 1), ("affine_truncate", 64, 3)])
+def test_cast_rays_grow_kernel_equals_host_loop(monkeypatch, mode, n_trunc, n_sub):
+    """The persistent ray kernel of the growing-form modes (csrc/niq_rays_grow.cuh) against the host-level iteration it replaces
+    (NIQ_RAYS_HOST_LOOP=1): same propagation code per segment, same summation order of the two point values -> identical."""
+    import queries
+    import render
+    pf, pb = sample_params("fox"), sample_params("bunny")
+    funcs = (make(pf, mode, n_trunc), make(pb, mode, n_trunc))
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=20, fov_deg=30.)
+    opts = queries.get_default_cast_opts()
+    opts["n_substeps"] = n_sub
+    res = []
+    for host in ("", "1"):
+        if host:
+            monkeypatch.setenv("NIQ_RAYS_HOST_LOOP", host)
+        else:
+            monkeypatch.delenv("NIQ_RAYS_HOST_LOOP", raising=False)
+        res.append(queries.cast_rays(funcs, (pf, pb), roots, dirs, opts, return_near_tie=True))
+    a, b = res
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+    assert (a[1] == 1).any() and (a[1] == 2).any() and (a[1] == 0).any()
+
+
 def test_cast_rays_empty_and_single():
     import queries
     p = sample_params("fox")
@@ -713,16 +739,24 @@ def test_tree_vs_oracle(name, depth):
                                                           with_interior_nodes=True, with_exterior_nodes=True, stats=st)
     ref = otree.construct_uniform_unknown_levelset_tree(octx("affine_fixed"), p, LO, HI, split_depth=depth,
                                                         with_interior_nodes=True, with_exterior_nodes=True, stats=ost)
-    if ost["n_near_tie"] == 0 and st["n_near_tie"] == 0:
+    n_tie = ost["n_near_tie"] + st["n_near_tie"]
+    parity_report(f"tree_vs_oracle[{name}-d{depth}]", boxes=ost["n_evals"], near_tie_gpu=st["n_near_tie"], near_tie_oracle=ost["n_near_tie"])
+    assert n_tie <= 1e-3 * ost["n_evals"] + 2, "more than 0.1 % of the boxes inside the near-tie band"
+    if n_tie == 0:
         assert st["n_evals"] == ost["n_evals"]
         for tag in ("unknown", "interior", "exterior"):
             v, rv = out[f"{tag}_node_valid"], ref[f"{tag}_node_valid"]
             assert v.shape == rv.shape
             np.testing.assert_array_equal(out[f"{tag}_node_lower"][v], ref[f"{tag}_node_lower"][rv])
             np.testing.assert_array_equal(out[f"{tag}_node_upper"][v], ref[f"{tag}_node_upper"][rv])
-    else:   # topology may differ only below near-tie boxes: the node counts stay within that budget
-        n, rn = int(out["unknown_node_valid"].sum()), int(ref["unknown_node_valid"].sum())
-        assert abs(n - rn) <= (ost["n_near_tie"] + st["n_near_tie"]) * 2 ** 4
+    else:
+        # topology may differ only below near-tie boxes: every leaf of one tree that is missing from the other must lie
+        # inside a near-tie box's subtree, so the symmetric difference is bounded by the flagged boxes' descendants
+        a = {r.tobytes() for r in _canon(out["unknown_node_lower"][out["unknown_node_valid"]], out["unknown_node_upper"][out["unknown_node_valid"]])}
+        b = {r.tobytes() for r in _canon(ref["unknown_node_lower"][ref["unknown_node_valid"]], ref["unknown_node_upper"][ref["unknown_node_valid"]])}
+        n_diff = len(a ^ b)
+        parity_report(f"tree_vs_oracle[{name}-d{depth}]:topology", leaves=len(b), leaves_differing=n_diff)
+        assert n_diff <= n_tie * 2 ** 4
 
 
 def test_tree_deep_properties():
@@ -786,6 +820,69 @@ def test_tree_multi_root_and_sharded_equal_single_tree():
         kd_tree.build_tree(func, p, np.zeros((2, 2), np.float32), np.ones((2, 2), np.float32), split_depth=2)
 
 
+@pytest.mark.parametrize("name,mode,kw", [
+    ("fox", "affine_fixed", dict(split_depth=11, with_interior_nodes=True, with_exterior_nodes=True, batch_process_size=128)),
+    ("bunny", "interval", dict(split_depth=13, with_interior_nodes=True)),
+    ("hammer", "slope_interval", dict(split_depth=12, with_exterior_nodes=True, offset=0.01)),
+    ("birdcage_occ", "affine_fixed", dict(node_terminate_thresh=3000, with_interior_nodes=True, with_exterior_nodes=True)),
+    ("bunny", "affine_fixed", dict(split_depth=17, batch_process_size=4096)),
+    ("fox", "affine_fixed", dict(split_depth=2)),
+])
+def test_tree_persistent_kernel_equals_level_loop(monkeypatch, name, mode, kw):
+    """The one-launch cooperative tree kernel (csrc/niq_tree.cuh) against the per-level host loop it replaces
+    (NIQ_TREE_LEGACY=1): the same engine classifies the same boxes, so every array, its ORDER, the per-level counts and the
+    statistics must be bit-identical."""
+    import kd_tree
+    p = sample_params(name)
+    func = make(p, mode)
+    res = []
+    for legacy in ("0", "1"):
+        monkeypatch.setenv("NIQ_TREE_LEGACY", legacy)
+        st = {}
+        out = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, stats=st, **kw)
+        res.append((out, st))
+    (a, sa), (b, sb) = res
+    assert sa == sb, (sa, sb)
+    assert sorted(a) == sorted(b)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert int(a["unknown_node_valid"].sum()) > 0
+
+
+def test_tree_persistent_kernel_multi_root_and_growth(monkeypatch):
+    """Multi-root builds (the unit of the subtree sharding) through the cooperative kernel, and a build whose frontier
+    outgrows the first buffer (relaunch from the level that did not fit): both equal the level loop."""
+    import kd_tree
+    p = sample_params("bunny")
+    func = make(p, "affine_fixed")
+    top = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, split_depth=7)
+    tv = top["unknown_node_valid"]
+    rl, ru = top["unknown_node_lower"][tv], top["unknown_node_upper"][tv]
+    outs = []
+    for legacy in ("0", "1"):
+        monkeypatch.setenv("NIQ_TREE_LEGACY", legacy)
+        tree = kd_tree.build_tree(func, p, rl, ru, split_depth=9, with_interior_nodes=True)
+        try:
+            outs.append((tree.nodes(0), tree.nodes(1), tree.stats(), tree.level_info()))
+        finally:
+            tree.close()
+    for x, y in zip(outs[0][:2], outs[1][:2]):
+        np.testing.assert_array_equal(x[0], y[0])
+        np.testing.assert_array_equal(x[1], y[1])
+    assert outs[0][2] == outs[1][2] and outs[0][3] == outs[1][3]
+    # growth: NIQ_TREE_CAP (test knob) makes the first buffers 3,000 nodes, so the frontier and the exterior list outgrow them
+    monkeypatch.setenv("NIQ_TREE_LEGACY", "0")
+    monkeypatch.setenv("NIQ_TREE_CAP", "3000")
+    st = {}
+    deep = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, split_depth=20, with_exterior_nodes=True, stats=st)
+    monkeypatch.setenv("NIQ_TREE_LEGACY", "1")
+    st2 = {}
+    deep2 = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, split_depth=20, with_exterior_nodes=True, stats=st2)
+    assert st == st2 and int(deep["exterior_node_valid"].sum()) > 65536 and st["max_frontier"] > 100000
+    for k in deep:
+        np.testing.assert_array_equal(deep[k], deep2[k], err_msg=k)
+
+
 @pytest.mark.parametrize("case,name", [("mc_fox_d4_s2", "fox"), ("mc_bunny_d4_s3", "bunny")])
 def test_marching_cubes_golden(case, name):
     import kd_tree
@@ -831,15 +928,22 @@ def test_find_any_intersection_golden(case, mode):
     pA = sample_params("hammer")
     pB = mlp.prepend_op(sample_params("bunny"), mlp.spatial_transformation())
     fA, fB = make(pA, mode, g["n_trunc"]), make(pB, mode, g["n_trunc"])
+    n_cmp = n_flag = n_bad = 0
     for i in range(g["R"].shape[0]):
         pB["0000.spatial_transformation.R"] = g["R"][i]
         pB["0000.spatial_transformation.t"] = g["t"][i]
         st = {}
         found, ia, ib, loc = kd_tree.find_any_intersection((fA, fB), (pA, pB), LO, HI, float(g["eps"]), stats=st)
+        n_cmp += 1
         if st["n_near_tie"] == 0:
             assert bool(found) == bool(g["found"][i])
             np.testing.assert_allclose(loc, g["loc"][i], rtol=0, atol=1e-6)
+        else:
+            n_flag += 1
+            n_bad += bool(found) != bool(g["found"][i])
         assert (ia, ib) == ((1, 2) if found else (0, 0))
+    parity_report(f"find_any_intersection_golden[{case}]", queries=n_cmp, flagged=n_flag, flagged_verdict_mismatch=n_bad)
+    assert n_flag <= max(1, n_cmp // 2) and n_bad == 0
 
 
 def test_find_any_intersection_vs_oracle_list():
@@ -850,7 +954,7 @@ def test_find_any_intersection_vs_oracle_list():
     pA = sample_params("hammer")
     pB = mlp.prepend_op(sample_params("bunny"), mlp.spatial_transformation())
     fA, fB = make(pA, "affine_fixed"), make(pB, "affine_fixed")
-    n_found = 0
+    n_found = n_flag = n_bad = 0
     for i in range(12):
         th = rng.uniform(0, 2 * np.pi)
         R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
@@ -865,7 +969,12 @@ def test_find_any_intersection_vs_oracle_list():
             assert bool(found) == bool(ofound)
             assert st["n_nodes"] == ost["n_nodes"] and st["n_rounds"] == ost["n_rounds"]
             np.testing.assert_allclose(loc, oloc, rtol=0, atol=1e-6)
+        else:
+            n_flag += 1
+            n_bad += bool(found) != bool(ofound)
         n_found += bool(found)
+    parity_report("find_any_intersection_vs_oracle_list", queries=12, flagged=n_flag, flagged_verdict_mismatch=n_bad)
+    assert n_flag <= 6 and n_bad == 0
     assert 0 < n_found < 12
 
 
@@ -890,13 +999,20 @@ def test_closest_point_vs_oracle(B):
     st, ost = {}, {}
     d, loc = kd_tree.closest_point(make(p, "affine_fixed"), p, LO, HI, q, eps=0.01, batch_process_size=B, stats=st)
     od, oloc = otree.closest_point(octx("affine_fixed"), p, LO, HI, q, eps=0.01, batch_process_size=B, stats=ost)
+    ok = np.abs(d - od) <= RTOL * od
+    ok |= ~np.isfinite(od) & ~np.isfinite(d)
+    parity_report(f"closest_point_vs_oracle[B={B}]", queries=24, near_tie_boxes_gpu=st["n_near_tie"], near_tie_boxes_oracle=ost["n_near_tie"],
+                  visits=ost["n_visits"], dist_within_1e5=int(ok.sum()))
     if st["n_near_tie"] == 0 and ost["n_near_tie"] == 0:
         assert st["n_visits"] == ost["n_visits"] and st["n_rounds"] == ost["n_rounds"]
         np.testing.assert_allclose(d, od, rtol=RTOL)
         fin = np.isfinite(od)
         np.testing.assert_allclose(loc[fin], oloc[fin], rtol=0, atol=1e-6)
     else:
-        assert np.mean(np.abs(d - od) <= 1e-5 * od) > 0.7
+        # a label flipped inside the band re-orders the shared LIFO stack: the flagged boxes must stay rare
+        # and the distances must still agree for most queries
+        assert st["n_near_tie"] + ost["n_near_tie"] <= 1e-3 * ost["n_visits"] + 2
+        assert ok.mean() > 0.7
 
 
 # ---------------------------------------------------------------------------------------------------
