@@ -596,6 +596,20 @@ def config_metrics(ctx, peak_tflops, cpu=True):
     cfg["cfg1_fox_512x512_cast_rays"] = {"rays_per_s": roots.shape[0] / dt, "ray_steps_per_s": steps1 / dt, "ms": dt * 1e3, "device_ms": dms,
                                          "hits": int((r[1] > 0).sum()), "ray_steps": steps1, "roofline": roof(10 * Mf * steps1, macs, dms * 1e-3),
                                          "kernel": "k_cast_rays<32>"}
+    # ---- config 5's other activation: the same 3->256x8->1 shape with TanH (north_star "ReLU/TanH").  PARITY UNPINNED: the reference has
+    # no tanh rule; ours is checked for soundness and against its own oracle (tests/test_tanh.py) ----
+    pt = mlp.initialize_params(mlp.build_spec(mlp.quick_mlp_spec(LAYERS, "tanh")), 0)
+    ft = implicit_mlp_utils.generate_implicit_from_params(pt, "affine_fixed")
+    tl, ntx = chosen_tiles(74)
+    pix = pixels_of_tiles(tl, ntx)
+    r5, d5 = camera_rays()
+    r5, d5 = r5[pix], d5[pix]
+    dt, dms, macs, r = timed(lambda: queries.cast_rays((ft,), (pt,), r5, d5, o, ctx=ctx), reps=2)
+    steps5 = int(r[2].sum())
+    cfg["cfg5_tanh_8x256_cast_rays"] = {"rays_per_s": r5.shape[0] / dt, "ray_steps_per_s": steps5 / dt, "ms": dt * 1e3, "device_ms": dms, "rays": int(r5.shape[0]),
+                                        "hits": int((r[1] > 0).sum()), "ray_steps": steps5, "roofline": roof(10 * ctx.mlp(pt).macs * steps5, macs, dms * 1e-3),
+                                        "kernel": "k_cast_rays<256>", "parity": "UNPINNED (no tanh rule in the reference; self-written oracle, soundness tests)",
+                                        "sample": "74 of the image's 16x16 tiles (every 109th)"}
     # ---- config 2: bunny tree depth 12 / 21, hierarchical marching cubes depth 7 (n_subcell_depth 3) ----
     p = mlps["bunny"]
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")

@@ -2,7 +2,7 @@
  * niq.h -- C ABI of the B200-native range-analysis backend for neural implicit queries.
  *
  * The reference (nmwsharp/neural-implicit-queries) has no native / FFI layer: its boundary is the Python
- * function API of src/*.py, backed by XLA.  This header is the boundary a binding would target instead;
+ * function API of its src/ modules, backed by XLA.  This header is the boundary a binding would target instead;
  * every entry point cites the reference function it replaces (paths relative to the reference repo).
  * The Python modules in neural-implicit-queries_b200/ bind it with ctypes and re-expose the reference's
  * module / function names.
@@ -49,8 +49,11 @@ typedef enum niq_op_kind {
     NIQ_OP_SQUEEZE_LAST = 3, /* src/mlp.py:328-332, src/affine_layers.py:164-172                            */
     NIQ_OP_SPATIAL = 4,      /* src/mlp.py:335-347, src/affine_layers.py:175-179 : A = R (3,3), b = t (3)    */
     NIQ_OP_SIN = 5,          /* src/mlp.py:296-300, src/affine_layers.py:100-137, src/slope_interval_layers.py:85-110 */
-    NIQ_OP_POW2_ENCODE = 6   /* src/mlp.py:304-322, src/affine_layers.py:140-161: in_dim = 3, out_dim = #coefs (per input
+    NIQ_OP_POW2_ENCODE = 6,  /* src/mlp.py:304-322, src/affine_layers.py:140-161: in_dim = 3, out_dim = #coefs (per input
                                 coordinate), A = coefs (out_dim), b = shift (out_dim) or NULL; must be the first op         */
+    NIQ_OP_TANH = 7          /* OURS, PARITY UNPINNED: the reference's README names TanH MLPs but its code registers no tanh op
+                                or rule; Chebyshev-style linearisation written from the paper's construction
+                                (csrc/niq_engine.cuh tanh_lin = oracle/niq_oracle/net.py _tanh_coeffs), key "<i>.tanh._"     */
 } niq_op_kind;
 
 typedef struct niq_op_desc {
@@ -133,7 +136,7 @@ int niq_measure_fp32_peak(niq_ctx* ctx, float* tflops);
 
 /* ---- MLP handle: replaces src/mlp.py:96-144 (op-list interpreter) + :173-185 (load) ---------- */
 /* Supported op sequences: an optional spatial_transformation, an optional pow2_frequency_encode on the 3-D input, then
- * dense ops each optionally followed by ONE of relu / elu / sin, with an optional trailing squeeze_last (requires
+ * dense ops each optionally followed by ONE of relu / elu / sin / tanh, with an optional trailing squeeze_last (requires
  * out_dim 1; no activation after the last dense).  Input dimension 3, hidden widths <= 256.  Weights are copied and
  * packed once.                                                                                              */
 int niq_mlp_create(niq_ctx* ctx, int32_t n_ops, const niq_op_desc* ops, niq_mlp** out);

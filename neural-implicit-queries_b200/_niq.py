@@ -20,7 +20,7 @@ LIB_PATH = os.environ.get("NIQ_LIB") or os.path.join(_HERE, "libniq.so")   # NIQ
 
 NIQ_OK, NIQ_EINVAL, NIQ_ENOMEM, NIQ_ECUDA, NIQ_ECAPACITY, NIQ_EUNSUPPORTED = 0, -1, -2, -3, -4, -5
 MEM_HOST, MEM_DEVICE = 0, 1
-OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL, OP_SIN, OP_POW2_ENCODE = 0, 1, 2, 3, 4, 5, 6
+OP_DENSE, OP_RELU, OP_ELU, OP_SQUEEZE_LAST, OP_SPATIAL, OP_SIN, OP_POW2_ENCODE, OP_TANH = 0, 1, 2, 3, 4, 5, 6, 7
 MODE_IDS = {"interval": 0, "affine_fixed": 1, "affine_truncate": 2, "affine_all": 3, "affine_append": 4, "sdf": 5,
             "slope_interval": 6}
 TREE_INTERIOR, TREE_EXTERIOR = 1, 2
@@ -246,7 +246,8 @@ def params_digest(params):
 
 
 _OP_KINDS = {"dense": OP_DENSE, "relu": OP_RELU, "elu": OP_ELU, "squeeze_last": OP_SQUEEZE_LAST,
-             "spatial_transformation": OP_SPATIAL, "sin": OP_SIN, "pow2_frequency_encode": OP_POW2_ENCODE}
+             "spatial_transformation": OP_SPATIAL, "sin": OP_SIN, "pow2_frequency_encode": OP_POW2_ENCODE,
+             "tanh": OP_TANH}          # tanh: ours, parity unpinned (the reference has no tanh op)
 
 
 def op_descs(params):
@@ -260,7 +261,7 @@ def op_descs(params):
         args.pop("_", None)
         if name not in _OP_KINDS:
             raise NiqError(NIQ_EUNSUPPORTED, f"op '{name}' is not an op of the reference's mlp format (dense, relu, elu, sin, "
-                                             "pow2_frequency_encode, squeeze_last, spatial_transformation)")
+                                             "pow2_frequency_encode, squeeze_last, spatial_transformation) nor 'tanh' (ours)")
         d = descs[i]
         d.kind = _OP_KINDS[name]
         if name == "dense":

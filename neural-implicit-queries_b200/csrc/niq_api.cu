@@ -295,9 +295,10 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
             case NIQ_OP_RELU:
             case NIQ_OP_ELU:
             case NIQ_OP_SIN:
+            case NIQ_OP_TANH:
                 if (raw.empty() || raw.back().act != ACT_NONE)
                     return fail(NIQ_EUNSUPPORTED, "op %d: an activation must directly follow a dense / spatial / encode op", i);
-                raw.back().act = op.kind == NIQ_OP_RELU ? ACT_RELU : op.kind == NIQ_OP_ELU ? ACT_ELU : ACT_SIN;
+                raw.back().act = op.kind == NIQ_OP_RELU ? ACT_RELU : op.kind == NIQ_OP_ELU ? ACT_ELU : op.kind == NIQ_OP_TANH ? ACT_TANH : ACT_SIN;
                 break;
             case NIQ_OP_SQUEEZE_LAST:
                 if (raw.empty() || raw.back().out != 1) return fail(NIQ_EINVAL, "squeeze_last needs a preceding op with out_dim 1");
@@ -362,6 +363,7 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
     nd.n_nets = 1;
     nd.tie_rel = 1e-5f;
     for (const HostLayer& L : m->layers) if (L.act == ACT_SIN) nd.tie_rel = 5e-5f;   // sin rule: float32 conditioning ~1.6e-5 (tests)
+    for (const HostLayer& L : m->layers) if (L.act == ACT_TANH) nd.tie_rel = 1e-4f;  // ours (unpinned rule): secant slope / atanh amplify 1-ulp tanhf differences
     for (const HostLayer& L : m->layers) if (L.act == ACT_ELU) nd.tie_rel = 2e-4f;   // ELU rule conditioning
     for (size_t l = 0; l < m->layers.size(); ++l) {
         const HostLayer& L = m->layers[l];

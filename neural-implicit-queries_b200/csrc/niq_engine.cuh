@@ -31,7 +31,7 @@
 
 namespace niq {
 
-enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_SIN = 3 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_ELU = 2, ACT_SIN = 3, ACT_TANH = 4 };
 
 constexpr int kMaxLayers = 32;     // layers of all nets of one launch (cast_rays concatenates funcs)
 constexpr int kMaxChunks = 192;
@@ -300,6 +300,34 @@ __device__ __forceinline__ void sin_lin(float l, float u, float& alpha, float& b
     alpha = a; beta = b; delta = fabsf(r_hi - b);
 }
 
+// tanh linearisation on [l,u].  PARITY UNPINNED: the reference registers no tanh rule -- this is the Chebyshev-style
+// construction of the paper written from scratch, the same formulas as oracle/niq_oracle/net.py _tanh_coeffs:
+//   alpha = secant slope (tanh u - tanh l) / (u - l), or the derivative at the midpoint for intervals narrower than 1e-2 (the
+//           secant cancels in float32); the residual tanh(x) - alpha x has its extrema over [l,u] at l, u or where
+//           tanh'(x) = alpha, x* = +-atanh(sqrt(1 - alpha)); beta = mid-range of the residual, delta = its half-range.
+// Sound for any alpha in [0,1] because the residual bounds belong to the alpha actually used.
+__device__ __forceinline__ void tanh_lin(float l, float u, float& alpha, float& beta, float& delta) {
+    const float tl = tanhf(l), tu = tanhf(u);
+    const float w = u - l;
+    const float tm = tanhf(0.5f * (l + u));
+    float a = w > 1e-2f ? (tu - tl) / w : 1.f - tm * tm;
+    if (a != a) a = 0.f;
+    a = fminf(fmaxf(a, 0.f), 1.f);
+    const bool zero = a == 0.f;
+    const float rl = zero ? tl : tl - a * l, ru = zero ? tu : tu - a * u;
+    float r_lo = fminf(rl, ru), r_hi = fmaxf(rl, ru);
+    const float xs = atanhf(sqrtf(fmaxf(1.f - a, 0.f)));
+#pragma unroll
+    for (int sgn = 0; sgn < 2; ++sgn) {
+        const float x = fminf(fmaxf(sgn == 0 ? xs : -xs, l), u);           // clipped: an end point, already covered
+        float v = tanhf(x) - a * x;
+        if (zero) v = rl;
+        r_lo = fminf(r_lo, v); r_hi = fmaxf(r_hi, v);
+    }
+    const float b = 0.5f * (r_hi + r_lo);
+    alpha = a; beta = b; delta = fabsf(r_hi - b);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Engine
 // ------------------------------------------------------------------------------------------------
@@ -557,6 +585,11 @@ struct Engine {
                         float dfl, dfu;
                         if (ACT == ACT_RELU) { dfl = pl > 0.f ? 1.f : 0.f; dfu = pu < 0.f ? 0.f : 1.f; }
                         else if (ACT == ACT_ELU) { dfl = fminf(expf(pl), 1.f); dfu = fminf(expf(pu), 1.f); }
+                        else if (ACT == ACT_TANH) {                       // ours (unpinned): 1 - tanh^2, largest nearest to 0
+                            const float far = tanhf(fmaxf(fabsf(pl), fabsf(pu))), near = tanhf(fminf(fabsf(pl), fabsf(pu)));
+                            dfl = 1.f - far * far;
+                            dfu = (pl <= 0.f && pu >= 0.f) ? 1.f : 1.f - near * near;
+                        }
                         else cos_bound(pl, pu, dfl, dfu);                 // sin: the derivative can be negative
 #pragma unroll
                         for (int v = 0; v < NV; ++v) {
@@ -569,7 +602,7 @@ struct Engine {
                             acc[n * RT + 1 + v][c] = nc;
                             acc[n * RT + 1 + NV + v][c] = nu - nc;
                         }
-                        acc[n * RT][c] = ACT == ACT_RELU ? fmaxf(p, 0.f) : ACT == ACT_ELU ? elu_f(p) : sinf(p);
+                        acc[n * RT][c] = ACT == ACT_RELU ? fmaxf(p, 0.f) : ACT == ACT_ELU ? elu_f(p) : ACT == ACT_TANH ? tanhf(p) : sinf(p);
                     } else {
                         acc[n * RT][c] = p;
                     }
@@ -593,6 +626,7 @@ struct Engine {
                     for (int c = 0; c < 8; ++c) {
                         if (ACT == ACT_RELU) relu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
                         else if (ACT == ACT_ELU) elu_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
+                        else if (ACT == ACT_TANH) tanh_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
                         else sin_lin(base[c] - rad[c], base[c] + rad[c], alpha[c], beta[c], delta[c]);
                     }
 #pragma unroll
@@ -615,6 +649,7 @@ struct Engine {
                         if (ACT == ACT_RELU) x = fmaxf(x, 0.f);
                         else if (ACT == ACT_ELU) x = elu_pt(x);
                         else if (ACT == ACT_SIN) x = sinf(x);
+                        else if (ACT == ACT_TANH) x = tanhf(x);
                         acc[n * RT + r][c] = x;
                     }
                 }
@@ -846,6 +881,7 @@ struct Engine {
             if (L.act == ACT_RELU) epilogue<ACT_RELU>(acc, bias);
             else if (L.act == ACT_ELU) epilogue<ACT_ELU>(acc, bias);
             else if (L.act == ACT_SIN) epilogue<ACT_SIN>(acc, bias);
+            else if (L.act == ACT_TANH) epilogue<ACT_TANH>(acc, bias);
             else epilogue<ACT_NONE>(acc, bias);
         }
         if (sp_out) {

@@ -38,14 +38,16 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 struct GrowCfg {          // what the growing-form propagation needs to know about the mode
     int truncate, n_keep, n_append, kcap, W;
+    int wfloats;          // floats of the largest layer's weights (in_pad x out_pad): the staging buffer of grow_forward
 };
 struct GrowState {        // shared-memory carve-up of one CTA (see grow_carve); aff / tmp swap on every truncation
     float *base, *base2, *err, *err2, *alpha, *delta, *red, *mags;
     int* rank;
     float *aff, *tmp;
+    float* wbuf;          // [wfloats] the current layer's weights, prefetched with cp.async while the previous layer's activation runs
 };
 __host__ __device__ inline size_t grow_state_floats(const GrowCfg& g) {
-    return (size_t)22 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W * (g.truncate ? 2 : 1) + 16;
+    return (size_t)22 * g.W + 2 * (size_t)g.kcap + (size_t)g.kcap * g.W * (g.truncate ? 2 : 1) + (size_t)g.wfloats + 16;
 }
 __device__ __forceinline__ void grow_carve(float* sm, const GrowCfg& g, GrowState& s) {
     const int W = g.W;
@@ -60,7 +62,17 @@ __device__ __forceinline__ void grow_carve(float* sm, const GrowCfg& g, GrowStat
     s.rank = reinterpret_cast<int*>(s.mags + g.kcap);     // [kcap]
     s.aff = reinterpret_cast<float*>(s.rank + g.kcap);    // [kcap][W]
     s.tmp = s.aff + (size_t)g.kcap * W;                   // [kcap][W] (truncate only): the truncated state is built here, then the two swap
+    s.wbuf = s.aff + (size_t)g.kcap * W * (g.truncate ? 2 : 1);
 }
+
+// cp.async (16 B per thread and request) of `n_floats` (a multiple of 4, 16-byte aligned source) into shared memory
+__device__ __forceinline__ void grow_stage_weights(float* dst, const float* src, int n_floats) {
+    const uint32_t d0 = smem_u32(dst);
+    for (int i = threadIdx.x * 4; i < n_floats; i += 256 * 4)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + i * 4), "l"(src + i) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void grow_wait_weights() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // Bound propagation of ONE general box through layers [l0, l1) of `net` by the whole CTA (256 threads).
 // Precondition: the caller wrote the input form -- base[0..3] = centre (4th entry 0), aff rows [0, k) = the box vectors
@@ -68,8 +80,16 @@ __device__ __forceinline__ void grow_carve(float* sm, const GrowCfg& g, GrowStat
 // A0 / b0 (optional): weights / bias that replace those of layer l0 (a per-query spatial_transformation, see
 // niq_find_any_intersection_batch).  On return every thread holds lower / upper / scale (= sum_j |base_j A_j| + |b| of the
 // last dot product, the near-tie yardstick).
+// Point rows (optional, hA != nullptr): warp p additionally evaluates f at the point whose coordinates the caller put in
+// hA[p*W + 0..3] = (x, y, z, 0), riding on the same staged weights (hA / hB: [8][W] ping-pong rows, private to their warp).
+// The arithmetic is that of the engine's point rows (niq_engine.cuh, reference src/mlp.py:253-347): a hidden neuron
+// accumulates fma(h_k, A_kc, acc) for ascending k from 0, then + bias, then the activation; the final dot product is split
+// over `cg_lanes` (= width class / 8) lanes -- lane cg takes k = cg, cg + CG, ... -- and combined by an xor butterfly, like
+// Engine::dot_layer.  pt_f / pt_scale return f and sum_k |h_k w_k| + |b| of point `warp` in every lane of that warp.
 __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, const float* A0, const float* b0, const GrowCfg& g,
-                                             GrowState& st, int k, float& lower, float& upper, float& scale) {
+                                             GrowState& st, int k, float& lower, float& upper, float& scale,
+                                             float* hA = nullptr, float* hB = nullptr, int cg_lanes = 0, float* pt_f = nullptr,
+                                             float* pt_scale = nullptr) {
     __shared__ float s_fin[3];
     __shared__ float s_rest;
     const int W = g.W;
@@ -82,21 +102,32 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
         float* b_nxt = base2;
         float* e_cur = err;
         float* e_nxt = err2;
+        // The weights of a layer are read by every thread many times; they come through shared memory: layer l + 1 is
+        // prefetched (cp.async) right after the dense phase of layer l, so the copy overlaps the activation / truncation phases.
+        float* const A = st.wbuf;
+        {
+            const LayerDev& F = net.layers[l0];
+            grow_stage_weights(A, A0 != nullptr ? A0 : net.chunks[F.chunk_begin].src, F.in_pad * (F.last_of_net ? 1 : F.out_pad));
+        }
         for (int l = l0; l < l1; ++l) {
             const LayerDev& L = net.layers[l];
-            const float* A = (l == l0 && A0 != nullptr) ? A0 : net.chunks[L.chunk_begin].src;
             const float* bias = (l == l0 && b0 != nullptr) ? b0 : L.bias;
+            grow_wait_weights();
+            __syncthreads();
             if (!L.last_of_net) {
                 const int K = L.in_pad, N = L.out_pad;
                 const int Np2 = next_pow2(N);
+                const int lgN = 31 - __clz(Np2);                 // Np2 is a power of two: (tid % Np2, tid / Np2) by mask and shift
                 const int parts = 256 / Np2 >= 8 ? 8 : (256 / Np2 > 0 ? 256 / Np2 : 1);
+                const int c_of_tid = tid & (Np2 - 1), p_of_tid = tid >> lgN;
                 // -- the two vector rows, K split over `parts` thread groups: base@A and err@|A| (partials in red) --
                 {
-                    const int c = tid % Np2, p = tid / Np2;
+                    const int c = c_of_tid, p = p_of_tid;
                     if (c < N && p < parts) {
                         float sb = 0.f, se = 0.f;
+#pragma unroll 4
                         for (int j = p; j < K; j += parts) {
-                            const float w = __ldg(A + (size_t)j * N + c);
+                            const float w = A[j * N + c];
                             sb = fmaf(b_cur[j], w, sb);
                             se = fmaf(e_cur[j], fabsf(w), se);
                         }
@@ -130,7 +161,7 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                                 for (int r = 0; r < 4; ++r) a4[r] = *reinterpret_cast<const float4*>(rp[r] + j);
 #pragma unroll
                                 for (int jj = 0; jj < 4; ++jj) {
-                                    const float4 w = __ldg(reinterpret_cast<const float4*>(A + (size_t)(j + jj) * N + 4 * cg));
+                                    const float4 w = *reinterpret_cast<const float4*>(A + (j + jj) * N + 4 * cg);
 #pragma unroll
                                     for (int r = 0; r < 4; ++r) {
                                         const float a = jj == 0 ? a4[r].x : jj == 1 ? a4[r].y : jj == 2 ? a4[r].z : a4[r].w;
@@ -153,7 +184,36 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                         __syncwarp();
                     }
                 }
+                if (hA != nullptr) {
+                    // -- point rows: warp p pushes point p through this layer (its rows of hin / hout are private to the warp) --
+                    float* hin = (((l - l0) & 1) ? hB : hA) + warp * W;
+                    float* hout = (((l - l0) & 1) ? hA : hB) + warp * W;
+                    float pacc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                    for (int kk = 0; kk < K; ++kk) {
+                        const float a = hin[kk];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (lane + 32 * i < N) pacc[i] = fmaf(a, A[kk * N + lane + 32 * i], pacc[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int c = lane + 32 * i;
+                        if (c < N) {
+                            float x = pacc[i] + __ldg(bias + c);
+                            if (L.act == ACT_RELU) x = fmaxf(x, 0.f);
+                            else if (L.act == ACT_ELU) x = elu_pt(x);
+                            else if (L.act == ACT_SIN) x = sinf(x);
+                            else if (L.act == ACT_TANH) x = tanhf(x);
+                            hout[c] = x;
+                        }
+                    }
+                }
                 __syncthreads();
+                if (l + 1 < l1) {      // every read of this layer's weights is done: fetch the next layer's behind the phases below
+                    const LayerDev& Nx = net.layers[l + 1];
+                    grow_stage_weights(A, net.chunks[Nx.chunk_begin].src, Nx.in_pad * (Nx.last_of_net ? 1 : Nx.out_pad));
+                }
                 // -- finish the vector rows --
                 if (tid < N) {
                     float sb = 0.f, se = 0.f;
@@ -167,7 +227,7 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                 if (L.act != ACT_NONE) {
                     // -- radius per neuron: rad[c] = sum_r |aff[r][c]| + err[c] (partials over row strides) --
                     {
-                        const int c = tid % Np2, p = tid / Np2;
+                        const int c = c_of_tid, p = p_of_tid;
                         if (c < N && p < parts) {
                             float s = 0.f;
                             for (int r = p; r < k; r += parts) s += fabsf(aff[(size_t)r * W + c]);
@@ -184,6 +244,7 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                         float al, be, de;
                         if (L.act == ACT_RELU) relu_lin(b0 - rad, b0 + rad, al, be, de);
                         else if (L.act == ACT_ELU) elu_lin(b0 - rad, b0 + rad, al, be, de);
+                        else if (L.act == ACT_TANH) tanh_lin(b0 - rad, b0 + rad, al, be, de);
                         else sin_lin(b0 - rad, b0 + rad, al, be, de);
                         b_cur[c] = al * b0 + be;
                         e_cur[c] = al * e_cur[c];
@@ -208,7 +269,8 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                             drank[tid] = rk;
                             if (rk < na) mags[rk] = d;
                         }
-                        for (int idx = tid; idx < na * N; idx += blockDim.x) aff[(size_t)k * W + (idx / N) * W + (idx % N)] = 0.f;
+                        for (int r = warp; r < na; r += 8)
+                            for (int c = lane; c < N; c += 32) aff[(size_t)(k + r) * W + c] = 0.f;
                         __syncthreads();
                         if (tid < w && drank[tid] < na) aff[(size_t)(k + drank[tid]) * W + tid] = delta[tid];
                         if (warp == 0) {
@@ -257,9 +319,9 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                             }
                         }
                     }
-                    for (int idx = tid; idx < L.out_dim * N; idx += blockDim.x) {
-                        const int r = idx / N, c = idx - r * N;
-                        aff[(size_t)(k + r) * W + c] = (r == c) ? delta[c] : 0.f;
+                    for (int r = warp; r < L.out_dim; r += 8) {              // row r of diag(delta): one warp per row
+                        float* row = aff + (size_t)(k + r) * W;
+                        for (int c = lane; c < N; c += 32) row[c] = (r == c) ? delta[c] : 0.f;
                     }
                     if (trunc && tid < L.out_dim) mags[k + tid] = fabsf(delta[tid]);   // L1 norm of a diag row
                     k += L.out_dim;
@@ -269,21 +331,30 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                         // -- keep the n_keep rows of largest L1 norm, stable (reference src/affine.py:127-162) --
                         // rank[r] = #rows that sort before r; two threads per row, each scans half of the rows
                         for (int r = tid; r < k; r += blockDim.x) rank[r] = 0;
+                        if (tid < 4 && k + tid < g.kcap) mags[k + tid] = -1.f;       // padding of the float4 scan below (magnitudes are >= 0)
                         __syncthreads();
                         for (int r0 = 0; r0 < k; r0 += 128) {
                             const int r = r0 + (tid & 127), half = tid >> 7;
                             if (r < k) {
                                 const float m = mags[r];
                                 int rk = 0;
-                                const int q0 = half ? (k + 1) / 2 : 0, q1 = half ? k : (k + 1) / 2;
-                                for (int q = q0; q < q1; ++q) { const float mq = mags[q]; rk += (mq > m) || (mq == m && q < r); }
+                                // kcap is a multiple of 4 and mags is 16-byte aligned: the half a thread scans starts at a multiple
+                                // of 4 and is read as float4 (entries >= k hold -1: never counted)
+                                const int q0 = half ? (((k + 1) / 2) & ~3) : 0, q1 = half ? k : (((k + 1) / 2) & ~3);
+                                for (int q = q0; q < q1; q += 4) {
+                                    const float4 mq = *reinterpret_cast<const float4*>(mags + q);
+                                    rk += (mq.x > m) || (mq.x == m && q < r);
+                                    rk += (mq.y > m) || (mq.y == m && q + 1 < r);
+                                    rk += (mq.z > m) || (mq.z == m && q + 2 < r);
+                                    rk += (mq.w > m) || (mq.w == m && q + 3 < r);
+                                }
                                 atomicAdd(&rank[r], rk);
                             }
                         }
                         __syncthreads();
                         // dropped rows fold into err (partials over row strides); kept rows move to tmp at their rank
                         {
-                            const int c = tid % Np2, p = tid / Np2;
+                            const int c = c_of_tid, p = p_of_tid;
                             if (c < N && p < parts) {
                                 float s = 0.f;
                                 for (int r = p; r < k; r += parts)
@@ -313,15 +384,34 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
                 float part = 0.f;
                 for (int r = warp; r < k; r += 8) {
                     float s = 0.f;
-                    for (int j = lane; j < K; j += 32) s = fmaf(aff[(size_t)r * W + j], __ldg(A + j), s);
+                    for (int j = lane; j < K; j += 32) s = fmaf(aff[(size_t)r * W + j], A[j], s);
                     s = warp_sum(s);
                     part += fabsf(s);
                 }
                 if (lane == 0) red[warp] = part;
+                if (hA != nullptr) {
+                    const float* hin = (((l - l0) & 1) ? hB : hA) + warp * W;
+                    float po = 0.f, pp = 0.f;
+                    if (lane < cg_lanes) {
+                        for (int j = lane; j < K; j += cg_lanes) {
+                            const float a = hin[j], w = A[j];
+                            po = fmaf(a, w, po);
+                            pp = fmaf(fabsf(a), fabsf(w), pp);
+                        }
+                    }
+                    for (int off = 1; off < cg_lanes; off <<= 1) {
+                        po += __shfl_xor_sync(0xffffffffu, po, off);
+                        pp += __shfl_xor_sync(0xffffffffu, pp, off);
+                    }
+                    const float bb = __ldg(bias);
+                    po += bb; pp += fabsf(bb);
+                    *pt_f = __shfl_sync(0xffffffffu, po, 0);
+                    *pt_scale = __shfl_sync(0xffffffffu, pp, 0);
+                }
                 if (warp == 0) {
                     float s = 0.f, sa = 0.f, se = 0.f;
                     for (int j = lane; j < K; j += 32) {
-                        const float w = __ldg(A + j);
+                        const float w = A[j];
                         s = fmaf(b_cur[j], w, s);
                         sa = fmaf(fabsf(b_cur[j]), fabsf(w), sa);
                         se = fmaf(e_cur[j], fabsf(w), se);
@@ -345,71 +435,6 @@ __device__ __forceinline__ void grow_forward(const NetDev& net, int l0, int l1, 
         }
     }
     st.aff = aff; st.tmp = tmp;        // a truncation swapped the two buffers
-}
-
-// f(x) of up to 8 points by the whole CTA (256 threads): warp p evaluates point p, whose activations live in row p of the
-// two ping-pong buffers hA / hB ([8][W] floats of shared memory, rows private to their warp).  Precondition: hA[p*W + 0..3] =
-// (x, y, z, 0) written and visible to warp p.  The arithmetic is that of the engine's point rows (niq_engine.cuh, reference
-// src/mlp.py:253-347): a hidden neuron accumulates fma(h_k, A_kc, acc) for ascending k from 0, then + bias, then the
-// activation; the final dot product is split over `cg_lanes` (= width class / 8) lanes -- lane cg takes k = cg, cg + CG, ...
-// -- and combined by an xor butterfly, like Engine::dot_layer.  Returns f and scale = sum_k |h_k w_k| + |b| of point `warp`
-// in every lane of that warp.
-__device__ __forceinline__ void cta_points8(const NetDev& net, int l0, int l1, const float* A0, const float* b0, int cg_lanes,
-                                            float* hA, float* hB, int W, float& f, float& scale) {
-    const int lane = threadIdx.x & 31, p = threadIdx.x >> 5;
-    float* hin = hA + p * W;
-    float* hout = hB + p * W;
-    f = 0.f; scale = 0.f;
-    for (int l = l0; l < l1; ++l) {
-        const LayerDev& L = net.layers[l];
-        const float* A = (l == l0 && A0 != nullptr) ? A0 : net.chunks[L.chunk_begin].src;
-        const float* bias = (l == l0 && b0 != nullptr) ? b0 : L.bias;
-        const int K = L.in_pad;
-        if (!L.last_of_net) {
-            const int N = L.out_pad;
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const float* wp = A + lane;
-#pragma unroll 4
-            for (int k = 0; k < K; ++k) {
-                const float a = hin[k];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (lane + 32 * i < N) acc[i] = fmaf(a, __ldg(wp + (size_t)k * N + 32 * i), acc[i]);
-            }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c = lane + 32 * i;
-                if (c < N) {
-                    float x = acc[i] + __ldg(bias + c);
-                    if (L.act == ACT_RELU) x = fmaxf(x, 0.f);
-                    else if (L.act == ACT_ELU) x = elu_pt(x);
-                    else if (L.act == ACT_SIN) x = sinf(x);
-                    hout[c] = x;
-                }
-            }
-            __syncwarp();
-            float* t2 = hin; hin = hout; hout = t2;
-        } else {
-            float out = 0.f, ps = 0.f;
-            if (lane < cg_lanes) {
-                for (int j = lane; j < K; j += cg_lanes) {
-                    const float a = hin[j], w = __ldg(A + j);
-                    out = fmaf(a, w, out);
-                    ps = fmaf(fabsf(a), fabsf(w), ps);
-                }
-            }
-            for (int off = 1; off < cg_lanes; off <<= 1) {
-                out += __shfl_xor_sync(0xffffffffu, out, off);
-                ps += __shfl_xor_sync(0xffffffffu, ps, off);
-            }
-            const float b = __ldg(bias);
-            out += b; ps += fabsf(b);
-            f = __shfl_sync(0xffffffffu, out, 0);
-            scale = __shfl_sync(0xffffffffu, ps, 0);
-            __syncwarp();
-        }
-    }
 }
 
 __global__ void __launch_bounds__(256, 1) k_classify_grow(const __grid_constant__ NetDev net, const GrowArgs g) {

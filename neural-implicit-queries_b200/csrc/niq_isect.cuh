@@ -6,7 +6,7 @@
 // the frontier of ALL queries lives in one device array (node -> query id; the nodes of a query stay contiguous and in the
 // reference's order because the compaction is an ordered scan), and a cooperative kernel runs the rounds:
 //   phase 1   work item = (node, shape): one CTA propagates the box through that shape's net (grow_forward) and evaluates
-//             the 7 sample points (cta_points8)
+//             the 7 sample points (the point rows of grow_forward)
 //   phase 2a  per node: the verdict logic (src/kd_tree.py:449-518); a query's first hit of the round is the lowest node index
 //             (atomicMax of a round-tagged key)
 //   phase 2b  nodes of queries that were hit are dropped; survivors are counted per tile of 2048 nodes
@@ -117,14 +117,12 @@ __global__ void __launch_bounds__(256) k_isect_persistent(const __grid_constant_
                 float c[3] = {cx, cy, cz};
                 if (k >= 1 && k <= 3) c[k - 1] = c[k - 1] + a.eps_w;
                 if (k >= 4 && k <= 6) c[k - 4] = c[k - 4] + a.eps_w * -1.f;
-                float* d = hA + k * a.W;
+                float* d = hA + k * g.W;                  // row stride = this net's W (grow_forward indexes hA + warp * W)
                 d[0] = c[0]; d[1] = c[1]; d[2] = c[2]; d[3] = 0.f;
             }
             __syncthreads();
-            float lo_b, up_b, sc;
-            grow_forward(net, 0, net.n_layers, A0, b0, g, st, 3, lo_b, up_b, sc);
-            float f, fs;
-            cta_points8(net, 0, net.n_layers, A0, b0, a.cg_lanes[s], hA, hB, a.W, f, fs);
+            float lo_b, up_b, sc, f, fs;
+            grow_forward(net, 0, net.n_layers, A0, b0, g, st, 3, lo_b, up_b, sc, hA, hB, a.cg_lanes[s], &f, &fs);
             if (lane == 0 && warp < 7) a.vals[((size_t)s * a.cap + node) * 7 + warp] = f;
             if (tid == 0) {
                 a.lab[(size_t)s * a.cap + node] = label_of(lo_b, up_b, 0.f);

@@ -1,6 +1,6 @@
 // niq_rays_grow.cuh -- cast_rays for the growing-form modes (affine_truncate / affine_all / affine_append) as one persistent
 // kernel (reference src/queries.py:39-175).  One CTA marches one ray from its root to termination -- the segment bound through
-// grow_forward (v = 1 general box = the ray segment, src/queries.py:55-58), f(start) and f(start + eps) through cta_points8
+// grow_forward (v = 1 general box = the ray segment, src/queries.py:55-58), f(start) and f(start + eps) through the point rows of grow_forward
 // (:67-70), the step update in the reference's operation order -- then takes the next ray from a global atomic queue.  No host
 // round trip per iteration, no bucket padding; N_evals is replayed by the host from the per-ray step counts like the fixed modes.
 #pragma once
@@ -68,17 +68,15 @@ __global__ void __launch_bounds__(256) k_cast_rays_grow(const __grid_constant__ 
                 }
                 if (tid >= 32 && tid < 40) {
                     const int k = tid - 32;
-                    float* d = hA + k * a.W;
+                    float* d = hA + k * g.W;                  // row stride = this net's W (grow_forward indexes hA + warp * W)
                     d[0] = k == 0 ? psx : k == 1 ? rx + te * dx : 0.f;
                     d[1] = k == 0 ? psy : k == 1 ? ry + te * dy : 0.f;
                     d[2] = k == 0 ? psz : k == 1 ? rz + te * dz : 0.f;
                     d[3] = 0.f;
                 }
                 __syncthreads();
-                float lo_b, up_b, sc;
-                grow_forward(net, l0, l1, nullptr, nullptr, g, st, 1, lo_b, up_b, sc);
-                float fv, fs;
-                cta_points8(net, l0, l1, nullptr, nullptr, a.cg_lanes[f], hA, hB, a.W, fv, fs);
+                float lo_b, up_b, sc, fv, fs;
+                grow_forward(net, l0, l1, nullptr, nullptr, g, st, 1, lo_b, up_b, sc, hA, hB, a.cg_lanes[f], &fv, &fs);
                 if (lane == 0 && warp < 2) { s_pt[warp] = fv; s_pt[2 + warp] = fs; }
                 __syncthreads();
                 const float v0 = s_pt[0], v1 = s_pt[1];

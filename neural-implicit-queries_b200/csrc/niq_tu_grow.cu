@@ -20,6 +20,7 @@ static int make_grow_cfg(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, 
              : g.n_append > 0 ? v + g.n_append * m->n_act_layers : v + m->sum_act_out;
     g.kcap = round_up(std::max(g.kcap, 4), 4);   // keeps the aff matrix 16-byte aligned behind mags/rank
     g.W = round_up(m->maxw_pad, 8);
+    for (const HostLayer& L : m->layers) g.wfloats = std::max(g.wfloats, round_up(L.in_pad * (L.dot ? 1 : L.out_pad), 4));
     if (grow_state_floats(g) * sizeof(float) > c->prop.sharedMemPerBlockOptin)
         return fail(NIQ_EUNSUPPORTED, "affine state of %zu bytes exceeds shared memory (%zu): network too wide/deep for this mode",
                     grow_state_floats(g) * sizeof(float), (size_t)c->prop.sharedMemPerBlockOptin);

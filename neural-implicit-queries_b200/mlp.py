@@ -112,6 +112,12 @@ def sin():
     return {"sin._": np.zeros((0,), np.float32)}
 
 
+def tanh():
+    """OURS, parity unpinned: the reference's README (:24) names TanH MLPs but src/mlp.py registers no tanh op.
+    Key "<i>.tanh._", point rule tanh(x), bound rules csrc/niq_engine.cuh tanh_lin."""
+    return {"tanh._": np.zeros((0,), np.float32)}
+
+
 def pow2_frequency_encode(count_pow2, start_pow=0, with_shift=True):
     """src/mlp.py:304-315: positional encoding coefficients 2^k * pi (and the pi shift that turns every second sin into a
     cos); followed by sin() in the reference's fitting script (src/main_fit_implicit.py:113-115)."""
@@ -135,7 +141,7 @@ def spatial_transformation():
 
 
 def quick_mlp_spec(layer_sizes, activation):
-    """src/mlp.py:73-94 (relu / elu only, as there)."""
+    """src/mlp.py:73-94 (relu / elu as there; 'tanh' is ours: see tanh())."""
     spec_list = []
     for i in range(len(layer_sizes) - 1):
         spec_list.append(dense(layer_sizes[i], layer_sizes[i + 1]))
@@ -144,6 +150,8 @@ def quick_mlp_spec(layer_sizes, activation):
                 spec_list.append(relu())
             elif activation == "elu":
                 spec_list.append(elu())
+            elif activation == "tanh":
+                spec_list.append(tanh())
             else:
                 raise ValueError("unrecognized activation")
     spec_list.append(squeeze_last())

@@ -198,6 +198,8 @@ def eval_points(params, x):
             h = _elu(h)
         elif name == "sin":
             h = np.sin(h)
+        elif name == "tanh":                       # OURS (parity unpinned): the reference has no tanh op, see _tanh_coeffs
+            h = np.tanh(h)
         elif name == "pow2_frequency_encode":
             h = _pow2_encode(h, args["coefs"], args.get("shift"), True)
         elif name == "squeeze_last":
@@ -397,6 +399,47 @@ def _sin_rule(ctx, base, aff, err):
     return _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta)
 
 
+TANH_SECANT_MIN_WIDTH = F32(1e-2)
+
+
+def _tanh_coeffs(base, aff, err):
+    """PARITY UNPINNED -- the reference registers no tanh rule (README.md:24 names TanH, the code has only
+    relu / elu / sin), so this restates nothing: it is the Chebyshev-style linearisation of the paper's construction, written
+    here and in csrc/niq_engine.cuh tanh_lin from the same formulas.  On [l, u]:
+      alpha = the secant slope (tanh u - tanh l) / (u - l)        (the minimax slope of a convex or concave piece); for
+              intervals narrower than 1e-2 the derivative at the midpoint 1 - tanh^2(mid) (the secant cancels in float32);
+      r(x)  = tanh(x) - alpha x attains its extrema over [l, u] at l, u or where tanh'(x) = alpha, x* = +-atanh(sqrt(1-alpha));
+      beta  = (r_max + r_min) / 2,  delta = r_max - beta.
+    Sound for ANY alpha in [0, 1] (the residual bounds are exact for the alpha actually used), tight for the secant."""
+    rad = _radius(aff, err)
+    lower, upper = (base - rad).astype(F32), (base + rad).astype(F32)
+    tl, tu = np.tanh(lower).astype(F32), np.tanh(upper).astype(F32)
+    width = (upper - lower).astype(F32)
+    tm = np.tanh((F32(0.5) * (lower + upper)).astype(F32)).astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        alpha = np.where(width > TANH_SECANT_MIN_WIDTH, (tu - tl) / width, F32(1) - tm * tm).astype(F32)
+        alpha = np.nan_to_num(alpha, nan=0.0).astype(F32)
+        alpha = np.clip(alpha, F32(0), F32(1))
+        zero = alpha == 0
+        rl = np.where(zero, tl, tl - alpha * lower).astype(F32)
+        ru = np.where(zero, tu, tu - alpha * upper).astype(F32)
+        r_lo, r_hi = np.minimum(rl, ru), np.maximum(rl, ru)
+        xs = np.arctanh(np.sqrt(np.maximum(F32(1) - alpha, F32(0)))).astype(F32)        # alpha = 0 -> inf: skipped below
+        for sgn in (F32(1), F32(-1)):
+            x = np.minimum(np.maximum(sgn * xs, lower), upper).astype(F32)              # clipped: an end point, already covered
+            v = (np.tanh(x).astype(F32) - alpha * x).astype(F32)
+            v = np.where(zero, rl, v)
+            r_lo, r_hi = np.minimum(r_lo, v), np.maximum(r_hi, v)
+    beta = (F32(0.5) * (r_hi + r_lo)).astype(F32)
+    delta = (r_hi - beta).astype(F32)
+    return alpha, beta, delta
+
+
+def _tanh_rule(ctx, base, aff, err):
+    alpha, beta, delta = _tanh_coeffs(base, aff, err)
+    return _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta)
+
+
 def _dense_rule(base, aff, err, A, b):
     """affine_layers.py:11-31 -- base@A+b, every aff row @A, err@|A|."""
     A = np.asarray(A, F32)
@@ -441,8 +484,8 @@ def affine_forward(params, ctx, center, vecs):
         elif name == "spatial_transformation":
             A, b = _spatial_as_dense(args["R"], args["t"])
             base, aff, err = _dense_rule(base, aff, err, A, b)
-        elif name in ("relu", "elu", "sin"):
-            base, aff, err = {"relu": _relu_rule, "elu": _elu_rule, "sin": _sin_rule}[name](ctx, base, aff, err)
+        elif name in ("relu", "elu", "sin", "tanh"):
+            base, aff, err = {"relu": _relu_rule, "elu": _elu_rule, "sin": _sin_rule, "tanh": _tanh_rule}[name](ctx, base, aff, err)
         elif name == "pow2_frequency_encode":                      # affine_layers.py:140-161
             base = _pow2_encode(base, args["coefs"], args.get("shift"), True)
             aff = _pow2_encode(aff, args["coefs"], None, False)
@@ -483,6 +526,12 @@ def _slope_activation(name, primal, sc, sw):
         dfl = np.where(pl > 0, F32(1), F32(0))
         dfu = np.where(pu < 0, F32(0), F32(1))
         new_primal = np.maximum(primal, F32(0))
+    elif name == "tanh":            # OURS (parity unpinned): tanh' = 1 - tanh^2 is largest nearest to 0, smallest farthest from it
+        far = np.tanh(np.maximum(np.abs(pl), np.abs(pu))).astype(F32)
+        near = np.tanh(np.minimum(np.abs(pl), np.abs(pu))).astype(F32)
+        dfl = (F32(1) - far * far).astype(F32)
+        dfu = np.where((pl <= 0) & (pu >= 0), F32(1), F32(1) - near * near).astype(F32)
+        new_primal = np.tanh(primal)
     else:
         with np.errstate(over="ignore"):
             dfl = np.minimum(np.exp(pl), F32(1))
@@ -520,7 +569,7 @@ def slope_forward(params, center, vecs):
             primal = primal.astype(F32)
             sc = np.matmul(sc, A).astype(F32)
             sw = np.matmul(sw, np.abs(A)).astype(F32)
-        elif name in ("relu", "elu", "sin"):
+        elif name in ("relu", "elu", "sin", "tanh"):
             primal, sc, sw = _slope_activation(name, primal, sc, sw)
         elif name == "pow2_frequency_encode":                      # slope_interval_layers.py:112-126
             primal = _pow2_encode(primal, args["coefs"], args.get("shift"), True)
@@ -617,6 +666,7 @@ def classify_box(params, ctx, lo, hi, offset=0.0, return_bounds=False, return_sc
 
 NEAR_TIE_REL = 1e-5
 NEAR_TIE_REL_ELU = 2e-4
+NEAR_TIE_REL_TANH = 1e-4   # nets with a tanh layer (ours, unpinned): the secant slope and atanh(sqrt(1 - alpha)) amplify 1-ulp differences of tanhf
 NEAR_TIE_REL_SIN = 5e-5    # nets with a sin layer: float32 vs float64 of the same formulas differ by up to 1.6e-5 (tests)
 
 
@@ -627,7 +677,11 @@ def tie_rel(params):
     1 ulp in exp/log/expm1 disagree by ~1e-7 ABSOLUTE per neuron, amplified by the following layers
     (tests/test_oracle_golden.py::test_elu_rule_conditioning measures it against float64)."""
     names = {nm for nm, _ in op_list(params)}
-    return NEAR_TIE_REL_ELU if "elu" in names else NEAR_TIE_REL_SIN if "sin" in names else NEAR_TIE_REL
+    if "elu" in names:
+        return NEAR_TIE_REL_ELU
+    if "tanh" in names:
+        return NEAR_TIE_REL_TANH
+    return NEAR_TIE_REL_SIN if "sin" in names else NEAR_TIE_REL
 
 
 def mode_rel(params, ctx):

@@ -145,3 +145,36 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "niq_oracle" not in src and "jaxshim" not in src, f"{f} references the oracle"
+
+
+def _header_struct_fields(name):
+    src = open(os.path.join(ROOT, "include", "niq.h")).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = re.findall(r"([A-Za-z_][A-Za-z0-9_]*)\s*(?:\[\d+\])?\s*(?:,|$)", decl.split(None, 1)[1] if " " in decl else decl)
+        fields += names
+    return fields
+
+
+def test_struct_mirrors_do_not_drift(built):
+    """include/niq.h, the ctypes mirrors in _niq.py and the reference-side stubs printed in INTEGRATION.md describe the same
+    structs (field names, order and -- for ctypes -- sizes): an array of niq_mode_cfg built from a stale stub would be read at
+    the wrong stride."""
+    import _niq
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for cname, mirror, stub in (("niq_mode_cfg", _niq.ModeCfg, "_Cfg"), ("niq_cast_opts", _niq.CastOpts, "_Opts"),
+                                ("niq_op_desc", _niq.OpDesc, "_Op"), ("niq_camera", _niq.Camera, "_Cam")):
+        hdr = _header_struct_fields(cname)
+        assert [f[0] for f in mirror._fields_] == hdr, (cname, hdr)
+        block = re.search(r"class %s\(C\.Structure\):.*?_fields_ = \[(.*?)\]\n" % stub, doc, flags=re.S).group(1)
+        assert re.findall(r'\("([a-z_A-Z0-9]+)"', block) == hdr, (stub, hdr)
+    assert ctypes.sizeof(_niq.ModeCfg) == 16 and ctypes.sizeof(_niq.CastOpts) == 32
+    # every op kind / mode of the header is known to the binding
+    src = open(os.path.join(ROOT, "include", "niq.h")).read()
+    assert len(re.findall(r"NIQ_OP_[A-Z0-9_]+ = \d", src)) == len(_niq._OP_KINDS)
+    assert len(re.findall(r"NIQ_MODE_[A-Z0-9_]+ = \d", src)) == len(_niq.MODE_IDS)

@@ -76,7 +76,9 @@ def test_intersection_persistent_kernel_equals_round_loop(monkeypatch, mode):
     import kd_tree
     g = golden("cfg3_isect_trunc64_list")
     fA, fB, pA, pB = _cfg3_pair(mode)
-    picks = [0, 1, 2, 3, 5, 8, 13, 21] if mode == "affine_truncate" else [0, 2, 5]
+    hit = np.nonzero(g["found"])[0]
+    miss = np.nonzero(~g["found"])[0]
+    picks = list(hit[:3]) + list(miss[:5]) if mode == "affine_truncate" else [hit[0], hit[1], miss[0], miss[1]]
     n_found = 0
     for i in picks:
         pB["0000.spatial_transformation.R"] = g["R"][i]
@@ -261,7 +263,12 @@ def test_strict_band_accounting(name):
                   mismatch_outside_band=int((mism & ~tie_wide).sum()))
     parity_report(f"strict_band_accounting[{name}]", **counts)
     assert counts["mismatch_outside_band"] == 0 and counts["values_beyond_band_wide"] == 0
-    if rel_wide == 1e-5 or name != "bunny":
-        # relu nets: the strict yardstick would change the verdict of at most a handful of boxes
-        assert counts["mismatch_outside_strict_1e5"] <= 2
-        assert counts["values_beyond_1e5_strict"] <= 0.002 * lo.shape[0]
+    if name != "bunny":
+        # relu-only nets meet north_star's literal tolerance: every bound within 1e-5 of |base| + rad, no label differs outside
+        # the strict band (measured: max error 1.2e-6 of the strict yardstick, 0 mismatches)
+        assert counts["mismatch_outside_strict_1e5"] == 0
+        assert counts["values_beyond_1e5_strict"] == 0
+    else:
+        # elu (bunny): the reference's float32 rule is itself conditioned to ~5e-5 (tests/test_oracle_golden.py::
+        # test_elu_rule_conditioning), hence the 2e-4 band on the wider yardstick; the counts at 1e-5 are reported beside it
+        assert counts["max_err_over_strict_scale"] < 5e-3

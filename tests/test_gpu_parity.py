@@ -553,8 +553,13 @@ def test_cast_rays_grow_kernel_equals_host_loop(monkeypatch, mode, n_trunc, n_su
             monkeypatch.delenv("NIQ_RAYS_HOST_LOOP", raising=False)
         res.append(queries.cast_rays(funcs, (pf, pb), roots, dirs, opts, return_near_tie=True))
     a, b = res
-    for x, y in zip(a, b):
+    for x, y in zip(a[:4], b[:4]):                 # t, hit_id, count, N_evals
         np.testing.assert_array_equal(x, y)
+    # near-tie flags: the kernel bands every func's bounds with the WIDEST tie_rel of the call (2e-4 here: bunny has elu), the
+    # host loop with each func's own -> the kernel flags a superset
+    assert not (b[4] & ~a[4]).any()
+    parity_report(f"cast_rays_grow_kernel_vs_host_loop[{mode}-{n_trunc}-{n_sub}]", rays=int(a[0].shape[0]), flagged_kernel=int(a[4].sum()),
+                  flagged_host_loop=int(b[4].sum()))
     assert (a[1] == 1).any() and (a[1] == 2).any() and (a[1] == 0).any()
 
 
@@ -954,7 +959,7 @@ def test_find_any_intersection_vs_oracle_list():
     pA = sample_params("hammer")
     pB = mlp.prepend_op(sample_params("bunny"), mlp.spatial_transformation())
     fA, fB = make(pA, "affine_fixed"), make(pB, "affine_fixed")
-    n_found = n_flag = n_bad = 0
+    n_found = n_flag = n_bad = n_diff = n_nodes = n_tie = 0
     for i in range(12):
         th = rng.uniform(0, 2 * np.pi)
         R = np.array([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], np.float32)
@@ -965,16 +970,20 @@ def test_find_any_intersection_vs_oracle_list():
         st, ost = {}, {}
         found, _, _, loc = kd_tree.find_any_intersection((fA, fB), (pA, pB), LO, HI, 1e-3, stats=st)
         ofound, _, _, oloc = otree.find_any_intersection((octx("affine_fixed"),) * 2, (pA, opB), LO, HI, 1e-3, stats=ost)
-        if st["n_near_tie"] == 0 and ost["n_near_tie"] == 0:
-            assert bool(found) == bool(ofound)
-            assert st["n_nodes"] == ost["n_nodes"] and st["n_rounds"] == ost["n_rounds"]
-            np.testing.assert_allclose(loc, oloc, rtol=0, atol=1e-6)
-        else:
-            n_flag += 1
-            n_bad += bool(found) != bool(ofound)
+        same = (bool(found) == bool(ofound) and st["n_nodes"] == ost["n_nodes"] and st["n_rounds"] == ost["n_rounds"]
+                and np.allclose(loc, oloc, rtol=0, atol=1e-6))
+        flagged = st["n_near_tie"] > 0 or ost["n_near_tie"] > 0
+        assert same or flagged, f"transform {i}: differs with no near-tie box on either side"
+        n_flag += flagged
+        n_diff += not same
+        n_bad += bool(found) != bool(ofound)
+        n_nodes += ost["n_nodes"]
+        n_tie += max(st["n_near_tie"], ost["n_near_tie"])
         n_found += bool(found)
-    parity_report("find_any_intersection_vs_oracle_list", queries=12, flagged=n_flag, flagged_verdict_mismatch=n_bad)
-    assert n_flag <= 6 and n_bad == 0
+    parity_report("find_any_intersection_vs_oracle_list", queries=12, nodes=n_nodes, near_tie_boxes=n_tie, queries_flagged=n_flag,
+                  flagged_differing=n_diff, verdict_mismatch=n_bad)
+    # every query is compared; a difference is tolerated only where a box sat inside the band, and those boxes stay rare
+    assert n_tie <= 0.01 * n_nodes and n_bad == 0 and n_diff <= 2
     assert 0 < n_found < 12
 
 
@@ -1336,3 +1345,52 @@ def test_cast_rays_frustum_non_square_two_fov_golden():
         np.testing.assert_allclose(t[ok], g["out_t"][ok], rtol=RTOL, atol=0)
         if not tie.any():
             assert n_evals == int(g["n_evals"])
+
+
+# ---------------------------------------------------------------------------------------------------
+# the C ABI from plain C (no Python struct mirrors in between)
+# ---------------------------------------------------------------------------------------------------
+
+def test_c_abi_program(tmp_path):
+    """tests/abi_c_test.c includes include/niq.h, links libniq.so, builds the fox MLP from a raw weight blob and runs
+    niq_classify_boxes + niq_cast_rays; its printed results equal the ctypes binding's bit for bit."""
+    import os
+    import struct
+    import subprocess
+    import queries
+    import render
+    from conftest import PKG, ROOT
+    p = sample_params("fox")
+    dense = sorted(k for k in p if k.endswith(".dense.A"))
+    lo, hi = random_boxes(21, 40)
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=12, fov_deg=30.)
+    blob = tmp_path / "fox.blob"
+    with open(blob, "wb") as f:
+        f.write(struct.pack("<i", len(dense)))
+        for k in dense:
+            A = np.ascontiguousarray(p[k], np.float32)
+            b = np.ascontiguousarray(p[k.replace(".A", ".b")], np.float32)
+            f.write(struct.pack("<ii", *A.shape)); f.write(A.tobytes()); f.write(b.tobytes())
+        f.write(struct.pack("<i", lo.shape[0])); f.write(lo.tobytes()); f.write(hi.tobytes())
+        f.write(struct.pack("<i", roots.shape[0])); f.write(roots.tobytes()); f.write(dirs.tobytes())
+    exe = tmp_path / "abi_c_test"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "abi_c_test.c"),
+                    "-L", PKG, "-lniq", f"-Wl,-rpath,{PKG}", "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe), str(blob)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.strip().splitlines()
+    assert lines[-1] == "ok" and lines[-2].startswith("einval ")
+    func = make(p, "affine_fixed")
+    lab, blo, bup, tie = func.bound_box(p, lo, hi)
+    t, hit, cnt, n_evals = queries.cast_rays((func,), (p,), roots, dirs, queries.get_default_cast_opts())
+    boxes = [ln.split() for ln in lines if ln.startswith("box ")]
+    rays_ = [ln.split() for ln in lines if ln.startswith("ray ")]
+    assert len(boxes) == lo.shape[0] and len(rays_) == roots.shape[0]
+    for i, b in enumerate(boxes):
+        assert int(b[2]) == lab[i] and int(b[3], 16) == blo[i:i + 1].view(np.uint32)[0] and int(b[4], 16) == bup[i:i + 1].view(np.uint32)[0]
+        assert int(b[5]) == int(tie[i])
+    for i, r in enumerate(rays_):
+        assert int(r[2], 16) == t[i:i + 1].view(np.uint32)[0] and int(r[3]) == hit[i] and int(r[4]) == cnt[i]
+    assert int([ln for ln in lines if ln.startswith("n_evals ")][0].split()[1]) == n_evals

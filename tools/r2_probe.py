@@ -86,6 +86,48 @@ def main():
     st = {}
     ms, r = timed(lambda: kd_tree.find_any_intersection((s[0], s[1]), (s[2], s[3]), LO, HI, 1e-3, stats=st))
     out["isect_trunc64_disjoint"] = {"ms": ms, "found": bool(r[0]), **st}
+    # the same query through the per-round host loop, and the 64 config-3 transforms: one by one and as ONE batch
+    os.environ["NIQ_ISECT_LEGACY"] = "1"
+    st = {}
+    ms, r = timed(lambda: kd_tree.find_any_intersection((s[0], s[1]), (s[2], s[3]), LO, HI, 1e-3, stats=st))
+    out["isect_trunc64_disjoint_round_loop"] = {"ms": ms, "found": bool(r[0]), **st}
+    os.environ["NIQ_ISECT_LEGACY"] = "0"
+    g = np.load(os.path.join(ROOT, "tests", "golden", "cfg3_isect_trunc64_list.npz"))
+    def singles():
+        n = 0
+        for i in range(64):
+            s[3]["0000.spatial_transformation.R"], s[3]["0000.spatial_transformation.t"] = g["R"][i], g["t"][i]
+            n += bool(kd_tree.find_any_intersection((s[0], s[1]), (s[2], s[3]), LO, HI, 1e-3)[0])
+        return n
+    ms, nf = timed(singles, reps=2)
+    out["cfg3_64_single_queries"] = {"ms": ms, "found": nf, "queries_per_s": 64 / ms * 1e3}
+    for reps in (1, 4, 16):
+        R, t = np.tile(g["R"], (reps, 1, 1)), np.tile(g["t"], (reps, 1))
+        st = {}
+        ms, r = timed(lambda: kd_tree.find_any_intersection_batch((s[0], s[1]), (s[2], s[3]), LO, HI, 1e-3, R_B=R, t_B=t, stats=st), reps=2)
+        out[f"cfg3_batch_{64 * reps}"] = {"ms": ms, "found": int(r[0].sum()), "queries_per_s": 64 * reps / ms * 1e3, "nodes": int(st["n_nodes"].sum()),
+                                          "nodes_per_s": int(st["n_nodes"].sum()) / ms * 1e3}
+    # cast_rays in a growing-form mode: persistent kernel vs host-level loop (fox, 128 x 128)
+    import queries
+    import render
+    pf = sample("fox")
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, _ = render.look_at(eye)
+    roots, dirs = render.generate_camera_rays(eye, look, up, res=128, fov_deg=30.)
+    for mode, kw in (("affine_truncate", dict(affine_n_truncate=8, affine_truncate_policy="absolute")), ("affine_all", {})):
+        f = implicit_mlp_utils.generate_implicit_from_params(pf, mode, **kw)
+        for host in ("", "1"):
+            if host:
+                os.environ["NIQ_RAYS_HOST_LOOP"] = "1"
+            else:
+                os.environ.pop("NIQ_RAYS_HOST_LOOP", None)
+            ms, r = timed(lambda: queries.cast_rays((f,), (pf,), roots, dirs, queries.get_default_cast_opts()), reps=2)
+            out[f"cast_rays_fox128_{mode}_{'host_loop' if host else 'persistent'}"] = {"ms": ms, "ray_steps": int(r[2].sum()), "ray_steps_per_s": int(r[2].sum()) / ms * 1e3}
+    os.environ.pop("NIQ_RAYS_HOST_LOOP", None)
+    # marching cubes (bank-skewed point tiles)
+    fb = implicit_mlp_utils.generate_implicit_from_params(bunny, "affine_fixed")
+    ms, tri = timed(lambda: kd_tree.hierarchical_marching_cubes(fb, bunny, LO, HI, 9, n_subcell_depth=3), reps=2)
+    out["hmc_bunny_d9"] = {"ms": ms, "triangles": int(tri.shape[0])}
     print(json.dumps(out, indent=1))
 
 
