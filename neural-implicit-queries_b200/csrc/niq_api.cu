@@ -723,8 +723,9 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
         if (cfgs[f].mode != cfgs[0].mode) return fail(NIQ_EUNSUPPORTED, "all funcs of one cast_rays_frustum call must use the same mode");
     }
     const bool slope = cfgs[0].mode == NIQ_MODE_SLOPE_INTERVAL;
-    if (!is_fixed_mode(&cfgs[0]) && !slope)
-        return fail(NIQ_EUNSUPPORTED, "cast_rays_frustum in this mode runs through the host-level loop of the Python layer");
+    const bool grow = cfgs[0].mode == NIQ_MODE_AFFINE_TRUNCATE || cfgs[0].mode == NIQ_MODE_AFFINE_ALL || cfgs[0].mode == NIQ_MODE_AFFINE_APPEND;
+    if (!is_fixed_mode(&cfgs[0]) && !slope && !grow)
+        return fail(NIQ_EUNSUPPORTED, "cast_rays_frustum in sdf mode runs through the host-level loop of the Python layer");
     const long long n = (long long)cam->res_x * cam->res_y;
     if (n_init > n) return fail(NIQ_EINVAL, "niq_cast_rays_frustum: more initial frusta than pixels");
     if (n_evals) *n_evals = 0;
@@ -777,7 +778,8 @@ extern "C" int niq_cast_rays_frustum(niq_ctx* c, int32_t n_funcs, const niq_mlp*
         CU(cudaGetLastError());
     }
     const int interval = cfgs[0].mode == NIQ_MODE_INTERVAL;
-    TRY(launch_cast_frustum(c, wmax, net, total_floats, co, fc, interval, q, n, slope));
+    if (grow) TRY(launch_cast_frustum_grow(c, n_funcs, mlps, cfgs, net, co, fc, q, n));
+    else TRY(launch_cast_frustum(c, wmax, net, total_floats, co, fc, interval, q, n, slope));
     {
         LaunchTimer lt(c, 1);
         const int blocks = (int)std::min<long long>((n + 7) / 8, 8ll * c->prop.multiProcessorCount);

@@ -198,3 +198,5 @@ int isect_grow_batch(niq_ctx* c, const niq_mlp* mA, const niq_mode_cfg* cfgA, co
 int launch_cast_rays_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs, const NetDev& net,
                           const CastOpts& o, long long n, const float* roots, const float* dirs, float* t, int* hit, int* cnt,
                           unsigned char* tie, unsigned long long* queue);
+int launch_cast_frustum_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs, const NetDev& net,
+                             const CastOpts& o, const FrustCam& cam, const FrustQueue& q, long long n_pixels);

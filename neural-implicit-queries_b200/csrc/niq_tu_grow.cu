@@ -4,6 +4,7 @@
 
 #include "niq_isect.cuh"
 #include "niq_rays_grow.cuh"
+#include "niq_frustum_grow.cuh"
 
 // mode -> sizes of the growing-form state (kcap rows of W floats); v = box vectors of the input form
 static int make_grow_cfg(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, int v, GrowCfg* out) {
@@ -201,6 +202,37 @@ int launch_cast_rays_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, c
     nd.exec_macs = nullptr;
     LaunchTimer lt(c, 0);
     k_cast_rays_grow<<<grid, 256, smem, c->stream>>>(nd, a);
+    CU(cudaGetLastError());
+    return NIQ_OK;
+}
+
+// cast_rays_frustum in a growing-form mode: one persistent kernel, one CTA per frustum in flight (niq_frustum_grow.cuh)
+int launch_cast_frustum_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs, const NetDev& net,
+                             const CastOpts& o, const FrustCam& cam, const FrustQueue& q, long long n_pixels) {
+    if (n_funcs > 4) return fail(NIQ_EUNSUPPORTED, "cast_rays_frustum in a growing-form mode supports up to 4 funcs");
+    FrustGrowArgs a{};
+    a.o = o; a.q = q; a.n_funcs = n_funcs;
+    size_t state = 0;
+    for (int f = 0; f < n_funcs; ++f) {
+        if (!is_grow_mode(&cfgs[f])) return fail(NIQ_EINVAL, "launch_cast_frustum_grow: func %d is not in a growing-form mode", f);
+        TRY(make_grow_cfg(c, mlps[f], &cfgs[f], 3, &a.g[f]));
+        a.cg_lanes[f] = mlps[f]->wmax / 8;
+        a.W = std::max(a.W, a.g[f].W);
+        state = std::max(state, grow_state_floats(a.g[f]));
+    }
+    a.state_floats = (long long)((state + 3) / 4 * 4);
+    const size_t smem = ((size_t)a.state_floats + 16 * (size_t)a.W) * sizeof(float);
+    if (smem > c->prop.sharedMemPerBlockOptin) return fail(NIQ_EUNSUPPORTED, "frustum state of %zu bytes exceeds shared memory", smem);
+    TRY(set_smem(k_cast_frustum_grow, smem));
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_cast_frustum_grow, 256, smem);
+    per_sm = std::max(per_sm, 1);
+    // idle CTAs poll the queue: never more CTAs than frusta can exist, all of them co-resident (a waiting CTA must not starve a queued one)
+    const int grid = (int)std::min<long long>(n_pixels, (long long)c->prop.multiProcessorCount * per_sm);
+    NetDev nd = net;
+    nd.exec_macs = nullptr;
+    LaunchTimer lt(c, 0);
+    k_cast_frustum_grow<<<grid, 256, smem, c->stream>>>(nd, cam, a);
     CU(cudaGetLastError());
     return NIQ_OK;
 }

@@ -239,7 +239,8 @@ def cast_rays_frustum(funcs_tuple, params_tuple, cam_params, in_opts, return_nea
         init_ranges = _initial_frusta(res_x, res_y, n_side)
     init_ranges = np.ascontiguousarray(init_ranges, np.int32).reshape(-1, 4)
     modes = {f.ctx.mode for f in funcs_tuple}
-    impl = _cast_rays_frustum_persistent if len(modes) == 1 and modes <= {"interval", "affine_fixed", "slope_interval"} else _cast_rays_frustum_host_loop
+    persistent = len(modes) == 1 and modes <= _PERSISTENT_RAY_MODES and not os.environ.get("NIQ_RAYS_HOST_LOOP")
+    impl = _cast_rays_frustum_persistent if persistent else _cast_rays_frustum_host_loop
     return impl(ctx, funcs_tuple, params_tuple, cam_params, in_opts, return_near_tie, init_ranges, iter_counts)
 
 

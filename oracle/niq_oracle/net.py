@@ -399,39 +399,56 @@ def _sin_rule(ctx, base, aff, err):
     return _apply_linear_approx(ctx, base, aff, err, alpha, beta, delta)
 
 
-TANH_SECANT_MIN_WIDTH = F32(1e-2)
-
-
-def _tanh_coeffs(base, aff, err):
+def _tanh_coeffs(base, aff, err, dtype=F32):
     """PARITY UNPINNED -- the reference registers no tanh rule (README.md:24 names TanH, the code has only
     relu / elu / sin), so this restates nothing: it is the Chebyshev-style linearisation of the paper's construction, written
-    here and in csrc/niq_engine.cuh tanh_lin from the same formulas.  On [l, u]:
-      alpha = the secant slope (tanh u - tanh l) / (u - l)        (the minimax slope of a convex or concave piece); for
-              intervals narrower than 1e-2 the derivative at the midpoint 1 - tanh^2(mid) (the secant cancels in float32);
+    here and in csrc/niq_engine.cuh tanh_lin from the same formulas.  On [l, u], w = u - l:
+      alpha = the secant slope (tanh u - tanh l) / w (the minimax slope of a convex or concave piece), evaluated WITHOUT the
+              cancelling difference through tanh u - tanh l = (1 - tanh u tanh l) tanh(u - l):
+              alpha = (1 - tanh u tanh l) * g(w),  g(w) = tanh(w) / w  (1 - w^2/3 below w = 1e-3);
       r(x)  = tanh(x) - alpha x attains its extrema over [l, u] at l, u or where tanh'(x) = alpha, x* = +-atanh(sqrt(1-alpha));
-      beta  = (r_max + r_min) / 2,  delta = r_max - beta.
+      beta  = (r_max + r_min) / 2,  delta = (r_max - r_min) / 2, both formed from d(x) = r(x) - r(l) (see below).
     Sound for ANY alpha in [0, 1] (the residual bounds are exact for the alpha actually used), tight for the secant."""
-    rad = _radius(aff, err)
-    lower, upper = (base - rad).astype(F32), (base + rad).astype(F32)
-    tl, tu = np.tanh(lower).astype(F32), np.tanh(upper).astype(F32)
-    width = (upper - lower).astype(F32)
-    tm = np.tanh((F32(0.5) * (lower + upper)).astype(F32)).astype(F32)
+    one = dtype(1)
+    rad = _radius(aff, err) if dtype is F32 else np.abs(aff).sum(axis=1) + err
+    lower, upper = (base - rad).astype(dtype), (base + rad).astype(dtype)
+    tl, tu = np.tanh(lower).astype(dtype), np.tanh(upper).astype(dtype)
+    width = (upper - lower).astype(dtype)
     with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-        alpha = np.where(width > TANH_SECANT_MIN_WIDTH, (tu - tl) / width, F32(1) - tm * tm).astype(F32)
-        alpha = np.nan_to_num(alpha, nan=0.0).astype(F32)
-        alpha = np.clip(alpha, F32(0), F32(1))
+        g = np.where(width < dtype(1e-3), one - width * width / dtype(3), np.tanh(width) / width).astype(dtype)
+        alpha = ((one - tu * tl) * g).astype(dtype)
+        alpha = np.nan_to_num(alpha, nan=0.0).astype(dtype)
+        alpha = np.clip(alpha, dtype(0), one)
         zero = alpha == 0
-        rl = np.where(zero, tl, tl - alpha * lower).astype(F32)
-        ru = np.where(zero, tu, tu - alpha * upper).astype(F32)
-        r_lo, r_hi = np.minimum(rl, ru), np.maximum(rl, ru)
-        xs = np.arctanh(np.sqrt(np.maximum(F32(1) - alpha, F32(0)))).astype(F32)        # alpha = 0 -> inf: skipped below
-        for sgn in (F32(1), F32(-1)):
-            x = np.minimum(np.maximum(sgn * xs, lower), upper).astype(F32)              # clipped: an end point, already covered
-            v = (np.tanh(x).astype(F32) - alpha * x).astype(F32)
-            v = np.where(zero, rl, v)
-            r_lo, r_hi = np.minimum(r_lo, v), np.maximum(r_hi, v)
-    beta = (F32(0.5) * (r_hi + r_lo)).astype(F32)
-    delta = (r_hi - beta).astype(F32)
+        # residual r(x) = tanh(x) - alpha x RELATIVE to its value at l: d(x) = (tanh x - tanh l) - alpha (x - l), with the tanh
+        # difference again in product form -- the cancellation then costs ~1 ulp of w, not of |tanh l| (delta of a narrow
+        # interval is O(w^3): formed from r(x) directly it would drown in the rounding noise of r, which the following
+        # layers amplify like any other error term)
+        def d_of(x):
+            dx = (x - lower).astype(dtype)
+            return ((one - np.tanh(x).astype(dtype) * tl) * np.tanh(dx).astype(dtype) - alpha * dx).astype(dtype)
+        du = np.where(zero, tu - tl, d_of(upper)).astype(dtype)
+        d_lo, d_hi = np.minimum(du, dtype(0)), np.maximum(du, dtype(0))
+        xs = np.arctanh(np.sqrt(np.maximum(one - alpha, dtype(0)))).astype(dtype)           # alpha = 0 -> inf: skipped below
+        for sgn in (one, dtype(-1)):
+            x = np.minimum(np.maximum(sgn * xs, lower), upper).astype(dtype)                # clipped: an end point, already covered
+            v = np.where(zero, dtype(0), d_of(x)).astype(dtype)
+            d_lo, d_hi = np.minimum(d_lo, v), np.maximum(d_hi, v)
+        rl = np.where(zero, tl, tl - alpha * lower).astype(dtype)                           # r(l)
+        # narrow intervals (w < 1e-2): the true half-range is O(w^2 |f''|) and even d(x) cannot resolve it in float32; there the
+        # residual is bounded by the secant-error theorem instead, |f(x) - secant(x)| <= max|f''| w^2 / 8, one-sided where f'' keeps
+        # its sign (tanh is convex below 0, concave above).  f'' = -2 t (1 - t^2), |f''| <= 4 / (3 sqrt 3) with equality at t^2 = 1/3
+        t_hi = np.maximum(np.abs(tl), np.abs(tu))
+        t_lo = np.where((lower <= 0) & (upper >= 0), dtype(0), np.minimum(np.abs(tl), np.abs(tu)))
+        f2 = lambda t: (dtype(2) * t * (one - t * t)).astype(dtype)
+        peak = dtype(0.5773502691896258)
+        M = np.where((t_lo <= peak) & (t_hi >= peak), dtype(0.7698003589195010), np.maximum(f2(t_lo), f2(t_hi))).astype(dtype)
+        bnd = (M * width * width / dtype(8)).astype(dtype)
+        narrow = (width < dtype(1e-2)) & ~zero
+        d_hi = np.where(narrow, np.where(lower >= 0, bnd, np.where(upper <= 0, dtype(0), bnd)), d_hi).astype(dtype)
+        d_lo = np.where(narrow, np.where(lower >= 0, dtype(0), np.where(upper <= 0, -bnd, -bnd)), d_lo).astype(dtype)
+    beta = (rl + dtype(0.5) * (d_hi + d_lo)).astype(dtype)
+    delta = (dtype(0.5) * (d_hi - d_lo)).astype(dtype)
     return alpha, beta, delta
 
 

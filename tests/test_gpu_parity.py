@@ -1212,6 +1212,34 @@ def test_cast_rays_frustum_vs_oracle(name, mode, res, n_side, n_sub):
         assert n_evals == on
 
 
+@pytest.mark.parametrize("mode,n_trunc,n_sub", [("affine_truncate", 8, 2), ("affine_all", 8, 1), ("affine_append", 4, 1)])
+def test_cast_rays_frustum_grow_kernel_equals_host_loop(monkeypatch, mode, n_trunc, n_sub):
+    """The persistent frustum kernel of the growing-form modes (csrc/niq_frustum_grow.cuh: one CTA per frustum, device work
+    queue) against the host-level iteration it replaces (NIQ_RAYS_HOST_LOOP=1): images, N_evals identical; two funcs."""
+    import queries
+    import render
+    pf, pb = sample_params("fox"), sample_params("bunny")
+    funcs = (make(pf, mode, n_trunc), make(pb, mode, n_trunc))
+    eye = np.array((2., 1., 2.), np.float32)
+    look, up, left = render.look_at(eye)
+    opts = queries.get_default_cast_opts()
+    opts["n_side_init"] = 4
+    opts["n_substeps"] = n_sub
+    cam = (eye, look, up, left, 30.0, 30.0, 24, 20)
+    res = []
+    for host in ("", "1"):
+        if host:
+            monkeypatch.setenv("NIQ_RAYS_HOST_LOOP", host)
+        else:
+            monkeypatch.delenv("NIQ_RAYS_HOST_LOOP", raising=False)
+        res.append(queries.cast_rays_frustum(funcs, (pf, pb), cam, opts, return_near_tie=True))
+    a, b = res
+    for x, y in zip(a[:4], b[:4]):                 # t, hit_id, count images, N_evals
+        np.testing.assert_array_equal(x, y)
+    assert not (b[4] & ~a[4]).any()                # the kernel bands with the widest tie_rel of the call: a superset
+    assert (a[1] != 0).any() and (a[1] == 0).any()
+
+
 def test_cast_rays_frustum_wide_streamed_and_render():
     """A 256-wide net (weights streamed through the ring: every warp of a CTA leaves together) against the oracle, the
     frustum branch of render.render_image, and argument errors."""

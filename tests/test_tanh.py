@@ -91,10 +91,11 @@ def test_gpu_tanh_classify_vs_oracle_and_sound(mode, width, depth):
                   near_tie=int(otie.sum()), label_mismatch=int(mism.sum()), mismatch_outside_band=int((mism & ~otie).sum()))
     assert err.max() <= rel and not (mism & ~otie).any()
     assert sound(p, lo[:150], hi[:150], lower[:150], upper[:150]) == 0
-    # point values
+    # point values: within 1e-5 of the magnitude the last dot product was summed from
     import mlp
     x = np.random.default_rng(1).uniform(-1, 1, (2000, 3)).astype(np.float32)
-    np.testing.assert_allclose(mlp.eval_points(p, x), net.eval_points(p, x), rtol=0, atol=2e-6)
+    fv, fsc = mlp.eval_points(p, x, return_scale=True)
+    assert np.all(np.abs(fv - net.eval_points(p, x)) <= 1e-5 * fsc)
 
 
 @pytest.mark.gpu
@@ -106,7 +107,10 @@ def test_gpu_tanh_queries_vs_oracle():
     import render
     from conftest import parity_report
     from niq_oracle import tree as otree
-    p = tanh_net(32, 3, seed=4)
+    p = tanh_net(32, 3, seed=5, gain=2.0)
+    xs = np.random.default_rng(0).uniform(-1, 1, (20000, 3)).astype(np.float32)
+    last = sorted(k for k in p if k.endswith("dense.b"))[-1]
+    p[last] = (p[last] - np.float32(np.median(net.eval_points(p, xs)))).astype(np.float32)     # the level set crosses the domain
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
     eye = np.array((2., 1., 2.), np.float32)
     look, up, _ = render.look_at(eye)
@@ -115,11 +119,17 @@ def test_gpu_tanh_queries_vs_oracle():
     t, hit, cnt, n_ev, tie = queries.cast_rays((f,), (p,), roots, dirs, opts, return_near_tie=True)
     ot, ohit, ocnt, on_ev, otie = rays.cast_rays((octx("affine_fixed"),), (p,), roots, dirs, opts, return_near_tie=True)
     ok = ~(tie | otie)
-    parity_report("tanh_cast_rays (unpinned)", rays=int(t.shape[0]), flagged=int((~ok).sum()), hits=int((ohit > 0).sum()))
-    assert ok.mean() > 0.9
+    both = (hit > 0) & (ohit > 0)
+    parity_report("tanh_cast_rays (unpinned)", rays=int(t.shape[0]), flagged=int((~ok).sum()), hits=int((ohit > 0).sum()),
+                  hit_flag_mismatch=int((hit != ohit).sum()), count_mismatch=int((cnt != ocnt).sum()),
+                  max_t_diff_on_hits=float(np.abs(t - ot)[both].max()) if both.any() else 0.0)
+    # rays whose every decision was outside the band: exact; all rays (a ray that comes to rest ON the surface is always
+    # inside the band of the 1e-4 tanh yardstick): hit flags and depths agree to the hit tolerance of the march
     np.testing.assert_array_equal(hit[ok], ohit[ok])
     np.testing.assert_array_equal(cnt[ok], ocnt[ok])
     np.testing.assert_allclose(t[ok], ot[ok], rtol=1e-5, atol=0)
+    assert (hit != ohit).mean() <= 0.02 and (ohit > 0).any() and (ohit == 0).any()
+    assert np.all(np.abs(t - ot)[both] <= 2 * opts["hit_eps"])
     st, ost = {}, {}
     out = kd_tree.construct_uniform_unknown_levelset_tree(f, p, LO, HI, split_depth=12, stats=st)
     ref = otree.construct_uniform_unknown_levelset_tree(octx("affine_fixed"), p, LO, HI, split_depth=12, stats=ost)
