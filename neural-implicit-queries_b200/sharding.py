@@ -156,6 +156,14 @@ def cast_rays_frustum_sharded(funcs_tuple, params_tuple, cam_params, opts, cast_
     return np.ascontiguousarray(t), np.ascontiguousarray(hit), np.ascontiguousarray(cnt), n_evals
 
 
+def default_top_depth(split_depth, world):
+    """Levels built replicated before the frontier is dealt.  A level of a few thousand boxes costs every GPU the latency of
+    ONE pass through the net whether it holds all of them or an eighth (the top of the tree is latency-bound), so replicating
+    down to depth 12 (<= 4,096 boxes) is free and leaves each rank hundreds of boxes: the round-robin deal then balances the
+    subtrees statistically instead of box by box."""
+    return min(split_depth, max(12, int(np.ceil(np.log2(max(8 * world, 2)))) + 3))
+
+
 def deal_boxes(n_boxes, rank, world):
     """Indices of the frontier boxes (top-of-tree leaves) owned by `rank`: round-robin."""
     return np.arange(rank, n_boxes, world, dtype=np.int64)
@@ -185,7 +193,7 @@ def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_
 def _top_frontier(func, params, lower, upper, split_depth, top_depth, world, kw):
     import kd_tree
     if top_depth is None:
-        top_depth = min(split_depth, int(np.ceil(np.log2(max(8 * world, 2)))) + 3)
+        top_depth = default_top_depth(split_depth, world)
     top = kd_tree.construct_uniform_unknown_levelset_tree(func, params, lower, upper, split_depth=top_depth, **kw)
     v = top['unknown_node_valid']
     return top['unknown_node_lower'][v], top['unknown_node_upper'][v], top_depth
@@ -241,7 +249,7 @@ def _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, ra
         import kd_tree
         build_fn = kd_tree.construct_uniform_unknown_levelset_tree
     if top_depth is None:
-        top_depth = min(split_depth, int(np.ceil(np.log2(max(8 * world, 2)))) + 3)
+        top_depth = default_top_depth(split_depth, world)
     top = build_fn(func, params, lower, upper, split_depth=top_depth, **kw)
     v = top['unknown_node_valid']
     flo, fhi = top['unknown_node_lower'][v], top['unknown_node_upper'][v]
@@ -362,3 +370,30 @@ def find_any_intersection_batch_sharded(func_tuple, params_of, n_queries, lower,
     order = np.argsort(rows[:, 0], kind="stable")
     rows = rows[order]
     return rows[:, 1] > 0.5, rows[:, 2:].copy()
+
+
+def find_any_intersection_transforms_sharded(func_tuple, params_tuple, lower, upper, eps, R_B=None, t_B=None, R_A=None, t_A=None,
+                                             batch_fn=None, group=None):
+    """kd_tree.find_any_intersection_batch with the queries (one per rigid transform) cut into contiguous ranges, one range per
+    rank: every rank runs ITS queries in one persistent kernel, one gather of (found, loc) = 16 B/query returns everything to
+    every rank.  -> (found (n,) bool, loc (n,3))."""
+    import torch
+    import torch.distributed as dist
+    if batch_fn is None:
+        import kd_tree
+        batch_fn = kd_tree.find_any_intersection_batch
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = (R_B if R_B is not None else R_A).shape[0]
+    bounds = np.linspace(0, n, world + 1).astype(np.int64)
+    a, b = int(bounds[rank]), int(bounds[rank + 1])
+    cut = lambda x: None if x is None else np.ascontiguousarray(x[a:b])
+    if b > a:
+        found, loc = batch_fn(func_tuple, params_tuple, lower, upper, eps, R_B=cut(R_B), t_B=cut(t_B), R_A=cut(R_A), t_A=cut(t_A))
+    else:
+        found, loc = np.zeros(0, bool), np.zeros((0, 3), np.float32)
+    if world == 1:
+        return found, loc
+    rows = np.concatenate((found.astype(np.float32)[:, None], np.asarray(loc, np.float32)), axis=1)
+    allr = np.concatenate(_gather_rows(rows, world, rank, group, 4, torch.float32))
+    return allr[:, 0] > 0.5, allr[:, 1:].copy()

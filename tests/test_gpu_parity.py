@@ -668,6 +668,41 @@ def test_zero_skipping_equals_dense(monkeypatch):
     assert s_[7] < 0.97 * d[7]
 
 
+def test_weight_ring_stress_skewed_trip_counts(monkeypatch):
+    """Stress of the barrier-free streamed weight ring (niq_engine.cuh acquire_chunk / release): within every CTA the warps
+    0-3 get tiny boxes (most columns dead after each relu -> short list-driven K loops) and the warps 4-7 huge ones (no dead
+    column -> full loops), so the warps drift as far apart as the ring allows while the last one to release a stage refills
+    it.  A race between a refill and a late reader would corrupt weights: repeated launches must be bit-identical to each
+    other, equal to the dense loops (NIQ_NO_SPARSE=1) within the summation-order noise, and equal to the oracle."""
+    import _niq
+    p = net.random_mlp([3] + [256] * 8 + [1], "relu", seed=0)
+    func = make(p, "affine_fixed")
+    rng = np.random.default_rng(9)
+    n = 16 * 148 * 6 + 5                               # six passes per CTA and a ragged tail
+    c = rng.uniform(-0.8, 0.8, (n, 3)).astype(np.float32)
+    warp = (np.arange(n) % 16) // 2                     # 16 boxes per CTA pass, 2 per warp (Engine<256, TileBox3>)
+    h = np.where(warp[:, None] < 4, 2.0 ** -14, 0.9).astype(np.float32) * rng.uniform(0.5, 1, (n, 3)).astype(np.float32)
+    runs = {}
+    for tag, env in (("sparse", "0"), ("dense", "1")):
+        monkeypatch.setenv("NIQ_NO_SPARSE", env)
+        ctx = _niq.Context(0)
+        try:
+            runs[tag] = [func.bound_box(p, c - h, c + h, ctx=ctx) for _ in range(6 if tag == "sparse" else 1)]
+        finally:
+            ctx.close()
+    first = runs["sparse"][0]
+    for r in runs["sparse"][1:]:
+        for a, b in zip(first, r):
+            np.testing.assert_array_equal(a, b)
+    d = runs["dense"][0]
+    mag = np.maximum(np.abs(d[1]), np.abs(d[2])) + 1e-30
+    assert np.all(np.abs(d[1] - first[1]) <= 4e-6 * mag) and np.all(np.abs(d[2] - first[2]) <= 4e-6 * mag)
+    sub = slice(0, 600)
+    olab, olo, oup, osc = net.classify_box(p, octx("affine_fixed"), (c - h)[sub], (c + h)[sub], return_scale=True)
+    check_bounds(first[1][sub], first[2][sub], olo, oup, osc)
+    check_labels(first[0][sub], olab, olo, oup, osc)
+
+
 def test_exec_macs_counter_and_device_timer():
     """niq_ctx_exec_macs counts the multiply-adds the network kernels issue; an elu net has no exact zeros, so the
     count is the padded dense count (>= algorithmic 5*M per box).  niq_ctx_timer_* brackets device time only."""
