@@ -962,6 +962,14 @@ struct Engine {
         __syncwarp();
     }
 
+    // A warp that sits a pass out (niq_tree.cuh: small levels use half of the warps so that each runs alone on its scheduler)
+    // still takes part in the streamed weight ring: it acquires every chunk of layers [l0, l1) in order and lets go of it at once.
+    __device__ __forceinline__ void skip_net(int l0, int l1) {
+        if (resident) return;
+        for (int l = l0; l < l1; ++l)
+            for (int ch = net.layers[l].chunk_begin; ch < net.layers[l].chunk_end; ++ch) acquire_chunk(ch);
+    }
+
     // Run layers [l0, l1) of the stream; the last one must be a dot layer.
     __device__ __forceinline__ void run_net(int l0, int l1, float out[ROWS], float pscale[ROWS]) {
         bool sp = false;

@@ -128,9 +128,16 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         const long long n_tiles = (N + kTreeTile - 1) / kTreeTile;
 
         // ---------------- phase 1: classify ----------------
-        const long long n_pass = (N + E::CTA_TILES - 1) / E::CTA_TILES;
+        // A level that fits the grid with HALF of the warps uses warps 0-3 only: each then has its scheduler (and its share of
+        // the FMA pipe) to itself, which halves the latency of the pass -- and the top of a tree is nothing but latency:
+        // a level costs one pass whether it holds one box or a full wave.
+        const bool half = N <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
+        const int warps_used = half ? kWarps / 2 : kWarps;
+        const long long pass_boxes = (long long)warps_used * E::SLOTS;
+        const long long n_pass = (N + pass_boxes - 1) / pass_boxes;
         for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-            const long long warp_box0 = pass * E::CTA_TILES + (long long)warp * E::SLOTS;
+            if (warp >= warps_used) { eng.skip_net(0, net.n_layers); continue; }
+            const long long warp_box0 = pass * pass_boxes + (long long)warp * E::SLOTS;
             if (lane < E::SLOTS) {
                 const long long i = warp_box0 + lane;
                 float4 rows[5];

@@ -695,7 +695,8 @@ def test_weight_ring_stress_skewed_trip_counts(monkeypatch):
         for a, b in zip(first, r):
             np.testing.assert_array_equal(a, b)
     d = runs["dense"][0]
-    mag = np.maximum(np.abs(d[1]), np.abs(d[2])) + 1e-30
+    mag = np.maximum(np.abs(d[1]), np.abs(d[2]))
+    mag = np.maximum(mag, np.median(mag))        # a bound that cancels to ~0 still carries the summation noise of its terms
     assert np.all(np.abs(d[1] - first[1]) <= 4e-6 * mag) and np.all(np.abs(d[2] - first[2]) <= 4e-6 * mag)
     sub = slice(0, 600)
     olab, olo, oup, osc = net.classify_box(p, octx("affine_fixed"), (c - h)[sub], (c + h)[sub], return_scale=True)
