@@ -2,6 +2,7 @@
 // Build: see __graft_entry__.build (one translation unit per kernel family, linked into libniq.so).
 #define NIQ_HELPER_KERNELS
 #include "niq_internal.h"
+#include "niq_cp.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // error plumbing
@@ -1379,6 +1380,45 @@ extern "C" int niq_closest_point(niq_ctx* c, const niq_mlp* m, const niq_mode_cf
     // evaluation + ONE fused single-CTA kernel, captured once into a CUDA graph and replayed (the launch-bound inner
     // loop of the query); buffers of the graph live for the whole call.
     const bool small_window = Bw <= 2 * kCpSmallThreads;
+    // ---- the reference's default regime (window <= 2048), fixed-row modes, resident weights: every round of the search inside
+    // ONE cooperative kernel (niq_cp.cuh); the stack top never leaves the device ----
+    if (small_window && is_fixed_mode(cfg) && !(getenv("NIQ_CP_LEGACY") && getenv("NIQ_CP_LEGACY")[0] != '0')) {
+        int coop = 0;
+        CU(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, c->device));
+        DevBuf p_label(c), p_tie(c), p_vals(c), p_ctl(c);
+        TRY(p_label.alloc(Bw * 4)); TRY(p_tie.alloc(Bw)); TRY(p_vals.alloc(Bw * 28)); TRY(p_ctl.alloc(sizeof(CpCtl)));
+        CpCtl h{};
+        h.top = q; h.max_top = q;
+        CU(cudaMemcpyAsync(p_ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+        bool ran = false;
+        for (int attempt = 0; coop && attempt < 40; ++attempt) {
+            // room for the window's children of many rounds; a round that would not fit stops the kernel at its boundary
+            TRY(reserve(std::max<long long>(h.top, q) + 64 * Bw + 16, h.top));
+            CpArgs a{};
+            a.stack_lo = s_lo; a.stack_hi = s_hi; a.stack_qid = s_id; a.cap = cap; a.window = Bw;
+            a.query = dq.as<float>(); a.min_dist = dd.as<float>(); a.min_loc = dl.as<float>(); a.winner = d_winner.as<unsigned long long>();
+            a.n_query = q; a.label = p_label.as<int>(); a.tie = p_tie.as<unsigned char>(); a.vals = p_vals.as<float>();
+            a.eps_w = eps_w; a.interval = cfg->mode == NIQ_MODE_INTERVAL; a.ctl = p_ctl.as<CpCtl>();
+            bool fits = false;
+            TRY(launch_cp_persistent(c, m, a, &fits));
+            if (!fits) break;                       // streamed / wide nets: the CUDA-graph round loop below
+            ran = true;
+            timer_mark(c);
+            CU(cudaMemcpyAsync(&h, p_ctl.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+            CU(cudaStreamSynchronize(c->stream));
+            if (h.status == 0) break;
+            h.status = 0;                           // the stack was too small for the next round: grow it and go on
+            CU(cudaMemcpyAsync(p_ctl.p, &h, sizeof(h), cudaMemcpyHostToDevice, c->stream));
+            if (attempt == 39) return fail(NIQ_ENOMEM, "closest_point: the stack kept growing (%lld entries)", h.top);
+        }
+        if (ran) {
+            if (stats) { stats[0] = h.stats[0]; stats[1] = h.stats[1]; stats[2] = h.max_top; stats[3] = h.stats[2]; }
+            c->launches += 0;
+            TRY(dd.flush(c)); TRY(dl.flush(c));
+            CU(cudaStreamSynchronize(c->stream));
+            return NIQ_OK;
+        }
+    }
     DevBuf g_label(c), g_tie(c), g_vals(c);
     cudaGraphExec_t cp_exec = nullptr;
     struct GraphGuard { cudaGraphExec_t* e; ~GraphGuard() { if (*e) cudaGraphExecDestroy(*e); } } gg{&cp_exec};

@@ -404,7 +404,10 @@ struct Engine {
     unsigned int seq_consumed;
     unsigned long long exec_macs;   // tile-row MACs / RT actually executed by this warp (k-steps x out_pad x SLOTS), lane-uniform
 
-    __device__ Engine(const NetDev& n, unsigned char* smem_raw) : net(n) {
+    // primary = false: a SECOND engine over the same shared memory (another tile shape for another kind of pass of the same
+    // kernel, niq_cp.cuh): it shares the resident weights the first one staged and only lays out its own activation buffers
+    // (resident nets only; the two kinds of pass never run at the same time in one CTA).
+    __device__ Engine(const NetDev& n, unsigned char* smem_raw, bool primary = true) : net(n) {
         warp = threadIdx.x >> 5;
         lane = threadIdx.x & 31;
         t = lane / G::CG;
@@ -420,6 +423,7 @@ struct Engine {
         seg = reinterpret_cast<int*>(acts + kWarps * WARP_FLOATS + kWarps * SLOTS * 8 + kWarps * LIST_WORDS) + warp * SEG_WORDS;
         seq_consumed = 0;
         exec_macs = 0;
+        if (!primary) return;
         for (int i = lane; i < LIST_WORDS; i += 32) lst[i] = 0u;   // every entry is always a valid in-chunk offset
         if (threadIdx.x == 0) {
             for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); done[s] = 0; }

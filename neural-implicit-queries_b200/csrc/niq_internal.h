@@ -200,3 +200,5 @@ int launch_cast_rays_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, c
                           unsigned char* tie, unsigned long long* queue);
 int launch_cast_frustum_grow(niq_ctx* c, int n_funcs, const niq_mlp* const* mlps, const niq_mode_cfg* cfgs, const NetDev& net,
                              const CastOpts& o, const FrustCam& cam, const FrustQueue& q, long long n_pixels);
+namespace niq { struct CpArgs; }
+int launch_cp_persistent(niq_ctx* c, const niq_mlp* m, const niq::CpArgs& a, bool* fits);

@@ -1060,6 +1060,29 @@ def test_closest_point_vs_oracle(B):
         assert ok.mean() > 0.7
 
 
+@pytest.mark.parametrize("name,mode,B,Q,eps", [("fox", "affine_fixed", 256, 40, 0.01), ("birdcage_occ", "affine_fixed", 2048, 24, 1e-3),
+                                               ("fox", "interval", 64, 12, 0.05), ("hammer", "affine_fixed", 2048, 3000, 0.02)])
+def test_closest_point_persistent_kernel_equals_graph_loop(monkeypatch, name, mode, B, Q, eps):
+    """The one-launch cooperative search (csrc/niq_cp.cuh: every round of the LIFO window inside the kernel) against the
+    CUDA-graph round loop it replaces (NIQ_CP_LEGACY=1): same engine passes, same round logic -> distances, locations and
+    statistics identical.  Q = 3000 > window: the stack starts longer than the window; eps 0.02 keeps it short."""
+    import kd_tree
+    p = sample_params(name)
+    q = np.random.default_rng(8).uniform(-1, 1, (Q, 3)).astype(np.float32)
+    res = []
+    for legacy in ("0", "1"):
+        monkeypatch.setenv("NIQ_CP_LEGACY", legacy)
+        st = {}
+        d, loc = kd_tree.closest_point(make(p, mode), p, LO, HI, q, eps=eps, batch_process_size=B, stats=st)
+        res.append((d, loc, st))
+    (d0, l0, s0), (d1, l1, s1) = res
+    assert s0 == s1, (s0, s1)
+    np.testing.assert_array_equal(d0, d1)
+    fin = np.isfinite(d1)
+    np.testing.assert_array_equal(l0[fin], l1[fin])
+    assert fin.any() and s0["n_rounds"] > 3
+
+
 # ---------------------------------------------------------------------------------------------------
 # tree consumers (SURVEY 8(f) row 3)
 # ---------------------------------------------------------------------------------------------------
