@@ -93,7 +93,8 @@ def test_param_dict_helpers_follow_reference_grammar():
     init = mlp.initialize_params(spec, 0)
     assert init["0000.dense.A"].shape == (3, 16) and init["0004.dense.b"].shape == (1,)
     with pytest.raises(ValueError):
-        mlp.quick_mlp_spec([3, 4, 1], "tanh")       # the reference accepts relu / elu only (src/mlp.py:86-90)
+        mlp.quick_mlp_spec([3, 4, 1], "gelu")       # the reference accepts relu / elu only (src/mlp.py:86-90); 'tanh' is ours
+    assert "0001.tanh._" in mlp.initialize_params(mlp.build_spec(mlp.quick_mlp_spec([3, 4, 1], "tanh")), 0)
 
 
 def test_bucketing_matches_oracle():

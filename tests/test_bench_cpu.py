@@ -44,3 +44,37 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_fixed_tile_set_is_the_same_for_every_rank_count():
+    """Strong scaling: the step's tile set does not depend on N, the ranks' shares partition it, and both arms describe the
+    same workload (`config` identical)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    tiles, ntx = bench.chosen_tiles(bench.TILES_TOTAL)
+    assert len(tiles) == bench.TILES_TOTAL == 296 and len(set(tiles.tolist())) == 296
+    allpix = bench.pixels_of_tiles(tiles, ntx)
+    assert allpix.shape[0] == len(set(allpix.tolist())) and allpix.max() < bench.RES_X * bench.RES_Y
+    for world in (1, 2, 4, 8):
+        parts = [bench.pixels_of_tiles(tiles[r::world], ntx) for r in range(world)]
+        assert sum(p.shape[0] for p in parts) == allpix.shape[0]
+        assert sorted(np.concatenate(parts).tolist()) == sorted(allpix.tolist())
+    cfg = bench.workload_config(bench.TILES_TOTAL, 1)
+    assert cfg["rays_per_step"] == allpix.shape[0] and cfg["tiles_per_step"] == 296
+
+
+def test_config_cpu_legs_run_on_small_samples():
+    """The CPU (oracle) legs of bench.py's configs block, on tiny samples: each returns (kind, seconds, units)."""
+    sys.path.insert(0, ROOT)
+    import bench
+    from conftest import sample_params
+    fox = sample_params("fox")
+    r, d = bench.camera_rays()
+    k, dt, u = bench._cpu_cfg(("cfg1", fox, r[::200000], d[::200000]))
+    assert k == "cfg1" and dt > 0 and u["rays"] == r[::200000].shape[0] and u["ray_steps"] >= u["rays"]
+    k, dt, u = bench._cpu_cfg(("cfg2_tree", fox, 4))
+    assert u["boxes"] >= 5
+    k, dt, u = bench._cpu_cfg(("cfg4", fox, np.zeros((2, 3), np.float32)))
+    assert u["queries"] == 2 and u["visits"] > 0
+    R, t = bench.cfg3_transforms(3)
+    assert R.shape == (3, 3, 3) and t.shape == (3, 3) and np.allclose(np.linalg.det(R), 1.0, atol=1e-5)
