@@ -301,7 +301,7 @@ __device__ __forceinline__ void sin_lin(float l, float u, float& alpha, float& b
 }
 
 // tanh linearisation on [l,u].  PARITY UNPINNED: the reference registers no tanh rule -- this is the Chebyshev-style
-// construction of the paper written from scratch, the same formulas as oracle/niq_oracle/net.py _tanh_coeffs:
+// construction of the paper written from scratch, the same formulas as the CPU checker's tanh coefficients (tests/test_tanh.py compares the two):
 //   alpha = secant slope (tanh u - tanh l) / w, w = u - l, evaluated without the cancelling difference through
 //           tanh u - tanh l = (1 - tanh u tanh l) tanh(w):  alpha = (1 - tanh u tanh l) * g(w), g = tanh(w)/w (1 - w^2/3 below 1e-3);
 //   the residual tanh(x) - alpha x has its extrema over [l,u] at l, u or where tanh'(x) = alpha, x* = +-atanh(sqrt(1 - alpha));
