@@ -398,6 +398,21 @@ def run_ours(args):
     d21_host_s = (time.perf_counter() - t0) / 3
     BOXES21 = 1786421 if n_boxes21 is None else n_boxes21      # boxes of the single-device tree (the sharded build classifies the
                                                                # replicated top levels on every rank: not counted twice)
+    # where the sharded build's time goes (names the residual of the strong scaling): this rank's own build alone
+    # (replicated top + own subtrees, one dealt launch) against the whole call (+ the NCCL gather of the leaves)
+    own_s = own_dev_ms = 0.0
+    own_levels = own_boxes = 0
+    if world > 1:
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            ctx.timer_start()
+            tr = sharding._build_own_tree(fb, bunny, lo3, hi3, 21, None, rank, world, {"ctx": ctx})
+            own_dev_ms = ctx.timer_stop()
+            stt = tr.stats()
+            own_levels, own_boxes = stt["n_levels"], stt["n_evals"]
+            tr.close()
+        own_s = (time.perf_counter() - t0) / 3
 
     # ---- optional: the WHOLE 1920x1080 image once (this rank's share of it for N > 1) ----
     full_image = None
@@ -420,9 +435,9 @@ def run_ours(args):
         del rf, df, tf_, hf, cf
 
     if world > 1:
-        red = torch.tensor([total_ms, e2e_s, kernel_ms, d21_s, d21_host_s], dtype=torch.float64, device=dev)
+        red = torch.tensor([total_ms, e2e_s, kernel_ms, d21_s, d21_host_s, own_s, own_dev_ms, own_boxes], dtype=torch.float64, device=dev)
         dist.all_reduce(red, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kernel_ms, d21_s, d21_host_s = (float(x) for x in red.tolist())
+        total_ms, e2e_s, kernel_ms, d21_s, d21_host_s, own_s, own_dev_ms, own_boxes_max = (float(x) for x in red.tolist())
         rs = torch.tensor([ray_steps, n], dtype=torch.int64, device=dev)
         dist.all_reduce(rs)
         ray_steps_all, n_sum = (int(x) for x in rs.tolist())
@@ -471,6 +486,14 @@ def run_ours(args):
                                                 "leaves all-gathered from device buffers (one NCCL all_gather_into_tensor of 24 B/leaf)",
                                  "timer": "wall clock, max over ranks: value = until the leaves are in HBM (of every rank for N > 1); e2e = until every rank "
                                           "holds them on the host (sharding.tree_sharded / kd_tree.construct_uniform_unknown_levelset_tree)"}
+        if world > 1:
+            tree["bunny_depth21"]["residual"] = {
+                "own_build_ms": own_s * 1e3, "own_build_device_ms": own_dev_ms, "gather_ms": (d21_s - own_s) * 1e3,
+                "levels": own_levels, "boxes_classified_max_rank": int(own_boxes_max), "boxes_single_tree_over_world": BOXES21 / world,
+                "note": "own_build = this rank's dealt launch (max over ranks, wall / CUDA events): the 22 dependent levels cost one pass "
+                        "through the net each however few boxes a rank holds (the latency floor that does not shrink with N), the top "
+                        "levels are replicated, and the slowest rank's share sets the time; gather = count-carrying all_gather of 24 B/leaf "
+                        "+ its host-side launch / sync"}
         out["tree"] = {"metric": "kd-tree boxes/s (construct_uniform_unknown_levelset_tree, affine_fixed, domain [-1,1]^3)", **tree}
         # ---- CPU baseline beside it (rank 0, N=1 only): the oracle port on the host cores ----
         if world == 1 and not args.no_cpu:
@@ -653,7 +676,17 @@ def config_metrics(ctx, peak_tflops, cpu=True):
     cfg["cfg3_hammer_x_bunny_intersection_truncate64"] = {"queries": 64, "found": n_found, "queries_per_s": 64 / tot, "nodes_per_s": n_nodes / tot,
                                                          "nodes": n_nodes, "rounds": n_rounds, "mean_ms": 1e3 * tot / 64, "max_ms": 1e3 * max(lat),
                                                          "median_ms": 1e3 * float(np.median(lat)),
-                                                         "roofline": roof(FLOP_NODE3 * n_nodes, 0, tot), "kernel": "k_classify_grow + k_eval_points<64> + k_isect_logic"}
+                                                         "roofline": roof(FLOP_NODE3 * n_nodes, 0, tot),
+                                                         "kernel": "k_isect_persistent (one cooperative launch per query: the rounds stay on the device)",
+                                                         "timer": "wall clock per kd_tree.find_any_intersection call (latency of one query at a time)"}
+    # the same 64 queries as ONE call: all of them advance round by round inside one persistent kernel
+    stb = {}
+    tb, _, _, rb = timed(lambda: kd_tree.find_any_intersection_batch((fA, fB), (pA, pB), lo, hi, 1e-3, R_B=R, t_B=t, stats=stb, ctx=ctx), reps=2)
+    nb = int(np.sum(stb["n_nodes"]))
+    cfg["cfg3_batched_64_transforms"] = {"queries": 64, "found": int(rb[0].sum()), "queries_per_s": 64 / tb, "nodes_per_s": nb / tb, "nodes": nb,
+                                         "ms": 1e3 * tb, "roofline": roof(FLOP_NODE3 * nb, 0, tb),
+                                         "kernel": "k_isect_persistent (niq_find_any_intersection_batch: one launch for the whole list)",
+                                         "same_verdicts_as_single_queries": bool(int(rb[0].sum()) == n_found)}
     # ---- config 4: birdcage_occ closest_point, affine_fixed, eps 1e-3, Q = 256 of the 1 M seeded queries ----
     p = mlps["birdcage_occ"]
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_fixed")
@@ -665,7 +698,7 @@ def config_metrics(ctx, peak_tflops, cpu=True):
         cfg[f"cfg4_birdcage_closest_point_{tag}"] = {"queries": nq, "batch_process_size": B, "queries_per_s": nq / dt, "node_visits_per_s": st["n_visits"] / dt,
                                                     "visits_per_query": st["n_visits"] / nq, "rounds": st["n_rounds"], "max_stack": st["max_stack"], "ms": dt * 1e3,
                                                     "device_ms": dms, "roofline": roof((10 + 14) * Mc * st["n_visits"], macs, dt),
-                                                    "kernel": "k_classify_fixed<64> + k_eval_points<64> + k_cp_round_small (CUDA graph)" if B <= 2048 else "k_classify_fixed<64> + k_eval_points<64> + k_cp_*"}
+                                                    "kernel": "k_cp_persistent<64> (one cooperative launch for all rounds)" if B <= 2048 else "k_classify_fixed<64> + k_eval_points<64> + k_cp_* (one launch set per round: a few large rounds)"}
     # ---- the CPU oracle beside each config, bounded samples, in parallel processes ----
     if cpu:
         import multiprocessing as mp

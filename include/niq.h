@@ -216,6 +216,14 @@ int niq_tree_build(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, co
 int niq_tree_build_roots(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, int64_t n_roots, const float* lower,
                          const float* upper, int32_t split_depth, int64_t node_terminate_thresh, float offset,
                          int32_t flags, int32_t batch_process_size, niq_tree** out);
+/* Ours (multi-GPU subtree partition, no reference counterpart: the reference is single-device): rank `rank` of `world`
+ * builds the levels above deal_depth like niq_tree_build, keeps every world-th node of the frontier entering level
+ * deal_depth (i = rank mod world) and refines those to split_depth, all in one launch.  The union of the ranks' UNKNOWN
+ * leaves is the leaf set of niq_tree_build(split_depth); leaf order is per rank.  Modes: interval, affine_fixed,
+ * slope_interval (NIQ_EUNSUPPORTED otherwise: deal on the host and use niq_tree_build_roots).               */
+int niq_tree_build_dealt(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, const float lower[3],
+                         const float upper[3], int32_t split_depth, float offset, int32_t batch_process_size,
+                         int32_t deal_depth, int32_t rank, int32_t world, niq_tree** out);
 /* which: 0 unknown leaves, 1 interior (NEGATIVE) nodes, 2 exterior (POSITIVE) nodes                    */
 int niq_tree_count(const niq_tree* tree, int which, int64_t* n);
 int niq_tree_copy(const niq_tree* tree, int which, float* lower, float* upper, int64_t capacity, int mem);

@@ -980,6 +980,28 @@ extern "C" int niq_tree_build(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* 
                               int32_t split_depth, int64_t node_thresh, float offset, int32_t flags, int32_t bps, niq_tree** out) {
     return niq_tree_build_roots(c, m, cfg, 1, lower, upper, split_depth, node_thresh, offset, flags, bps, out);
 }
+// One rank's share of a tree whose subtrees are partitioned over `world` ranks: the levels above `deal_depth` are built as in
+// niq_tree_build (replicated on every rank), the nodes entering level deal_depth are dealt round-robin, and the rank refines
+// its own ones to split_depth -- one persistent launch (niq_tree.cuh TreeArgs::deal_*).  UNKNOWN leaves only.
+extern "C" int niq_tree_build_dealt(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, const float lower[3], const float upper[3],
+                                    int32_t split_depth, float offset, int32_t bps, int32_t deal_depth, int32_t rank, int32_t world,
+                                    niq_tree** out) {
+    if (!c || !m || !lower || !upper || !out) return fail(NIQ_EINVAL, "niq_tree_build_dealt: bad argument");
+    TRY(check_cfg(cfg));
+    if (split_depth < 0 || deal_depth < 0 || deal_depth > split_depth || world < 1 || rank < 0 || rank >= world || bps <= 0)
+        return fail(NIQ_EINVAL, "niq_tree_build_dealt: need 0 <= deal_depth <= split_depth, 0 <= rank < world, batch_process_size > 0");
+    CU(cudaSetDevice(c->device));
+    timer_touch(c);
+    niq_tree* T = new niq_tree();
+    T->ctx = c;
+    struct Guard { niq_tree* t; bool ok = false; ~Guard() { if (!ok) niq_tree_destroy(t); } } guard{T};
+    bool handled = false;
+    TRY(tree_build_persistent(c, m, cfg, 1, lower, upper, split_depth, 9999999999ll, offset, 0, bps, T, &handled, deal_depth, rank, world));
+    if (!handled) return fail(NIQ_EUNSUPPORTED, "niq_tree_build_dealt: interval / affine_fixed / slope_interval only (other modes: build the top, deal on the host, niq_tree_build_roots)");
+    guard.ok = true;
+    *out = T;
+    return NIQ_OK;
+}
 extern "C" int niq_tree_count(const niq_tree* t, int which, int64_t* n) {
     if (!t || !n || which < 0 || which > 2) return fail(NIQ_EINVAL, "bad argument");
     *n = t->lists[which].n;

@@ -186,9 +186,10 @@ int launch_cast_frustum(niq_ctx* c, int wmax, const NetDev& net, int total_float
 int launch_classify_grow(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, BoxSource src, long long n,
                          float offset, int* label, float* lower, float* upper, unsigned char* tie);
 // the whole level-set tree in one cooperative launch (niq_tree.cuh); *handled = false when the mode has no persistent kernel
+// deal_world > 1: the frontier entering level deal_level is dealt round-robin, this rank keeps i = deal_rank (mod deal_world)
 int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, long long n_roots, const float* lower,
                           const float* upper, int split_depth, long long node_thresh, float offset, int flags, int bps,
-                          niq_tree* T, bool* handled);
+                          niq_tree* T, bool* handled, int deal_level = -1, int deal_rank = 0, int deal_world = 1);
 // find_any_intersection for the growing-form modes as one persistent cooperative kernel (niq_isect.cuh), for a batch of n_q
 // queries that differ in the rigid transforms prepended to the two shapes (xfA / xfB: HOST (n_q, 12) = R (3x3) + t (3) per
 // query, or NULL: the handle's own first layer).  *handled = false when a mode is not a growing-form mode.

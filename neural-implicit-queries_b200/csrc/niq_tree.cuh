@@ -49,8 +49,14 @@ struct TreeArgs {
     long long n_splits, node_thresh, bps;
     float offset;
     int want_neg, want_pos, interval;
+    // Multi-GPU subtree partition (ours): every rank builds the top of the tree replicated; of the frontier that ENTERS level
+    // deal_level a rank keeps the nodes i = deal_rank (mod deal_world) and drops the rest, so below that level it refines its own
+    // subtrees only -- in the same launch, without a host round trip.  deal_world <= 1: no deal.
+    long long deal_level;
+    int deal_rank, deal_world;
     TreeCtl* ctl;
 };
+constexpr int kTreeDropped = 0x7f;       // label of a node another rank owns (matches no SIGN_* value: every compaction skips it)
 
 // sense-reversing grid barrier (cooperative launch: all CTAs are co-resident).  __threadfence() is a gpu-scope fence: it
 // orders this CTA's writes before the arrival and invalidates the SM's L1 after the release, so plain loads of data other
@@ -131,19 +137,28 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         // A level that fits the grid with HALF of the warps uses warps 0-3 only: each then has its scheduler (and its share of
         // the FMA pipe) to itself, which halves the latency of the pass -- and the top of a tree is nothing but latency:
         // a level costs one pass whether it holds one box or a full wave.
-        const bool half = N <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
+        // the deal (TreeArgs): at this one level the rank classifies only its own nodes j -> i = rank + j * world; the others
+        // are labelled "dropped" and vanish in the compaction of phase 2
+        const bool dealing = a.deal_world > 1 && level == a.deal_level;
+        const long long Nc = !dealing ? N : (N > a.deal_rank ? (N - a.deal_rank + a.deal_world - 1) / a.deal_world : 0);
+        const long long i_mul = dealing ? a.deal_world : 1, i_add = dealing ? a.deal_rank : 0;
+        if (dealing)
+            for (long long i = (long long)blockIdx.x * kThreads + tid; i < N; i += (long long)gridDim.x * kThreads)
+                if (i % a.deal_world != a.deal_rank) a.label[i] = kTreeDropped;
+        const bool half = Nc <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
         const int warps_used = half ? kWarps / 2 : kWarps;
         const long long pass_boxes = (long long)warps_used * E::SLOTS;
-        const long long n_pass = (N + pass_boxes - 1) / pass_boxes;
+        const long long n_pass = (Nc + pass_boxes - 1) / pass_boxes;
         for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
             if (warp >= warps_used) { eng.skip_net(0, net.n_layers); continue; }
             const long long warp_box0 = pass * pass_boxes + (long long)warp * E::SLOTS;
             if (lane < E::SLOTS) {
-                const long long i = warp_box0 + lane;
+                const long long j = warp_box0 + lane;
+                const long long i = j * i_mul + i_add;
                 float4 rows[5];
 #pragma unroll
                 for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (i < N) {
+                if (j < Nc) {
                     BoxSource src{};
                     src.kind = 1; src.v = 3; src.a = cur_lo; src.b = cur_hi;
                     src.interval = Tile::rule == 2 ? 0 : a.interval;
@@ -166,9 +181,10 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
             if (eng.cg == 0) {      // label + near-tie flag of every slot, handed to lane `slot` through the warp's scratch
 #pragma unroll
                 for (int nn = 0; nn < E::NT; ++nn) {
-                    const long long i = warp_box0 + nn * E::G::TPW + eng.t;
+                    const long long j = warp_box0 + nn * E::G::TPW + eng.t;
+                    const long long i = j * i_mul + i_add;
                     int code = 0xff;
-                    if (i < N) {
+                    if (j < Nc) {
                         float lo_b, up_b;
                         if (Tile::rule == 2) {     // src/slope_interval.py:201-206
                             float prad = 0.f;
@@ -198,7 +214,16 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
                 const unsigned b_neg = __ballot_sync(0xffffffffu, lab == SIGN_NEGATIVE);
                 const unsigned b_pos = __ballot_sync(0xffffffffu, lab == SIGN_POSITIVE);
                 const unsigned b_tie = __ballot_sync(0xffffffffu, tie);
-                if (lane == 0 && warp_box0 < N) {
+                if (dealing) {
+                    // the slots of a warp pass are `world` nodes apart: they fall into several tiles, each lane counts its own
+                    if (lane < E::SLOTS && lab != 0xff) {
+                        const long long tile = ((warp_box0 + lane) * i_mul + i_add) / kTreeTile;
+                        if (lab == SIGN_UNKNOWN) atomicAdd(cnt + tile, 1);
+                        if (lab == SIGN_NEGATIVE && a.want_neg) atomicAdd(cnt + T + tile, 1);
+                        if (lab == SIGN_POSITIVE && a.want_pos) atomicAdd(cnt + 2 * T + tile, 1);
+                    }
+                    if (lane == 0 && b_tie) atomicAdd(&a.ctl->n_tie_level, (unsigned long long)__popc(b_tie));
+                } else if (lane == 0 && warp_box0 < N) {
                     const long long tile = warp_box0 / kTreeTile;
                     if (b_unk) atomicAdd(cnt + tile, __popc(b_unk));
                     if (b_neg && a.want_neg) atomicAdd(cnt + T + tile, __popc(b_neg));
@@ -357,7 +382,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         if (blockIdx.x == 0 && tid == 0 && level < kTreeMaxLevels) {
             a.levels[4 * level] = N; a.levels[4 * level + 1] = tot[0]; a.levels[4 * level + 2] = tot[1]; a.levels[4 * level + 3] = tot[2];
         }
-        n_evals += N;
+        n_evals += Nc;
         if (N > max_frontier) max_frontier = N;
         n_fin[0] += tot[1]; n_fin[1] += tot[2];
         N = n_out;

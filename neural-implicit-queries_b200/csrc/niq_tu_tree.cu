@@ -90,7 +90,7 @@ int launch_tree_t(niq_ctx* c, const niq_mlp* m, const TreeArgs& a) {
 
 int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg, long long n_roots, const float* lower,
                           const float* upper, int split_depth, long long node_thresh, float offset, int flags, int bps,
-                          niq_tree* T, bool* handled) {
+                          niq_tree* T, bool* handled, int deal_level, int deal_rank, int deal_world) {
     const bool fixed = cfg->mode == NIQ_MODE_INTERVAL || cfg->mode == NIQ_MODE_AFFINE_FIXED;
     const bool slope = cfg->mode == NIQ_MODE_SLOPE_INTERVAL;
     *handled = false;
@@ -108,6 +108,8 @@ int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg,
     if (const char* e = getenv("NIQ_TREE_CAP")) kCapFirst = std::max(1ll, atoll(e));       // test knob: force the growth path
     long long want = kCapFirst;
     if (split_depth >= 0 && split_depth < 40) want = std::min(want, n_roots << std::min(split_depth, 40));
+    // a dealt build holds the replicated top frontier or its share of the bottom (x2 for imbalance), whichever is larger
+    if (deal_world > 1) want = std::min(want, std::max(want / deal_world * 2, (long long)n_roots << std::min(std::max(deal_level, 0), 40)));
     if (node_thresh < (1ll << 40)) want = std::min(want, std::max(2 * node_thresh, n_roots));
     want = std::max<long long>(std::max(want, n_roots), getenv("NIQ_TREE_CAP") ? 1 : 4096);
 
@@ -133,6 +135,7 @@ int tree_build_persistent(niq_ctx* c, const niq_mlp* m, const niq_mode_cfg* cfg,
         a.cap = b.cap; a.label = b.label; a.tile_cnt = b.tile_cnt; a.n_tiles_max = b.n_tiles_max; a.levels = b.levels;
         a.n_splits = n_splits; a.node_thresh = node_thresh; a.bps = bps; a.offset = offset;
         a.want_neg = want_fin[0]; a.want_pos = want_fin[1]; a.interval = cfg->mode == NIQ_MODE_INTERVAL; a.ctl = b.ctl;
+        a.deal_level = deal_level; a.deal_rank = deal_rank; a.deal_world = deal_world;
         if (slope) TRY(launch_tree_t<TileSlope3>(c, m, a));
         else TRY(launch_tree_t<TileBox3>(c, m, a));
         timer_mark(c);

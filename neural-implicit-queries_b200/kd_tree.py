@@ -91,6 +91,21 @@ def build_tree(func, params, lower, upper, node_terminate_thresh=None, split_dep
     return _Tree(ctx, h)
 
 
+def build_tree_dealt(func, params, lower, upper, split_depth, deal_depth, rank, world, offset=0., batch_process_size=2048, ctx=None):
+    """Ours: this rank's share of the tree at `split_depth` when the subtrees below `deal_depth` are partitioned round-robin
+    over `world` ranks (niq_tree_build_dealt: replicated top + own subtrees in ONE persistent launch).  Fixed-row modes and
+    slope_interval; raises NiqError(NIQ_EUNSUPPORTED) otherwise (sharding.tree_sharded then deals on the host)."""
+    ctx = ctx or _niq.default_context()
+    lower, upper = _vec3(lower, "lower"), _vec3(upper, "upper")
+    cfg = _niq.mode_cfg(func.ctx)
+    m = ctx.mlp(params)
+    h = C.c_void_p()
+    _niq.check(_niq.lib().niq_tree_build_dealt(
+        ctx.handle, m.handle, C.byref(cfg), _niq.ptr(lower), _niq.ptr(upper), C.c_int32(int(split_depth)), C.c_float(offset),
+        C.c_int32(int(batch_process_size)), C.c_int32(int(deal_depth)), C.c_int32(int(rank)), C.c_int32(int(world)), C.byref(h)))
+    return _Tree(ctx, h)
+
+
 def _padded(lo, hi, size):
     n = lo.shape[0]
     out_lo = np.zeros((size, 3), np.float32)

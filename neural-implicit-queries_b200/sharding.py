@@ -199,37 +199,66 @@ def _top_frontier(func, params, lower, upper, split_depth, top_depth, world, kw)
     return top['unknown_node_lower'][v], top['unknown_node_upper'][v], top_depth
 
 
+def _build_own_tree(func, params, lower, upper, split_depth, top_depth, rank, world, kw):
+    """This rank's subtrees as a device-resident tree: one dealt persistent launch where the mode has one
+    (niq_tree_build_dealt), else the top on every rank, the deal on the host and one multi-root build."""
+    import _niq
+    import kd_tree
+    tkw = {k: v for k, v in kw.items() if k in ("offset", "batch_process_size", "ctx")}
+    if top_depth is None:
+        top_depth = default_top_depth(split_depth, world)
+    try:
+        return kd_tree.build_tree_dealt(func, params, lower, upper, split_depth, top_depth, rank, world, **tkw)
+    except _niq.NiqError as e:
+        if e.code != _niq.NIQ_EUNSUPPORTED:
+            raise
+    flo, fhi, top_depth = _top_frontier(func, params, lower, upper, split_depth, top_depth, world, kw)
+    mine = deal_boxes(flo.shape[0], rank, world)
+    if not len(mine):
+        return None
+    return kd_tree.build_tree(func, params, flo[mine], fhi[mine], split_depth=split_depth - top_depth, **tkw)
+
+
+_GATHER_CAP = {}      # (split_depth, top_depth, world) -> rows per rank of the last gather: the next one needs no count exchange
+
+
 def _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, rank, world, group, kw, to_host=True):
     """NCCL path: this rank's leaves never visit the host before the gather -- the tree's device-resident leaf list is copied
-    into a padded device buffer (niq_tree_copy, device to device), ONE all_gather_into_tensor moves 24 B/leaf over NVLink
-    (after an 8-byte all_gather of the counts), and the gathered leaves are read back once."""
+    into a padded device buffer (niq_tree_copy, device to device) and ONE all_gather_into_tensor moves 24 B/leaf over NVLink;
+    the gathered leaves are read back once.  The buffer's first row carries the rank's leaf count, so a call whose capacity is
+    known from the previous one (same depths and world) needs no separate exchange of the counts; when a rank's leaves do not fit
+    (every rank sees that in the gathered counts) the gather is repeated with the capacity they need."""
     import ctypes as C
     import torch
     import torch.distributed as dist
     import _niq
-    import kd_tree
     dev = torch.device("cuda", torch.cuda.current_device())
-    flo, fhi, top_depth = _top_frontier(func, params, lower, upper, split_depth, top_depth, world, kw)
-    mine = deal_boxes(flo.shape[0], rank, world)
-    tkw = {k: v for k, v in kw.items() if k in ("offset", "batch_process_size", "ctx")}
-    tree = None
-    n_mine = 0
-    if len(mine):
-        tree = kd_tree.build_tree(func, params, flo[mine], fhi[mine], split_depth=split_depth - top_depth, **tkw)
-        n_mine = tree.count(0)
+    tree = _build_own_tree(func, params, lower, upper, split_depth, top_depth, rank, world, kw)
+    n_mine = tree.count(0) if tree is not None else 0
+    key = (int(split_depth), top_depth, world)
     try:
-        cnt = torch.tensor([n_mine], dtype=torch.int64, device=dev)
-        counts = torch.empty(world, dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(counts, cnt, group=group)
-        counts = counts.cpu().tolist()
-        cap = max(max(counts), 1)
-        pack = torch.zeros((2, cap, 3), dtype=torch.float32, device=dev)
-        torch.cuda.current_stream().synchronize()
-        if n_mine:
-            _niq.check(_niq.lib().niq_tree_copy(tree.handle, C.c_int(0), C.c_void_p(pack[0].data_ptr()), C.c_void_p(pack[1].data_ptr()),
-                                                C.c_int64(cap), C.c_int(_niq.MEM_DEVICE)))
-        out = torch.empty((world, 2, cap, 3), dtype=torch.float32, device=dev)
-        dist.all_gather_into_tensor(out, pack, group=group)
+        cap = _GATHER_CAP.get(key)
+        if cap is None:
+            cnt = torch.tensor([n_mine], dtype=torch.int64, device=dev)
+            counts = torch.empty(world, dtype=torch.int64, device=dev)
+            dist.all_gather_into_tensor(counts, cnt, group=group)
+            cap = int(counts.max().item()) * 9 // 8 + 64
+        while True:
+            # rows 1..cap of each half hold the leaves, row 0 of the first half the count (as int32 bits)
+            pack = torch.zeros((2, cap + 1, 3), dtype=torch.float32, device=dev)
+            pack.view(torch.int32)[0, 0, 0] = n_mine
+            torch.cuda.current_stream().synchronize()
+            if 0 < n_mine <= cap:
+                _niq.check(_niq.lib().niq_tree_copy(tree.handle, C.c_int(0), C.c_void_p(pack[0, 1:].data_ptr()),
+                                                    C.c_void_p(pack[1, 1:].data_ptr()), C.c_int64(cap), C.c_int(_niq.MEM_DEVICE)))
+            out = torch.empty((world, 2, cap + 1, 3), dtype=torch.float32, device=dev)
+            dist.all_gather_into_tensor(out, pack, group=group)
+            counts = out.view(torch.int32)[:, 0, 0, 0].cpu().tolist()
+            if max(counts) <= cap:
+                break
+            cap = max(counts) * 9 // 8 + 64
+        _GATHER_CAP[key] = cap
+        out = out[:, :, 1:]
         if not to_host:
             torch.cuda.current_stream().synchronize()
             return out, counts
@@ -244,33 +273,29 @@ def _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, ran
 
 def _own_leaves(func, params, lower, upper, split_depth, top_depth, build_fn, rank, world, kw):
     """The UNKNOWN leaves at `split_depth` below this rank's share of the frontier (top levels replicated)."""
-    injected = build_fn is not None
     if build_fn is None:
-        import kd_tree
-        build_fn = kd_tree.construct_uniform_unknown_levelset_tree
+        # the CUDA backend: one dealt persistent launch (or top + host deal + one multi-root build, _build_own_tree)
+        tree = _build_own_tree(func, params, lower, upper, split_depth, top_depth, rank, world, kw)
+        if tree is None:
+            return np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32)
+        try:
+            lo, hi = tree.nodes(0)
+        finally:
+            tree.close()
+        return np.ascontiguousarray(lo, np.float32).reshape(-1, 3), np.ascontiguousarray(hi, np.float32).reshape(-1, 3)
+    # an injected builder (the CPU tests run the oracle through this): top tree, round-robin deal, one build per frontier box
     if top_depth is None:
         top_depth = default_top_depth(split_depth, world)
     top = build_fn(func, params, lower, upper, split_depth=top_depth, **kw)
     v = top['unknown_node_valid']
     flo, fhi = top['unknown_node_lower'][v], top['unknown_node_upper'][v]
-    mine = deal_boxes(flo.shape[0], rank, world)
-    if injected or len(mine) == 0:
-        los, his = [], []
-        for i in mine:
-            sub = build_fn(func, params, flo[i], fhi[i], split_depth=split_depth - top_depth, **kw)
-            sv = sub['unknown_node_valid']
-            los.append(sub['unknown_node_lower'][sv]); his.append(sub['unknown_node_upper'][sv])
-        lo = np.concatenate(los) if los else np.zeros((0, 3), np.float32)
-        hi = np.concatenate(his) if his else np.zeros((0, 3), np.float32)
-    else:
-        # all of this rank's frontier boxes are refined in ONE level-synchronous build (niq_tree_build_roots)
-        import kd_tree
-        tkw = {k: v for k, v in kw.items() if k in ("offset", "batch_process_size", "ctx")}
-        tree = kd_tree.build_tree(func, params, flo[mine], fhi[mine], split_depth=split_depth - top_depth, **tkw)
-        try:
-            lo, hi = tree.nodes(0)
-        finally:
-            tree.close()
+    los, his = [], []
+    for i in deal_boxes(flo.shape[0], rank, world):
+        sub = build_fn(func, params, flo[i], fhi[i], split_depth=split_depth - top_depth, **kw)
+        sv = sub['unknown_node_valid']
+        los.append(sub['unknown_node_lower'][sv]); his.append(sub['unknown_node_upper'][sv])
+    lo = np.concatenate(los) if los else np.zeros((0, 3), np.float32)
+    hi = np.concatenate(his) if his else np.zeros((0, 3), np.float32)
     return np.ascontiguousarray(lo, np.float32).reshape(-1, 3), np.ascontiguousarray(hi, np.float32).reshape(-1, 3)
 
 

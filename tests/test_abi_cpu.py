@@ -179,3 +179,31 @@ def test_struct_mirrors_do_not_drift(built):
     src = open(os.path.join(ROOT, "include", "niq.h")).read()
     assert len(re.findall(r"NIQ_OP_[A-Z0-9_]+ = \d", src)) == len(_niq._OP_KINDS)
     assert len(re.findall(r"NIQ_MODE_[A-Z0-9_]+ = \d", src)) == len(_niq.MODE_IDS)
+
+
+def test_params_digest_follows_content_not_identity():
+    """The handle cache key (_niq.params_digest): equal content -> equal key whatever the objects; any changed byte, shape,
+    dtype or key name -> another key.  The reference reads `params` afresh on every call (src/main_intersection.py:171-183
+    mutates the transform entries in place), so identity may never be the key."""
+    import _niq
+    p = sample_params("bunny")
+    d = _niq.params_digest(p)
+    assert _niq.params_digest({k: np.array(v) for k, v in p.items()}) == d
+    rng = np.random.default_rng(0)
+    big = [k for k in p if np.asarray(p[k]).nbytes > 256]
+    small = [k for k in p if 0 < np.asarray(p[k]).nbytes <= 256]
+    for k in [big[0], big[-1], small[0]]:
+        for _ in range(8):                                   # one flipped mantissa bit anywhere in the array
+            q = {kk: np.array(v) for kk, v in p.items()}
+            flat = q[k].reshape(-1).view(np.uint32)
+            flat[rng.integers(flat.size)] ^= np.uint32(1)
+            assert _niq.params_digest(q) != d
+    k = big[0]
+    q = dict(p); q[k] = np.ascontiguousarray(p[k].T.reshape(p[k].shape)) if p[k].ndim == 2 else p[k][::-1].copy()
+    assert _niq.params_digest(q) != d or np.array_equal(q[k], p[k])      # permuted entries (a plain sum would not notice)
+    q = dict(p); q[k] = p[k].reshape(-1)
+    assert _niq.params_digest(q) != d                                      # same bytes, another shape
+    q = dict(p); q[k] = p[k].astype(np.float64)
+    assert _niq.params_digest(q) != d
+    q = dict(p); q["9999.extra._"] = np.zeros(0, np.float32)
+    assert _niq.params_digest(q) != d

@@ -861,6 +861,50 @@ def test_tree_multi_root_and_sharded_equal_single_tree():
         kd_tree.build_tree(func, p, np.zeros((2, 2), np.float32), np.ones((2, 2), np.float32), split_depth=2)
 
 
+@pytest.mark.parametrize("name,mode,depth,deal,world,kw", [
+    ("bunny", "affine_fixed", 15, 6, 3, {}),
+    ("bunny", "affine_fixed", 16, 12, 8, {}),            # the default top depth of sharding.tree_sharded
+    ("fox", "interval", 13, 0, 2, {}),                   # deal at the root level: one rank owns the whole tree, the other nothing
+    ("hammer", "slope_interval", 12, 5, 4, dict(offset=0.01)),
+    ("fox", "affine_fixed", 14, 14, 5, {}),              # deal at the last level (classification only, no split)
+    ("bunny", "affine_fixed", 14, 7, 3, dict(batch_process_size=128)),
+])
+def test_tree_dealt_builds_partition_the_single_tree(monkeypatch, name, mode, depth, deal, world, kw):
+    """niq_tree_build_dealt (one persistent launch: replicated top, round-robin deal of the frontier entering level `deal`,
+    own subtrees below): the ranks' leaf sets are disjoint and their union is exactly the leaf set of the single tree; the
+    boxes classified over all ranks = the single tree's below the deal + world x the replicated top.  Also through the
+    capacity-growth relaunch (NIQ_TREE_CAP)."""
+    import _niq
+    import kd_tree
+    p = sample_params(name)
+    func = make(p, mode)
+    st = {}
+    full = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, split_depth=depth, stats=st, **kw)
+    v = full["unknown_node_valid"]
+    want = _canon(full["unknown_node_lower"][v], full["unknown_node_upper"][v])
+    for cap in (None, "64"):
+        if cap:
+            monkeypatch.setenv("NIQ_TREE_CAP", cap)
+        parts, evals = [], 0
+        for rank in range(world):
+            t = kd_tree.build_tree_dealt(func, p, LO, HI, depth, deal, rank, world, **kw)
+            try:
+                parts.append(t.nodes(0))
+                evals += t.stats()["n_evals"]
+            finally:
+                t.close()
+        lo = np.concatenate([a for a, _ in parts]); hi = np.concatenate([b for _, b in parts])
+        got = _canon(lo, hi)
+        assert got.shape == want.shape and np.array_equal(got, want)           # same multiset: no leaf twice, none missing
+        top_boxes = sum(st["level_sizes"][:deal])
+        assert evals == st["n_evals"] + (world - 1) * top_boxes
+    f2 = make(p, "affine_truncate")
+    with pytest.raises(_niq.NiqError):
+        kd_tree.build_tree_dealt(f2, p, LO, HI, 6, 3, 0, 2)                   # no persistent kernel for the growing-form modes
+    with pytest.raises(ValueError):
+        kd_tree.build_tree_dealt(func, p, LO, HI, 6, 7, 0, 2)                  # deal below the split depth
+
+
 @pytest.mark.parametrize("name,mode,kw", [
     ("fox", "affine_fixed", dict(split_depth=11, with_interior_nodes=True, with_exterior_nodes=True, batch_process_size=128)),
     ("bunny", "interval", dict(split_depth=13, with_interior_nodes=True)),
