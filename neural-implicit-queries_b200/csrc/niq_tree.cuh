@@ -50,13 +50,35 @@ struct TreeArgs {
     float offset;
     int want_neg, want_pos, interval;
     // Multi-GPU subtree partition (ours): every rank builds the top of the tree replicated; of the frontier that ENTERS level
-    // deal_level a rank keeps the nodes i = deal_rank (mod deal_world) and drops the rest, so below that level it refines its own
+    // deal_level a rank keeps the nodes deal_owner(i) == deal_rank (below) and drops the rest, so below that level it refines its own
     // subtrees only -- in the same launch, without a host round trip.  deal_world <= 1: no deal.
     long long deal_level;
     int deal_rank, deal_world;
     TreeCtl* ctl;
 };
 constexpr int kTreeDropped = 0x7f;       // label of a node another rank owns (matches no SIGN_* value: every compaction skips it)
+
+// The deal.  Plain round-robin (i mod world) would be the worst choice here: the children of a level are stored
+// [A-children..., B-children...], so the LOW bits of a node's index are its FIRST split decisions -- i mod 8 is the octant of the
+// domain, and a shape that does not fill the octants evenly (measured on bunny.npz, depth 21, 8 ranks) leaves the fullest rank
+// with 1.44x the mean.  Owner = (sum of the base-`world` digits of i) mod world instead: every aligned group of `world`
+// consecutive nodes still gives one node to every rank (so a rank's j-th node is computable), but which member a rank gets
+// rotates with the higher digits, i.e. with the later splits.
+__host__ __device__ __forceinline__ int deal_digit_sum(long long b, int world) {
+    long long s = 0;
+    while (b > 0) { s += b % world; b /= world; }
+    return (int)(s % world);
+}
+__host__ __device__ __forceinline__ int deal_owner(long long i, int world) { return (int)((i % world + deal_digit_sum(i / world, world)) % world); }
+// index of the j-th node owned by `rank` (one per group of `world`)
+__host__ __device__ __forceinline__ long long deal_index(long long j, int rank, int world) {
+    return j * world + ((rank - deal_digit_sum(j, world)) % world + world) % world;
+}
+// nodes of a frontier of n that `rank` owns
+__host__ __device__ __forceinline__ long long deal_count(long long n, int rank, int world) {
+    const long long nb = n / world, rem = n % world;
+    return nb + ((rem > 0 && deal_index(nb, rank, world) - nb * world < rem) ? 1 : 0);
+}
 
 // sense-reversing grid barrier (cooperative launch: all CTAs are co-resident).  __threadfence() is a gpu-scope fence: it
 // orders this CTA's writes before the arrival and invalidates the SM's L1 after the release, so plain loads of data other
@@ -140,11 +162,10 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         // the deal (TreeArgs): at this one level the rank classifies only its own nodes j -> i = rank + j * world; the others
         // are labelled "dropped" and vanish in the compaction of phase 2
         const bool dealing = a.deal_world > 1 && level == a.deal_level;
-        const long long Nc = !dealing ? N : (N > a.deal_rank ? (N - a.deal_rank + a.deal_world - 1) / a.deal_world : 0);
-        const long long i_mul = dealing ? a.deal_world : 1, i_add = dealing ? a.deal_rank : 0;
+        const long long Nc = dealing ? deal_count(N, a.deal_rank, a.deal_world) : N;
         if (dealing)
             for (long long i = (long long)blockIdx.x * kThreads + tid; i < N; i += (long long)gridDim.x * kThreads)
-                if (i % a.deal_world != a.deal_rank) a.label[i] = kTreeDropped;
+                if (deal_owner(i, a.deal_world) != a.deal_rank) a.label[i] = kTreeDropped;
         const bool half = Nc <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
         const int warps_used = half ? kWarps / 2 : kWarps;
         const long long pass_boxes = (long long)warps_used * E::SLOTS;
@@ -154,7 +175,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
             const long long warp_box0 = pass * pass_boxes + (long long)warp * E::SLOTS;
             if (lane < E::SLOTS) {
                 const long long j = warp_box0 + lane;
-                const long long i = j * i_mul + i_add;
+                const long long i = dealing ? deal_index(j, a.deal_rank, a.deal_world) : j;
                 float4 rows[5];
 #pragma unroll
                 for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -182,7 +203,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
 #pragma unroll
                 for (int nn = 0; nn < E::NT; ++nn) {
                     const long long j = warp_box0 + nn * E::G::TPW + eng.t;
-                    const long long i = j * i_mul + i_add;
+                    const long long i = dealing ? deal_index(j, a.deal_rank, a.deal_world) : j;
                     int code = 0xff;
                     if (j < Nc) {
                         float lo_b, up_b;
@@ -215,9 +236,9 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
                 const unsigned b_pos = __ballot_sync(0xffffffffu, lab == SIGN_POSITIVE);
                 const unsigned b_tie = __ballot_sync(0xffffffffu, tie);
                 if (dealing) {
-                    // the slots of a warp pass are `world` nodes apart: they fall into several tiles, each lane counts its own
+                    // the slots of a warp pass are ~`world` nodes apart: they fall into several tiles, each lane counts its own
                     if (lane < E::SLOTS && lab != 0xff) {
-                        const long long tile = ((warp_box0 + lane) * i_mul + i_add) / kTreeTile;
+                        const long long tile = deal_index(warp_box0 + lane, a.deal_rank, a.deal_world) / kTreeTile;
                         if (lab == SIGN_UNKNOWN) atomicAdd(cnt + tile, 1);
                         if (lab == SIGN_NEGATIVE && a.want_neg) atomicAdd(cnt + T + tile, 1);
                         if (lab == SIGN_POSITIVE && a.want_pos) atomicAdd(cnt + 2 * T + tile, 1);

@@ -165,13 +165,23 @@ def default_top_depth(split_depth, world):
 
 
 def deal_boxes(n_boxes, rank, world):
-    """Indices of the frontier boxes (top-of-tree leaves) owned by `rank`: round-robin."""
-    return np.arange(rank, n_boxes, world, dtype=np.int64)
+    """Indices of the frontier boxes (top-of-tree leaves) owned by `rank`: box i goes to (sum of the base-`world` digits of i)
+    mod world -- one box of every aligned group of `world` to each rank, rotating with the higher digits.  (Plain i mod world
+    is the worst deal for a kd-tree frontier: the low bits of a node's index are its FIRST splits, so i mod 8 is the octant of
+    the domain; csrc/niq_tree.cuh deal_owner is the same rule on the device.)"""
+    i = np.arange(n_boxes, dtype=np.int64)
+    if world <= 1:
+        return i
+    s, b = i % world, i // world
+    while np.any(b > 0):
+        s += b % world
+        b //= world
+    return i[s % world == rank]
 
 
 def tree_sharded(func, params, lower, upper, split_depth, top_depth=None, build_fn=None, group=None, to_host=True, **kw):
     """construct_uniform_unknown_levelset_tree with subtrees sharded across ranks: the top `top_depth`
-    levels are built on every rank (replicated, tiny), the surviving frontier is dealt round-robin, each rank
+    levels are built on every rank (replicated, tiny), the surviving frontier is dealt (deal_boxes), each rank
     refines its own boxes to `split_depth`, and the UNKNOWN leaves are all-gathered (24 B/leaf).
     Leaf ORDER differs from the single-device call (canonicalise before comparing).  -> (lower, upper) (L,3).
     to_host=False (NCCL only): return (gathered device tensor (world, 2, cap, 3), per-rank counts) without the read-back."""
@@ -258,11 +268,10 @@ def _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, ran
                 break
             cap = max(counts) * 9 // 8 + 64
         _GATHER_CAP[key] = cap
-        out = out[:, :, 1:]
         if not to_host:
             torch.cuda.current_stream().synchronize()
-            return out, counts
-        out = out.cpu().numpy()
+            return out[:, :, 1:], counts
+        out = out.cpu().numpy()[:, :, 1:]             # one contiguous read-back; the count row is dropped on the host
     finally:
         if tree is not None:
             tree.close()

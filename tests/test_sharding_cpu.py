@@ -130,3 +130,22 @@ def test_sharded_rays_and_tree_world2_gloo():
     canon_t = lambda a: np.unique(np.asarray(a, np.float32).reshape(-1, 9), axis=0)
     assert tris.shape == ref_tris.shape and tris.shape[0] > 100
     np.testing.assert_array_equal(canon_t(tris), canon_t(ref_tris))
+
+
+def test_deal_boxes_is_a_partition_and_mixes_the_low_bits():
+    """sharding.deal_boxes: every box has exactly one owner, every aligned group of `world` boxes gives one box to every rank,
+    and -- the point of the digit-sum rule -- a rank's boxes are spread over all residues i mod world (for a kd-tree frontier
+    i mod 8 is the octant of the domain: plain round-robin would hand each rank one octant)."""
+    import sharding
+    for world in (1, 2, 3, 8):
+        for n in (0, 1, 7, 8, 9, 4096, 5000):
+            owned = [sharding.deal_boxes(n, r, world) for r in range(world)]
+            allb = np.sort(np.concatenate(owned)) if n else np.zeros(0, np.int64)
+            assert np.array_equal(allb, np.arange(n))
+            for r in range(world):
+                groups = owned[r] // world
+                assert np.array_equal(groups, np.arange(len(groups)))           # one per group, in order
+                assert abs(len(owned[r]) - n / world) < 1
+    mine = sharding.deal_boxes(4096, 3, 8)
+    hist = np.bincount(mine % 8, minlength=8)
+    assert hist.min() == hist.max() == 64                                       # all eight "octants" equally
