@@ -267,7 +267,7 @@ def _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, ran
             if max(counts) <= cap:
                 break
             cap = max(counts) * 9 // 8 + 64
-        _GATHER_CAP[key] = cap
+        _GATHER_CAP[key] = max(counts) * 9 // 8 + 64        # follows the tree actually built (another net under the same key)
         if not to_host:
             torch.cuda.current_stream().synchronize()
             return out[:, :, 1:], counts

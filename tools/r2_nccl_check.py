@@ -68,7 +68,7 @@ def main():
     pc = mlps["birdcage_occ"]
     fc = implicit_mlp_utils.generate_implicit_from_params(pc, "affine_fixed")
     q = np.random.default_rng(0).uniform(-1, 1, (1000000, 3)).astype(np.float32)[:512]
-    ms, (cd, cl) = timed(lambda: sharding.closest_point_sharded(fc, pc, lo, hi, q, eps=1e-3), reps=1)
+    ms, (cd, cl) = timed(lambda: sharding.closest_point_sharded(fc, pc, lo, hi, q, eps=1e-3), reps=3)
     rd, rl = kd_tree.closest_point(fc, pc, lo, hi, q, eps=1e-3, batch_process_size=2 ** 26)
     t0 = time.perf_counter(); kd_tree.closest_point(fc, pc, lo, hi, q, eps=1e-3, batch_process_size=2 ** 26); single = (time.perf_counter() - t0) * 1e3
     out["closest_point_sharded_512"] = {"ms": ms, "single_gpu_ms": single, "equal": bool(np.array_equal(cd, rd) and np.array_equal(cl, rl))}
