@@ -167,6 +167,12 @@ int niq_classify_general_boxes(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_
 int niq_classify_boxes(niq_ctx* ctx, const niq_mlp* mlp, const niq_mode_cfg* cfg, int64_t n,
                        const float* lo, const float* hi, float offset,
                        int32_t* label, float* lower, float* upper, uint8_t* near_tie, int mem);
+/* The slope-interval form of f over n general boxes (src/slope_interval.py:15-33 `slope_interval_func` applied to
+ * coordinates_in_general_box(center, vecs), :181-194): raw (n,7) = [primal, slope centre x3, slope width x3] (unused
+ * vectors 0), scale (n) or NULL = the magnitude the primal was summed from.  The reference's min_distance_to_zero /
+ * min_distance_to_zero_in_direction (:52-163) are closed-form in these numbers (slope_interval.py of this package). */
+int niq_slope_forward(niq_ctx* ctx, const niq_mlp* mlp, int64_t n, const float* center, const float* vecs, int32_t v,
+                      float* raw, float* scale, int mem);
 
 /* ---- cast_rays: src/queries.py:39-175 --------------------------------------------------------- */
 /* roots, dirs (n,3) -> t (n) f32, hit_id (n) i32, count (n) i32.  n_evals = the reference's N_evals

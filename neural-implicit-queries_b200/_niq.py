@@ -31,7 +31,7 @@ SYMBOLS = (
     "niq_ctx_launch_count", "niq_ctx_timer_start", "niq_ctx_timer_stop", "niq_ctx_kernel_ms",
     "niq_ctx_kernel_timing", "niq_ctx_exec_macs", "niq_ctx_mc_points", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
     "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
-    "niq_classify_general_boxes", "niq_classify_boxes", "niq_cast_rays", "niq_cast_rays_frustum", "niq_tree_build", "niq_tree_build_roots", "niq_tree_build_dealt", "niq_tree_count",
+    "niq_classify_general_boxes", "niq_classify_boxes", "niq_slope_forward", "niq_cast_rays", "niq_cast_rays_frustum", "niq_tree_build", "niq_tree_build_roots", "niq_tree_build_dealt", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
     "niq_mesh_count", "niq_mesh_copy", "niq_mesh_destroy", "niq_mc_tables", "niq_find_any_intersection",
     "niq_find_any_intersection_batch",

@@ -353,8 +353,10 @@ extern "C" int niq_mlp_create(niq_ctx* c, int32_t n_ops, const niq_op_desc* ops,
             m->min_act_out = std::min(m->min_act_out, L.out_dim); m->n_act_layers += 1;
         }
     }
-    CU(cudaMalloc(&m->d_weights, hw.size() * sizeof(float)));
-    CU(cudaMalloc(&m->d_bias, hb.size() * sizeof(float)));
+    // from the stream-ordered pool (kept across synchronisations, niq_ctx_create): a query that edits a transform makes a new handle
+    // per call, and cudaMalloc / cudaFree are device-wide synchronisation points with occasional long stalls
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&m->d_weights), hw.size() * sizeof(float), c->stream));
+    CU(cudaMallocAsync(reinterpret_cast<void**>(&m->d_bias), hb.size() * sizeof(float), c->stream));
     CU(cudaMemcpyAsync(m->d_weights, hw.data(), hw.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(m->d_bias, hb.data(), hb.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -402,8 +404,8 @@ extern "C" int niq_mlp_destroy(niq_mlp* m) {
     if (!m) return NIQ_OK;
     cudaSetDevice(m->ctx->device);
     cudaStreamSynchronize(m->ctx->stream);
-    if (m->d_weights) cudaFree(m->d_weights);
-    if (m->d_bias) cudaFree(m->d_bias);
+    if (m->d_weights) cudaFreeAsync(m->d_weights, m->ctx->stream);
+    if (m->d_bias) cudaFreeAsync(m->d_bias, m->ctx->stream);
     delete m;
     return NIQ_OK;
 }
@@ -588,6 +590,32 @@ extern "C" int niq_classify_boxes(niq_ctx* c, const niq_mlp* m, const niq_mode_c
     BoxSource src{};
     src.kind = 1; src.v = 3;
     return classify_common(c, m, cfg, n, src, (size_t)n * 12, (size_t)n * 12, lo, hi, offset, label, lower, upper, tie, mem);
+}
+
+// The slope-interval form of the output itself (reference src/slope_interval.py:15-33 `slope_interval_func` on
+// coordinates_in_general_box(center, vecs)): raw (n,7) = [primal, slope centre x3, slope width x3] (unused vectors: 0),
+// scale (n) or NULL = sum_j |h_j A_j| + |b| of the primal's last dot product (the near-tie yardstick).  What the
+// min_distance_to_zero* helpers (:52-163) are computed from on the host side.
+extern "C" int niq_slope_forward(niq_ctx* c, const niq_mlp* m, int64_t n, const float* center, const float* vecs, int32_t v,
+                                 float* raw, float* scale, int mem) {
+    if (!c || !m || n < 0 || (n > 0 && (!center || !vecs || !raw))) return fail(NIQ_EINVAL, "niq_slope_forward: bad argument");
+    if (v < 1) return fail(NIQ_EINVAL, "v must be >= 1");
+    if (v > 3) return fail(NIQ_EUNSUPPORTED, "slope_interval supports v <= 3 box vectors (got %d)", v);
+    if (n == 0) return NIQ_OK;
+    CU(cudaSetDevice(c->device));
+    timer_touch(c);
+    InBuf da(c), db(c); OutBuf dr(c), ds(c);
+    TRY(da.stage(c, center, (size_t)n * 12, mem));
+    TRY(db.stage(c, vecs, (size_t)n * v * 12, mem));
+    TRY(dr.stage(c, raw, (size_t)n * 28, mem));
+    TRY(ds.stage(c, scale, (size_t)n * 4, mem));
+    BoxSource src{};
+    src.kind = 0; src.v = v; src.interval = 0;
+    src.a = da.as<float>(); src.b = db.as<float>();
+    TRY(launch_classify_slope(c, m, src, n, 0.f, nullptr, nullptr, nullptr, nullptr, dr.as<float>(), ds.as<float>()));
+    TRY(dr.flush(c)); TRY(ds.flush(c));
+    FINAL_SYNC(c);
+    return NIQ_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -176,7 +176,7 @@ static bool invert3(const float* R, float* inv) {   // float32 Gauss-Jordan with
 int launch_classify_fixed(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
                           int* label, float* lower, float* upper, unsigned char* tie);
 int launch_classify_slope(niq_ctx* c, const niq_mlp* m, const BoxSource& src, long long n, float offset,
-                          int* label, float* lower, float* upper, unsigned char* tie);
+                          int* label, float* lower, float* upper, unsigned char* tie, float* raw = nullptr, float* raw_scale = nullptr);
 int launch_eval_points(niq_ctx* c, const niq_mlp* m, const PointSource& src, long long n, float* f, float* scale);
 int launch_cast_rays(niq_ctx* c, int wmax, const NetDev& net, int total_floats, const CastOpts& o, long long n, int interval,
                      const float* roots, const float* dirs, float* t, int* hit, int* cnt, unsigned char* tie,

@@ -233,7 +233,7 @@ template <int WMAX>
 __global__ void __launch_bounds__(kThreads, 1)
 k_classify_slope(const __grid_constant__ NetDev net, const BoxSource src, long long n, float offset,
                  int* __restrict__ label, float* __restrict__ lower, float* __restrict__ upper,
-                 unsigned char* __restrict__ near_tie) {
+                 unsigned char* __restrict__ near_tie, float* __restrict__ raw = nullptr, float* __restrict__ raw_scale = nullptr) {
     using E = Engine<WMAX, TileSlope3>;
     extern __shared__ __align__(128) unsigned char smem[];
     E eng(net, smem);
@@ -263,6 +263,11 @@ k_classify_slope(const __grid_constant__ NetDev net, const BoxSource src, long l
                 if (upper) upper[i] = up;
                 if (label) label[i] = label_of(lo, up, offset);
                 if (near_tie) near_tie[i] = bound_near_tie(lo, up, offset, ps[0], net.tie_rel) ? 1 : 0;
+                if (raw) {          // the propagated form itself: [primal, slope centre x3, slope width x3] (niq_slope_forward)
+#pragma unroll
+                    for (int r = 0; r < 7; ++r) raw[7 * i + r] = out[r];
+                }
+                if (raw_scale) raw_scale[i] = ps[0];
             }
         }
         __syncwarp();

@@ -634,6 +634,56 @@ def bound_general_box(params, ctx, center, vecs, chunk=None, return_scale=False)
     return lower, upper
 
 
+def slope_min_distance_to_zero(params, box_center, box_axis_vec):
+    """slope_interval.py:52-78, batched over N axis-aligned boxes (centre, half extents): -> (raw_primal, distance) (N,)."""
+    c = np.ascontiguousarray(box_center, F32).reshape(-1, 3)
+    a = np.ascontiguousarray(box_axis_vec, F32).reshape(-1, 3)
+    center, vecs = box_to_general(c - a, c + a)                     # coordinates_in_box (:177-181)
+    raw_primal, sc, sw, _ = slope_forward(params, center, vecs)
+    sl, su = (sc - sw).astype(F32), (sc + sw).astype(F32)           # slope_bounds (:196-199)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        primal = np.where(raw_primal >= 0, raw_primal, -raw_primal)
+        dec = np.maximum(np.abs(sl), np.abs(su))
+        vec_len = np.abs(a)
+        min_len = vec_len.min(axis=-1)
+        dec = np.maximum((dec / vec_len).astype(F32), F32(0))
+        axis_decrease = ((dec[:, 0] + dec[:, 1]) + dec[:, 2]).astype(F32)
+        dist = np.minimum((primal / axis_decrease).astype(F32), min_len)
+        dist = np.where(dist == 0, F32(0), dist).astype(F32)
+    return raw_primal, dist
+
+
+def slope_min_distance_to_zero_in_direction(params, source_point, bound_vec, source_range=None):
+    """slope_interval.py:81-163, batched over N: -> (source_val, distance), or with source_range (N,k,3):
+    (source_lower, source_upper, distance)."""
+    s = np.ascontiguousarray(source_point, F32).reshape(-1, 3)
+    b = np.ascontiguousarray(bound_vec, F32).reshape(-1, 3)
+    fwd = (b * F32(0.5)).astype(F32)
+    center = (s + fwd).astype(F32)
+    rng = None if source_range is None else np.ascontiguousarray(source_range, F32).reshape(s.shape[0], -1, 3)
+    vecs = fwd[:, None, :] if rng is None else np.concatenate((fwd[:, None, :], rng), axis=1)
+    _, sc, sw, _ = slope_forward(params, center, vecs)
+    sl, su = (sc - sw).astype(F32), (sc + sw).astype(F32)
+    blen = np.sqrt(((b[:, 0] * b[:, 0] + b[:, 1] * b[:, 1]) + b[:, 2] * b[:, 2]).astype(F32)).astype(F32)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if rng is not None:
+            sp, ssc, ssw, _ = slope_forward(params, s, rng)
+            prad = np.maximum(ssc + ssw, -(ssc - ssw)).sum(axis=1, dtype=F32)
+            s_lo, s_up = (sp - prad).astype(F32), (sp + prad).astype(F32)
+            is_pos = s_lo >= 0
+            val = np.where(is_pos, s_lo, -s_up)
+            slope = (F32(2) * np.where(is_pos, sl[:, 0], -su[:, 0]) / blen).astype(F32)
+            dist = np.minimum((val / np.maximum(-slope, F32(0))).astype(F32), blen)
+            dist = np.where((s_lo <= 0) & (s_up >= 0), F32(0), dist).astype(F32)
+            return s_lo, s_up, dist
+        sval = eval_points(params, s).astype(F32)
+        is_pos = sval >= 0
+        slope = (F32(2) * np.where(is_pos, sl[:, 0], -su[:, 0]) / blen).astype(F32)
+        dist = np.minimum((np.abs(sval) / np.maximum(-slope, F32(0))).astype(F32), blen)
+        dist = np.where(sval == 0, F32(0), dist).astype(F32)
+    return sval, dist
+
+
 def labels_from_bounds(lower, upper, offset=0.0):
     """affine.py:49-53: POSITIVE if lower > offset, then NEGATIVE if upper < -offset (wins)."""
     offset = F32(offset)

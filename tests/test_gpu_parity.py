@@ -445,14 +445,36 @@ def test_params_are_read_afresh_each_call():
     np.testing.assert_allclose(f1, f1_ref, rtol=1e-5)
 
 
+@pytest.mark.parametrize("name", ["fox", "bunny"])
+def test_slope_min_distance_helpers(name):
+    """SlopeIntervalImplicitFunction.min_distance_to_zero / min_distance_to_zero_in_direction (src/slope_interval.py:52-163) on
+    the CUDA path (niq_slope_forward + the reference's closed-form arithmetic) against the goldens of the unmodified reference,
+    with the checker the oracle is pinned by; a single box / ray must return scalars like the reference."""
+    import implicit_mlp_utils
+    from test_oracle_golden import check_min_distance
+    p = sample_params(name)
+    f = implicit_mlp_utils.generate_implicit_from_params(p, "slope_interval")
+    g = golden(f"mindist_{name}_slope")
+    rep = {}
+    check_min_distance(p, g, lambda pp, c, a: f.min_distance_to_zero(pp, c, a, return_source_value=True),
+                       lambda pp, s, b, r: f.min_distance_to_zero_in_direction(pp, s, b, source_range=r, return_source_value=True),
+                       net.tie_rel(p), report=rep)
+    parity_report(f"slope_min_distance[{name}]", max_rel_distance_error=rep)
+    d1 = f.min_distance_to_zero(p, g["box_center"][3], g["box_axis_vec"][3])
+    assert np.ndim(d1) == 0 and d1 == f.min_distance_to_zero(p, g["box_center"], g["box_axis_vec"])[3]
+    v1, r1 = f.min_distance_to_zero_in_direction(p, g["source"][5], g["bound_vec"][5], return_source_value=True)
+    assert np.ndim(r1) == 0 and r1 == f.min_distance_to_zero_in_direction(p, g["source"], g["bound_vec"])[5]
+
+
 def test_unsupported_and_invalid_arguments():
     import _niq
     import implicit_mlp_utils
     p = sample_params("fox")
     with pytest.raises(RuntimeError):
         implicit_mlp_utils.generate_implicit_from_params(p, "tanh_interval")          # not a mode of the reference
-    with pytest.raises(_niq.NiqError):                                              # not built
-        implicit_mlp_utils.generate_implicit_from_params(p, "slope_interval").min_distance_to_zero(p, LO, HI)
+    with pytest.raises(_niq.NiqError):                                              # more than 3 box vectors: forward + 3 source-range vectors
+        implicit_mlp_utils.generate_implicit_from_params(p, "slope_interval").min_distance_to_zero_in_direction(
+            p, LO, HI, source_range=np.eye(3, dtype=np.float32) * 0.01)
     f = implicit_mlp_utils.generate_implicit_from_params(p, "affine_truncate", affine_n_truncate=8,
                                                          affine_truncate_policy="relative")
     with pytest.raises(_niq.NiqError):

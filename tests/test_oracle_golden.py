@@ -133,6 +133,61 @@ def test_classify_slope_interval(name):
     assert_labels(lab, g["xf_label"], lo, up, sc)
 
 
+def check_min_distance(p, g, box_fn, dir_fn, rtol, report=None):
+    """Shared by the oracle (here) and the CUDA backend (tests/test_gpu_parity.py): the distance helpers of the slope-interval
+    bounder against the goldens of the unmodified reference.  A source value must lie within the band of the magnitude it was
+    summed from; a distance is value / slope, so its error is the value's band over the slope = distance * scale / |value|
+    (+ the slope's own band): checked with a factor 4 of head room.  "Contains zero" verdicts must agree unless a source bound
+    lies within the band of 0."""
+    f64 = np.float64
+
+    def close(a, b, tol):
+        a, b = np.asarray(a, f64), np.asarray(b, f64)
+        return bool(np.all((np.isnan(a) == np.isnan(b)) & (np.isnan(a) | (np.abs(a - b) <= tol))))
+
+    worst = {}
+    prim, dist = box_fn(p, g["box_center"], g["box_axis_vec"])
+    sc = rays.point_scale(p, g["box_center"]).astype(f64)
+    assert close(prim, g["box_primal"], rtol * sc)
+    cap = np.abs(g["box_axis_vec"]).min(axis=1)
+    gd = np.abs(g["box_distance"]).astype(f64)
+    assert close(dist, g["box_distance"], 4 * rtol * gd * (2 + sc / np.maximum(np.abs(g["box_primal"]), 1e-30)))
+    assert np.all(np.asarray(dist) <= cap) and np.all(np.asarray(dist) >= 0)
+    worst["box"] = float(np.max(np.abs(np.asarray(dist, f64) - g["box_distance"]) / np.maximum(gd, 1e-30)))
+    val, d = dir_fn(p, g["source"], g["bound_vec"], None)
+    ssc = rays.point_scale(p, g["source"]).astype(f64)
+    assert close(val, g["ray_value"], rtol * ssc)
+    gd = np.abs(g["ray_distance"]).astype(f64)
+    assert close(d, g["ray_distance"], 4 * rtol * gd * (2 + ssc / np.maximum(np.abs(g["ray_value"]), 1e-30)))
+    assert np.all(np.asarray(d, f64) <= np.linalg.norm(g["bound_vec"].astype(f64), axis=1) * (1 + 1e-6))
+    worst["ray"] = float(np.max(np.abs(np.asarray(d, f64) - g["ray_distance"]) / np.maximum(gd, 1e-30)))
+    for k, key in ((1, "swept1"), (2, "swept2")):
+        lo, up, d = dir_fn(p, g["source"], g["bound_vec"], g["source_range"][:, :k])
+        G = g[key].astype(f64)
+        bsc = net.tol_scale(G[:, 0].astype(np.float32), G[:, 1].astype(np.float32), ssc.astype(np.float32)).astype(f64)
+        assert close(lo, G[:, 0], rtol * bsc) and close(up, G[:, 1], rtol * bsc)
+        zero = (G[:, 0] <= 0) & (G[:, 1] >= 0)
+        v = np.minimum(np.abs(G[:, 0]), np.abs(G[:, 1]))
+        near = v <= rtol * bsc
+        assert np.array_equal((np.asarray(d) == 0)[~near], (G[:, 2] == 0)[~near])
+        sel = ~zero & ~near
+        assert close(np.asarray(d)[sel], G[sel, 2], 4 * rtol * np.abs(G[sel, 2]) * (2 + bsc[sel] / np.maximum(v[sel], 1e-30)))
+        worst[key] = float(np.max(np.abs(np.asarray(d, f64)[sel] - G[sel, 2]) / np.maximum(np.abs(G[sel, 2]), 1e-30))) if sel.any() else 0.0
+    if report is not None:
+        report.update(worst)
+    return worst
+
+
+@pytest.mark.parametrize("name", ["fox", "bunny"])
+def test_slope_min_distance_helpers(name):
+    """The distance helpers of the slope-interval bounder (src/slope_interval.py:52-163: min_distance_to_zero for axis-aligned
+    boxes, min_distance_to_zero_in_direction for a ray and for a swept box with 1 / 2 source-range vectors): the oracle's
+    restatement against the run of the unmodified reference."""
+    p = sample_params(name)
+    check_min_distance(p, golden(f"mindist_{name}_slope"), net.slope_min_distance_to_zero,
+                       lambda pp, s, b, r: net.slope_min_distance_to_zero_in_direction(pp, s, b, r), net.tie_rel(p))
+
+
 PE_MODES = ("interval", "affine_fixed", "affine_truncate", "affine_all", "slope_interval")
 
 
