@@ -94,19 +94,24 @@ def cast_rays_sharded(funcs_tuple, params_tuple, roots, dirs, opts, res_x, res_y
         out_t[idx] = out[r, 0, :sizes[r]].view(np.float32)
         out_h[idx] = out[r, 1, :sizes[r]]
         out_c[idx] = out[r, 2, :sizes[r]]
-    return out_t, out_h, out_c, replay_n_evals(out_c, opts)
+    # the replay needs the step counts of the rays that were cast + how many pixels nobody cast (count 0): on a stated sub-sample
+    # of the tiles that is 4 % of the image, and a histogram over all 2 M pixels would cost more than the gather
+    cast_counts = np.concatenate([out[r, 2, :sizes[r]] for r in range(world)])
+    return out_t, out_h, out_c, replay_n_evals(cast_counts, opts, n_zero=n - int(cast_counts.shape[0]))
 
 
-def replay_n_evals(count, opts):
+def replay_n_evals(count, opts, n_zero=0):
     """N_evals of src/queries.py:137,164-173 from the per-ray step counts of the whole image: every iteration evaluates
     the current padded array (n_substeps lanes each), which shrinks to the next bucket size whenever the live rays fit
-    (src/bucketing.py:7-14,35-36).  The same replay niq_cast_rays does for one device."""
+    (src/bucketing.py:7-14,35-36).  The same replay niq_cast_rays does for one device.  `n_zero`: further rays of the image
+    with a step count of 0 that are not listed in `count`."""
     from bucketing import get_next_bucket_size
     n_sub = int(opts['n_substeps'])
     n_bins = int(opts['n_max_step']) // n_sub + 3
     it = np.minimum((np.asarray(count, np.int64) + n_sub - 1) // n_sub, n_bins - 1)
     hist = np.bincount(it, minlength=n_bins)
-    cur = valid = int(it.shape[0])
+    hist[0] += int(n_zero)
+    cur = valid = int(it.shape[0]) + int(n_zero)
     evals = 0
     for k in range(1, n_bins):
         if valid <= 0:
