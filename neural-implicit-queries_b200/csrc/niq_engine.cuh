@@ -446,7 +446,7 @@ struct Engine {
             // one warp's epilogue overlap the other's main loop, and with no CTA barrier it stays that way.
             if (warp >= 4) {
                 const long long t0 = clock64();
-                const long long wait_cycles = 40ll * net.layers[net.n_layers > 1 ? 1 : 0].in_pad;
+                const long long wait_cycles = net.dephase > 0 ? (long long)net.dephase : 40ll * net.layers[net.n_layers > 1 ? 1 : 0].in_pad;
                 while (clock64() - t0 < wait_cycles) {}
             }
         } else if (threadIdx.x == 0) {

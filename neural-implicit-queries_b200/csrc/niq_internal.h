@@ -109,6 +109,11 @@ constexpr int kResidentPad = 512;   // floats after the resident weights: the pi
 template <class E>
 static size_t place_weights(niq_ctx* c, NetDev& net, int total_floats) {
     net.exec_macs = c->count_exec ? c->d_exec : nullptr;
+    {   // development knob: head start (cycles) of warps 0-3 over warps 4-7 (streamed ray kernels; resident nets: overrides the
+        // default of half a layer, niq_engine.cuh)
+        const char* e = getenv("NIQ_DEPHASE");
+        net.dephase = e ? atoi(e) : 0;
+    }
     const size_t res = E::smem_bytes(total_floats + kResidentPad);
     if (res <= c->prop.sharedMemPerBlockOptin) {
         net.resident = 1;
@@ -116,10 +121,6 @@ static size_t place_weights(niq_ctx* c, NetDev& net, int total_floats) {
         return res;
     }
     net.resident = 0;
-    {   // development knob: head start (cycles) of warps 0-3 over warps 4-7 in the streamed ray kernel
-        const char* e = getenv("NIQ_DEPHASE");
-        net.dephase = e ? atoi(e) : 0;
-    }
     return E::smem_bytes();
 }
 
