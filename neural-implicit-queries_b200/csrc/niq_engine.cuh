@@ -197,6 +197,10 @@ struct TileRaySlope { // [P, C, W, pt, pt] : one ray step in slope_interval mode
     static constexpr bool has_group = false;
 };
 
+// the same rows with ONE tile per thread (niq_tree.cuh: the small levels of a tree)
+template <class Tile>
+struct TileOne : Tile { static constexpr int NT = 1; };
+
 // ------------------------------------------------------------------------------------------------
 // scalar activation rules
 // ------------------------------------------------------------------------------------------------

@@ -16,6 +16,8 @@
 // Capacity: the buffers are sized by the host; a level that would not fit stops the kernel with its frontier intact, the
 // host grows the buffers and relaunches from that level.
 #pragma once
+#include <type_traits>
+
 #include "niq_kernels.cuh"
 
 namespace niq {
@@ -129,6 +131,13 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
     __shared__ long long s_red[kThreads / 32];
     __shared__ int s_warp[kThreads / 32];
     E eng(net, smem);
+    // Small levels of RESIDENT nets run on a second engine over the same staged weights that holds ONE tile per thread instead
+    // of two (half the FFMA2s and half the epilogue per pass): the top of a tree is pure latency, and a warp whose second tile is
+    // empty pays for it all the same.  (Streamed nets keep the one engine: two engines cannot share the ring's state.)
+    using E1 = Engine<WMAX, TileOne<Tile>>;
+    // (Not for the zero-skipping width classes: their per-warp lists live in the activation region the two engines share.)
+    constexpr bool kHasE1 = Tile::NT > 1 && !E::kSparse;
+    E1 eng1(net, smem, false);
     const int tid = threadIdx.x, lane = eng.lane, warp = eng.warp;
     // phase-2 scratch: the CTA's activation buffers are idle between passes (every warp is in phase 2 then)
     int* s_scan = reinterpret_cast<int*>(eng.act - warp * E::WARP_FLOATS);       // [kTreeTile + 1]
@@ -166,93 +175,100 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         if (dealing)
             for (long long i = (long long)blockIdx.x * kThreads + tid; i < N; i += (long long)gridDim.x * kThreads)
                 if (deal_owner(i, a.deal_world) != a.deal_rank) a.label[i] = kTreeDropped;
-        const bool half = Nc <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
-        const int warps_used = half ? kWarps / 2 : kWarps;
-        const long long pass_boxes = (long long)warps_used * E::SLOTS;
-        const long long n_pass = (Nc + pass_boxes - 1) / pass_boxes;
-        for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
-            if (warp >= warps_used) { eng.skip_net(0, net.n_layers); continue; }
-            const long long warp_box0 = pass * pass_boxes + (long long)warp * E::SLOTS;
-            if (lane < E::SLOTS) {
-                const long long j = warp_box0 + lane;
-                const long long i = dealing ? deal_index(j, a.deal_rank, a.deal_world) : j;
-                float4 rows[5];
-#pragma unroll
-                for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (j < Nc) {
-                    BoxSource src{};
-                    src.kind = 1; src.v = 3; src.a = cur_lo; src.b = cur_hi;
-                    src.interval = Tile::rule == 2 ? 0 : a.interval;
-                    load_box_rows(src, i, rows);
-                }
-                float* dst = eng.slot_ptr(lane);
-                if (Tile::rule == 2) {       // slope_interval: [primal, centre x3, width x3 = 0]
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
-#pragma unroll
-                    for (int r = 4; r < RT; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = make_float4(0.f, 0.f, 0.f, 0.f);
-                } else {
-#pragma unroll
-                    for (int r = 0; r < 5; ++r) *reinterpret_cast<float4*>(dst + r * E::G::S) = rows[r];
-                }
-            }
-            __syncwarp();
-            float out[E::ROWS], ps[E::ROWS];
-            eng.run_net(0, net.n_layers, out, ps);
-            if (eng.cg == 0) {      // label + near-tie flag of every slot, handed to lane `slot` through the warp's scratch
-#pragma unroll
-                for (int nn = 0; nn < E::NT; ++nn) {
-                    const long long j = warp_box0 + nn * E::G::TPW + eng.t;
+        auto run_passes = [&](auto& en, int warps_used) {
+            using EE = typename std::remove_reference<decltype(en)>::type;
+            const long long pass_boxes = (long long)warps_used * EE::SLOTS;
+            const long long n_pass = (Nc + pass_boxes - 1) / pass_boxes;
+            for (long long pass = blockIdx.x; pass < n_pass; pass += gridDim.x) {
+                if (warp >= warps_used) { en.skip_net(0, net.n_layers); continue; }
+                const long long warp_box0 = pass * pass_boxes + (long long)warp * EE::SLOTS;
+                if (lane < EE::SLOTS) {
+                    const long long j = warp_box0 + lane;
                     const long long i = dealing ? deal_index(j, a.deal_rank, a.deal_world) : j;
-                    int code = 0xff;
+                    float4 rows[5];
+    #pragma unroll
+                    for (int r = 0; r < 5; ++r) rows[r] = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (j < Nc) {
-                        float lo_b, up_b;
-                        if (Tile::rule == 2) {     // src/slope_interval.py:201-206
-                            float prad = 0.f;
-#pragma unroll
-                            for (int v = 0; v < 3; ++v)
-                                prad = prad + fmaxf(out[nn * RT + 1 + v] + out[nn * RT + 4 + v], -(out[nn * RT + 1 + v] - out[nn * RT + 4 + v]));
-                            lo_b = out[nn * RT] - prad; up_b = out[nn * RT] + prad;
-                        } else {                   // src/affine.py:119-125
-                            const float rad = ((fabsf(out[nn * RT + 1]) + fabsf(out[nn * RT + 2])) + fabsf(out[nn * RT + 3])) + out[nn * RT + 4];
-                            lo_b = out[nn * RT] - rad; up_b = out[nn * RT] + rad;
+                        BoxSource src{};
+                        src.kind = 1; src.v = 3; src.a = cur_lo; src.b = cur_hi;
+                        src.interval = Tile::rule == 2 ? 0 : a.interval;
+                        load_box_rows(src, i, rows);
+                    }
+                    float* dst = en.slot_ptr(lane);
+                    if (Tile::rule == 2) {       // slope_interval: [primal, centre x3, width x3 = 0]
+    #pragma unroll
+                        for (int r = 0; r < 4; ++r) *reinterpret_cast<float4*>(dst + r * EE::G::S) = rows[r];
+    #pragma unroll
+                        for (int r = 4; r < RT; ++r) *reinterpret_cast<float4*>(dst + r * EE::G::S) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    } else {
+    #pragma unroll
+                        for (int r = 0; r < 5; ++r) *reinterpret_cast<float4*>(dst + r * EE::G::S) = rows[r];
+                    }
+                }
+                __syncwarp();
+                float out[EE::ROWS], ps[EE::ROWS];
+                en.run_net(0, net.n_layers, out, ps);
+                if (en.cg == 0) {      // label + near-tie flag of every slot, handed to lane `slot` through the warp's scratch
+    #pragma unroll
+                    for (int nn = 0; nn < EE::NT; ++nn) {
+                        const long long j = warp_box0 + nn * EE::G::TPW + en.t;
+                        const long long i = dealing ? deal_index(j, a.deal_rank, a.deal_world) : j;
+                        int code = 0xff;
+                        if (j < Nc) {
+                            float lo_b, up_b;
+                            if (Tile::rule == 2) {     // src/slope_interval.py:201-206
+                                float prad = 0.f;
+    #pragma unroll
+                                for (int v = 0; v < 3; ++v)
+                                    prad = prad + fmaxf(out[nn * RT + 1 + v] + out[nn * RT + 4 + v], -(out[nn * RT + 1 + v] - out[nn * RT + 4 + v]));
+                                lo_b = out[nn * RT] - prad; up_b = out[nn * RT] + prad;
+                            } else {                   // src/affine.py:119-125
+                                const float rad = ((fabsf(out[nn * RT + 1]) + fabsf(out[nn * RT + 2])) + fabsf(out[nn * RT + 3])) + out[nn * RT + 4];
+                                lo_b = out[nn * RT] - rad; up_b = out[nn * RT] + rad;
+                            }
+                            const int lab = label_of(lo_b, up_b, a.offset);
+                            a.label[i] = lab;
+                            code = lab | (bound_near_tie(lo_b, up_b, a.offset, ps[nn * RT], net.tie_rel) ? 0x100 : 0);
                         }
-                        const int lab = label_of(lo_b, up_b, a.offset);
-                        a.label[i] = lab;
-                        code = lab | (bound_near_tie(lo_b, up_b, a.offset, ps[nn * RT], net.tie_rel) ? 0x100 : 0);
+                        en.fin[(nn * EE::G::TPW + en.t) * 8] = __int_as_float(code);
                     }
-                    eng.fin[(nn * E::G::TPW + eng.t) * 8] = __int_as_float(code);
                 }
-            }
-            __syncwarp();
-            {   // lane s < SLOTS counts slot s (all slots of a warp pass lie in one tile: 2048 % CTA_TILES == 0)
-                int lab = 0xff; bool tie = false;
-                if (lane < E::SLOTS) {
-                    const int code = __float_as_int(eng.fin[lane * 8]);
-                    lab = code & 0xff; tie = (code & 0x100) != 0;
-                }
-                const unsigned b_unk = __ballot_sync(0xffffffffu, lab == SIGN_UNKNOWN);
-                const unsigned b_neg = __ballot_sync(0xffffffffu, lab == SIGN_NEGATIVE);
-                const unsigned b_pos = __ballot_sync(0xffffffffu, lab == SIGN_POSITIVE);
-                const unsigned b_tie = __ballot_sync(0xffffffffu, tie);
-                if (dealing) {
-                    // the slots of a warp pass are ~`world` nodes apart: they fall into several tiles, each lane counts its own
-                    if (lane < E::SLOTS && lab != 0xff) {
-                        const long long tile = deal_index(warp_box0 + lane, a.deal_rank, a.deal_world) / kTreeTile;
-                        if (lab == SIGN_UNKNOWN) atomicAdd(cnt + tile, 1);
-                        if (lab == SIGN_NEGATIVE && a.want_neg) atomicAdd(cnt + T + tile, 1);
-                        if (lab == SIGN_POSITIVE && a.want_pos) atomicAdd(cnt + 2 * T + tile, 1);
+                __syncwarp();
+                {   // lane s < SLOTS counts slot s (all slots of a warp pass lie in one tile: 2048 % CTA_TILES == 0)
+                    int lab = 0xff; bool tie = false;
+                    if (lane < EE::SLOTS) {
+                        const int code = __float_as_int(en.fin[lane * 8]);
+                        lab = code & 0xff; tie = (code & 0x100) != 0;
                     }
-                    if (lane == 0 && b_tie) atomicAdd(&a.ctl->n_tie_level, (unsigned long long)__popc(b_tie));
-                } else if (lane == 0 && warp_box0 < N) {
-                    const long long tile = warp_box0 / kTreeTile;
-                    if (b_unk) atomicAdd(cnt + tile, __popc(b_unk));
-                    if (b_neg && a.want_neg) atomicAdd(cnt + T + tile, __popc(b_neg));
-                    if (b_pos && a.want_pos) atomicAdd(cnt + 2 * T + tile, __popc(b_pos));
-                    if (b_tie) atomicAdd(&a.ctl->n_tie_level, (unsigned long long)__popc(b_tie));
+                    const unsigned b_unk = __ballot_sync(0xffffffffu, lab == SIGN_UNKNOWN);
+                    const unsigned b_neg = __ballot_sync(0xffffffffu, lab == SIGN_NEGATIVE);
+                    const unsigned b_pos = __ballot_sync(0xffffffffu, lab == SIGN_POSITIVE);
+                    const unsigned b_tie = __ballot_sync(0xffffffffu, tie);
+                    if (dealing) {
+                        // the slots of a warp pass are ~`world` nodes apart: they fall into several tiles, each lane counts its own
+                        if (lane < EE::SLOTS && lab != 0xff) {
+                            const long long tile = deal_index(warp_box0 + lane, a.deal_rank, a.deal_world) / kTreeTile;
+                            if (lab == SIGN_UNKNOWN) atomicAdd(cnt + tile, 1);
+                            if (lab == SIGN_NEGATIVE && a.want_neg) atomicAdd(cnt + T + tile, 1);
+                            if (lab == SIGN_POSITIVE && a.want_pos) atomicAdd(cnt + 2 * T + tile, 1);
+                        }
+                        if (lane == 0 && b_tie) atomicAdd(&a.ctl->n_tie_level, (unsigned long long)__popc(b_tie));
+                    } else if (lane == 0 && warp_box0 < N) {
+                        const long long tile = warp_box0 / kTreeTile;
+                        if (b_unk) atomicAdd(cnt + tile, __popc(b_unk));
+                        if (b_neg && a.want_neg) atomicAdd(cnt + T + tile, __popc(b_neg));
+                        if (b_pos && a.want_pos) atomicAdd(cnt + 2 * T + tile, __popc(b_pos));
+                        if (b_tie) atomicAdd(&a.ctl->n_tie_level, (unsigned long long)__popc(b_tie));
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
+        };
+        if (kHasE1 && eng.resident && Nc <= (long long)gridDim.x * (kWarps / 2) * E1::SLOTS) {
+            run_passes(eng1, kWarps / 2);
+        } else {
+            const bool half = Nc <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
+            run_passes(eng, half ? kWarps / 2 : kWarps);
         }
         grid_barrier(a.ctl);
 
@@ -419,6 +435,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         c->status = status; c->need = need; c->n_evals = n_evals; c->max_frontier = max_frontier; c->n_tie = n_tie;
         c->level = level;                        // = levels processed so far
     }
+    if (kHasE1 && eng.resident) eng1.drain();      // resident: only adds its executed-MAC count
     eng.drain();
 }
 
