@@ -131,12 +131,12 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
     __shared__ long long s_red[kThreads / 32];
     __shared__ int s_warp[kThreads / 32];
     E eng(net, smem);
-    // Small levels of RESIDENT nets run on a second engine over the same staged weights that holds ONE tile per thread instead
-    // of two (half the FFMA2s and half the epilogue per pass): the top of a tree is pure latency, and a warp whose second tile is
-    // empty pays for it all the same.  (Streamed nets keep the one engine: two engines cannot share the ring's state.)
+    // Small levels run on a second engine over the same weights (resident set or streamed ring) that holds ONE tile per thread
+    // instead of two (half the FFMA2s and half the epilogue per pass): the top of a tree is pure latency, and a warp whose second
+    // tile is empty pays for it all the same.  The two engines are never in a pass at the same time; they share the shared-memory
+    // activation region, and for streamed weights the position in the chunk sequence is handed back and forth.
     using E1 = Engine<WMAX, TileOne<Tile>>;
-    // (Not for the zero-skipping width classes: their per-warp lists live in the activation region the two engines share.)
-    constexpr bool kHasE1 = Tile::NT > 1 && !E::kSparse;
+    constexpr bool kHasE1 = Tile::NT > 1;
     E1 eng1(net, smem, false);
     const int tid = threadIdx.x, lane = eng.lane, warp = eng.warp;
     // phase-2 scratch: the CTA's activation buffers are idle between passes (every warp is in phase 2 then)
@@ -264,8 +264,16 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
                 __syncwarp();
             }
         };
-        if (kHasE1 && eng.resident && Nc <= (long long)gridDim.x * (kWarps / 2) * E1::SLOTS) {
+        if (kHasE1 && Nc <= (long long)gridDim.x * (kWarps / 2) * E1::SLOTS) {
+            if (E1::kSparse) {
+                // the zero-skipping lists of this engine live where the other engine keeps activations: make every entry a valid
+                // offset again (the K loop's look-ahead reads run past a segment's end)
+                for (int i = lane; i < E1::LIST_WORDS; i += 32) eng1.lst[i] = 0u;
+                __syncwarp();
+            }
+            eng1.seq_consumed = eng.seq_consumed;
             run_passes(eng1, kWarps / 2);
+            eng.seq_consumed = eng1.seq_consumed;
         } else {
             const bool half = Nc <= (long long)gridDim.x * (kWarps / 2) * E::SLOTS;
             run_passes(eng, half ? kWarps / 2 : kWarps);
@@ -435,7 +443,7 @@ k_tree_persistent(const __grid_constant__ NetDev net, const TreeArgs a) {
         c->status = status; c->need = need; c->n_evals = n_evals; c->max_frontier = max_frontier; c->n_tie = n_tie;
         c->level = level;                        // = levels processed so far
     }
-    if (kHasE1 && eng.resident) eng1.drain();      // resident: only adds its executed-MAC count
+    if (kHasE1) eng.exec_macs += eng1.exec_macs;   // one drain: it owns the ring and reports the executed-MAC count of both
     eng.drain();
 }
 
