@@ -2,14 +2,14 @@
 # bench arms as the driver runs them, ncu launch list, one full capture of the dealt tree kernel, sanitizer on the dealt build
 set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r2d_smi.txt
-timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r2d_pytest_gpu.log 2>&1
-tail -6 gpurun_out/r2d_pytest_gpu.log
-timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2d_smoke.log 2>&1; tail -2 gpurun_out/r2d_smoke.log
-timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2d_bench_ref.json 2> gpurun_out/r2d_bench_ref.err
-timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2d_bench_n1.json 2> gpurun_out/r2d_bench_n1.err
-tail -c 600 gpurun_out/r2d_bench_n1.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2d_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r2d_bench_under_ncu.log 2>&1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/r2e_smi.txt
+timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/r2e_pytest_gpu.log 2>&1
+tail -6 gpurun_out/r2e_pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2e_smoke.log 2>&1; tail -2 gpurun_out/r2e_smoke.log
+timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2e_bench_ref.json 2> gpurun_out/r2e_bench_ref.err
+timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r2e_bench_n1.json 2> gpurun_out/r2e_bench_n1.err
+tail -c 600 gpurun_out/r2e_bench_n1.err
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r2e_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/r2e_bench_under_ncu.log 2>&1
 cat > /tmp/dealt_small.py <<'PY'
 import sys, numpy as np
 sys.path[:0] = ["oracle", "neural-implicit-queries_b200", "."]
@@ -26,7 +26,7 @@ for r in range(2):
 print(n)
 PY
 NCU="ncu --set full --clock-control none --import-source on -f"
-timeout 600 $NCU -k regex:k_tree_persistent -c 1 -o gpurun_out/r2d_tree_dealt python /tmp/dealt_small.py 21 > gpurun_out/r2d_ncu_tree.log 2>&1
-compute-sanitizer --tool memcheck python /tmp/dealt_small.py 15 > gpurun_out/r2d_memcheck_tree_dealt.txt 2>&1; tail -1 gpurun_out/r2d_memcheck_tree_dealt.txt
-compute-sanitizer --tool synccheck python /tmp/dealt_small.py 15 > gpurun_out/r2d_synccheck_tree_dealt.txt 2>&1; tail -1 gpurun_out/r2d_synccheck_tree_dealt.txt
-ls -la gpurun_out/r2d_*
+timeout 600 $NCU -k regex:k_tree_persistent -c 1 -o gpurun_out/r2e_tree_dealt python /tmp/dealt_small.py 21 > gpurun_out/r2e_ncu_tree.log 2>&1
+compute-sanitizer --tool memcheck python /tmp/dealt_small.py 15 > gpurun_out/r2e_memcheck_tree_dealt.txt 2>&1; tail -1 gpurun_out/r2e_memcheck_tree_dealt.txt
+compute-sanitizer --tool synccheck python /tmp/dealt_small.py 15 > gpurun_out/r2e_synccheck_tree_dealt.txt 2>&1; tail -1 gpurun_out/r2e_synccheck_tree_dealt.txt
+ls -la gpurun_out/r2e_*
