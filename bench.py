@@ -449,6 +449,20 @@ def run_ours(args):
         full_image = {"rays_this_rank": nf, "ms": ms_full, "rays_per_s_this_rank": nf / (ms_full * 1e-3),
                       "ray_steps": int(cf.sum().item()), "hits": int((hf != 0).sum().item())}
         del rf, df, tf_, hf, cf
+        if world > 1:
+            # whole job: the slowest rank's share sets the time; and once through the public sharded call (host rays in, the whole
+            # image back on the host of every rank, one NCCL all_gather of the device-resident results)
+            mx = torch.tensor([ms_full], dtype=torch.float64, device=dev)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            barrier()
+            t0 = time.perf_counter()
+            ft, fh, fc, _ = sharding.cast_rays_sharded((func,), (params,), roots, dirs, opts, RES_X, RES_Y, TILE)
+            barrier()
+            e2e_full = time.perf_counter() - t0
+            full_image.update({"ms_max_over_ranks": float(mx.item()), "rays": RES_X * RES_Y,
+                               "rays_per_s": RES_X * RES_Y / (float(mx.item()) * 1e-3),
+                               "e2e_s": e2e_full, "e2e_rays_per_s": RES_X * RES_Y / e2e_full,
+                               "e2e_ray_steps": int(fc.sum()), "e2e_hits": int((fh != 0).sum())})
 
     if world > 1:
         red = torch.tensor([total_ms, e2e_s, kernel_ms, d21_s, d21_host_s, own_s, own_dev_ms, own_boxes, d14_sh_s], dtype=torch.float64, device=dev)
