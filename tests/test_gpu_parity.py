@@ -956,6 +956,47 @@ def test_tree_persistent_kernel_equals_level_loop(monkeypatch, name, mode, kw):
     assert int(a["unknown_node_valid"].sum()) > 0
 
 
+@pytest.mark.parametrize("layers,act,mode,depth", [
+    ([3, 128, 128, 1], "relu", "affine_fixed", 13),        # resident weights + zero-skipping lists + the one-tile engine
+    ([3, 256, 256, 1], "relu", "affine_fixed", 12),        # 256-wide, still resident
+    ([3, 256, 256, 256, 256, 1], "relu", "interval", 11),  # streamed ring shared by the two engines
+    ([3, 128, 128, 128, 1], "elu", "affine_fixed", 11),    # 128-wide without zero-skipping (elu)
+])
+def test_tree_small_levels_on_the_one_tile_engine(monkeypatch, layers, act, mode, depth):
+    """The tree kernel runs small levels on a second engine with ONE tile per thread (niq_tree.cuh; for streamed weights the
+    two engines hand the ring position back and forth, for the zero-skipping width classes the one-tile engine's lists are
+    re-initialised before every use).  Random-init nets of the width classes the sample MLPs do not reach: the persistent
+    kernel must equal the per-level host loop bit for bit (arrays, order, per-level counts), and a dealt build -- whose
+    frontier SHRINKS at the deal level, so the one-tile engine is used again after the two-tile one -- must partition it."""
+    import kd_tree
+    import mlp
+    p = mlp.initialize_params(mlp.build_spec(mlp.quick_mlp_spec(layers, act)), 3)
+    func = make(p, mode)
+    res = []
+    for legacy in ("0", "1"):
+        monkeypatch.setenv("NIQ_TREE_LEGACY", legacy)
+        st = {}
+        out = kd_tree.construct_uniform_unknown_levelset_tree(func, p, LO, HI, split_depth=depth, stats=st)
+        res.append((out, st))
+    monkeypatch.setenv("NIQ_TREE_LEGACY", "0")
+    (a, sa), (b, sb) = res
+    assert sa == sb, (sa, sb)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    v = a["unknown_node_valid"]
+    assert int(v.sum()) > 0
+    want = _canon(a["unknown_node_lower"][v], a["unknown_node_upper"][v])
+    parts = []
+    for rank in range(4):
+        t = kd_tree.build_tree_dealt(func, p, LO, HI, depth, depth - 3, rank, 4)
+        try:
+            parts.append(t.nodes(0))
+        finally:
+            t.close()
+    got = _canon(np.concatenate([x for x, _ in parts]), np.concatenate([y for _, y in parts]))
+    assert got.shape == want.shape and np.array_equal(got, want)
+
+
 def test_tree_persistent_kernel_multi_root_and_growth(monkeypatch):
     """Multi-root builds (the unit of the subtree sharding) through the cooperative kernel, and a build whose frontier
     outgrows the first buffer (relaunch from the level that did not fit): both equal the level loop."""
