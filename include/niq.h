@@ -101,6 +101,9 @@ typedef struct niq_mesh niq_mesh;   /* result of niq_marching_cubes             
 
 const char* niq_last_error(void);
 const char* niq_version(void);
+/* Host-only helper (no GPU): 128-bit content fingerprint of a byte range -- the key of the Python layer's MLP-handle
+ * cache (the reference looks `params` up afresh on every call, so handles are cached by content, never by identity). */
+int niq_fingerprint128(const void* data, int64_t nbytes, uint64_t out[2]);
 
 /* ---- context ------------------------------------------------------------------------------- */
 int niq_ctx_create(int device, niq_ctx** out);

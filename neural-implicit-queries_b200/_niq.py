@@ -30,7 +30,7 @@ SYMBOLS = (
     "niq_last_error", "niq_version", "niq_ctx_create", "niq_ctx_destroy", "niq_ctx_sync", "niq_ctx_device_info",
     "niq_ctx_launch_count", "niq_ctx_timer_start", "niq_ctx_timer_stop", "niq_ctx_kernel_ms",
     "niq_ctx_kernel_timing", "niq_ctx_exec_macs", "niq_ctx_mc_points", "niq_dev_alloc", "niq_dev_free", "niq_dev_upload", "niq_dev_download",
-    "niq_measure_fp32_peak", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
+    "niq_measure_fp32_peak", "niq_fingerprint128", "niq_mlp_create", "niq_mlp_destroy", "niq_mlp_macs", "niq_mlp_tie_rel", "niq_eval_points",
     "niq_classify_general_boxes", "niq_classify_boxes", "niq_slope_forward", "niq_cast_rays", "niq_cast_rays_frustum", "niq_tree_build", "niq_tree_build_roots", "niq_tree_build_dealt", "niq_tree_count",
     "niq_tree_copy", "niq_tree_stats", "niq_tree_level_info", "niq_tree_destroy", "niq_marching_cubes", "niq_marching_cubes_tree",
     "niq_mesh_count", "niq_mesh_copy", "niq_mesh_destroy", "niq_mc_tables", "niq_find_any_intersection",
@@ -235,34 +235,14 @@ class Context:
         return m
 
 
-_FP_WEIGHTS = None
-
-
-def _fp_weights(n):
-    """Two rows of fixed odd 64-bit multipliers (PCG64, fixed seed), grown on demand."""
-    global _FP_WEIGHTS
-    if _FP_WEIGHTS is None or _FP_WEIGHTS.shape[1] < n:
-        m = max(int(n), 1 << 12)
-        rng = np.random.Generator(np.random.PCG64(0x6E6971))
-        _FP_WEIGHTS = rng.integers(0, 2 ** 64, size=(2, m), dtype=np.uint64) | np.uint64(1)
-    return _FP_WEIGHTS
-
-
 def _fingerprint(a):
-    """128-bit position-dependent fingerprint of an array's bytes: two multiply-accumulates mod 2^64 against fixed odd
-    multipliers (universal hashing: two different contents collide with probability ~2^-64 per row).  Memory-bound NumPy,
-    ~10x a cryptographic hash -- the digest is recomputed on EVERY query call, and at 2 MB of weights blake2b over the raw
-    bytes alone cost more than a whole depth-12 tree build."""
-    b = np.ascontiguousarray(a).view(np.uint8).reshape(-1)
-    n8 = b.size // 8
-    acc = np.zeros(2, np.uint64)
-    with np.errstate(over="ignore"):
-        if n8:
-            v = b[:n8 * 8].view(np.uint64)
-            acc += (_fp_weights(n8)[:, :n8] * v).sum(axis=1, dtype=np.uint64)
-        if b.size > n8 * 8:
-            acc += np.uint64(int.from_bytes(b[n8 * 8:].tobytes(), "little")) * np.uint64(0x9E3779B97F4A7C15)
-    return acc.tobytes()
+    """128-bit content fingerprint of an array's bytes (niq_fingerprint128: one memory-bound pass in the library, host code).
+    The digest is recomputed on EVERY query call; at 2 MB of weights blake2b over the raw bytes alone cost more than a whole
+    depth-12 tree build."""
+    b = np.ascontiguousarray(a)
+    out = (C.c_uint64 * 2)()
+    check(lib().niq_fingerprint128(C.c_void_p(b.ctypes.data), C.c_int64(b.nbytes), out))
+    return bytes(out)
 
 
 def params_digest(params):

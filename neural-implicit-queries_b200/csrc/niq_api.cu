@@ -1,6 +1,8 @@
 // niq_api.cu -- the C ABI (include/niq.h): contexts, MLP packing, and the host-side drivers of the queries.
 // Build: see __graft_entry__.build (one translation unit per kernel family, linked into libniq.so).
 #define NIQ_HELPER_KERNELS
+#include <cstring>
+
 #include "niq_internal.h"
 #include "niq_cp.cuh"
 
@@ -21,6 +23,32 @@ int niq_fail(int code, const char* fmt, ...) {
 
 extern "C" const char* niq_last_error(void) { return g_last_error.c_str(); }
 extern "C" const char* niq_version(void) { return "niq-b200 0.1 (sm_100a)"; }
+
+// 128-bit fingerprint of a byte range (host code, no GPU): four interleaved lanes of xor / rotate / odd-multiply over
+// 8-byte words (every step is a bijection of the lane state, so a changed word always changes its lane), mixed down with
+// splitmix64 finalisers.  The Python layer keys its MLP-handle cache with it: the reference re-reads `params` on every
+// call, so the key must follow the CONTENT, and it is recomputed per query call -- one memory-bound pass over the weights.
+extern "C" int niq_fingerprint128(const void* data, int64_t nbytes, uint64_t out[2]) {
+    if ((!data && nbytes > 0) || nbytes < 0 || !out) return fail(NIQ_EINVAL, "niq_fingerprint128: bad argument");
+    static const uint64_t K[4] = {0x9E3779B97F4A7C15ull, 0xC2B2AE3D27D4EB4Full, 0x165667B19E3779F9ull, 0xD6E8FEB86659FD93ull};
+    uint64_t s[4] = {0x243F6A8885A308D3ull ^ (uint64_t)nbytes, 0x13198A2E03707344ull, 0xA4093822299F31D0ull, 0x082EFA98EC4E6C89ull};
+    const unsigned char* p = static_cast<const unsigned char*>(data);
+    int64_t i = 0;
+    for (; i + 32 <= nbytes; i += 32) {
+        uint64_t x[4];
+        memcpy(x, p + i, 32);
+        for (int l = 0; l < 4; ++l) { const uint64_t v = s[l] ^ x[l]; s[l] = ((v << 29) | (v >> 35)) * K[l]; }
+    }
+    if (i < nbytes) {                                   // tail: zero-padded block (the length is part of the seed)
+        uint64_t x[4] = {0, 0, 0, 0};
+        memcpy(x, p + i, (size_t)(nbytes - i));
+        for (int l = 0; l < 4; ++l) { const uint64_t v = s[l] ^ x[l]; s[l] = ((v << 29) | (v >> 35)) * K[l]; }
+    }
+    auto mix = [](uint64_t z) { z ^= z >> 30; z *= 0xBF58476D1CE4E5B9ull; z ^= z >> 27; z *= 0x94D049BB133111EBull; return z ^ (z >> 31); };
+    out[0] = mix(s[0] + mix(s[1] + mix(s[2] + mix(s[3]))));
+    out[1] = mix(s[3] ^ mix(s[2] ^ mix(s[1] ^ mix(s[0] + 0x9E3779B97F4A7C15ull))));
+    return NIQ_OK;
+}
 
 // ------------------------------------------------------------------------------------------------
 // context
