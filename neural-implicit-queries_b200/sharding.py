@@ -234,7 +234,9 @@ def _build_own_tree(func, params, lower, upper, split_depth, top_depth, rank, wo
     return kd_tree.build_tree(func, params, flo[mine], fhi[mine], split_depth=split_depth - top_depth, **tkw)
 
 
-_GATHER_CAP = {}      # (split_depth, top_depth, world) -> rows per rank of the last gather: the next one needs no count exchange
+# (split_depth, top_depth, world) -> rows per rank of the last gather: the next one needs no count exchange.  Like every collective
+# call this relies on all ranks making the SAME sequence of tree_sharded calls (SPMD): the entry then exists on all ranks or on none.
+_GATHER_CAP = {}
 
 
 def _tree_sharded_device(func, params, lower, upper, split_depth, top_depth, rank, world, group, kw, to_host=True):
