@@ -149,3 +149,19 @@ def test_deal_boxes_is_a_partition_and_mixes_the_low_bits():
     mine = sharding.deal_boxes(4096, 3, 8)
     hist = np.bincount(mine % 8, minlength=8)
     assert hist.min() == hist.max() == 64                                       # all eight "octants" equally
+
+
+def test_replay_n_evals_over_the_cast_rays_only():
+    """sharding.replay_n_evals(count, opts, n_zero): listing only the rays that were cast and COUNTING the pixels nobody cast
+    gives the reference's N_evals of the whole image (src/queries.py:137,164-173); the sharded ray call of a sub-sampled
+    image relies on it."""
+    import queries
+    import sharding
+    rng = np.random.default_rng(5)
+    for n, n_cast, n_sub in ((100000, 7000, 1), (5000, 5000, 1), (40000, 123, 3), (129, 1, 1)):
+        opts = dict(queries.get_default_cast_opts(), n_substeps=n_sub)
+        count = np.zeros(n, np.int32)
+        idx = rng.choice(n, n_cast, replace=False)
+        count[idx] = rng.integers(1, int(opts["n_max_step"]) + 1, n_cast)
+        full = sharding.replay_n_evals(count, opts)
+        assert full == sharding.replay_n_evals(count[idx], opts, n_zero=n - n_cast)
